@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Wigner-3j hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (reference-shaped oracle)
+
+A *step* is one pass of the hot path over the BASELINE workload at lmax = 6143:
+TT MCM + fused M++/M-- (EE/BB) MCM from two distinct masks, and the TTTT / EEEE / TETE coupled
+covariance blocks (4 masks, product-mask window spectra).  Work unit = one 3j term, counted
+over the FULL families exactly as the reference evaluates them:
+7 reference families x T_fam(6143) = 5.41e11 terms per step.
+
+Under torchrun (N > 1) the l1 rows are split into N work-balanced bands, every rank computes
+its band, slabs are gathered to rank 0 with NCCL send/recv, rank 0 fills both triangles.
+Total work is fixed => strong scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "3j_terms_per_s (TT+EE/BB MCM and TTTT/EEEE/TETE coupledcov, lmax=6143)"
+UNIT = "terms/s"
+NOMINAL_FP64_TFLOPS = 37.2        # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
+
+# job name -> (api, code, reference families, [(families fed, n_acc)] for the declared flop model
+#              F = 20 + 2 n_acc per term)
+JOBS = [
+    ("M00", "mcm", 0, 1, [(1, 1)]),
+    ("Mpp_Mmm", "mcm", 4, 2, [(2, 1)]),
+    ("TTTT", "cov", 0, 1, [(1, 8)]),
+    ("EEEE", "cov", 1, 1, [(1, 8)]),
+    ("TETE", "cov", 3, 2, [(1, 4), (1, 1)]),
+]
+
+
+def job_flops_per_tfam(job):
+    return sum(f * (20 + 2 * n) for f, n in job[4])
+
+
+def t_fam(lmax, lo=0, hi=None):
+    hi = lmax + 1 if hi is None else hi
+    l = np.arange(lo, hi, dtype=np.int64)
+    return int(np.sum((2 * l + 1) * (lmax - l + 1)))
+
+
+# ------------------------------------------------------------------------------------------
+# inputs (host, numpy) -- synthetic zonal apodised masks, analytic spectra
+# ------------------------------------------------------------------------------------------
+def make_inputs(lmax):
+    import powerspectra_jl_b200 as ps
+    from powerspectra_jl_b200 import synthetic as syn
+    V = syn.mask_spectra(lmax, seeds=(1001, 1002))
+    ws, sp, rt = syn.covariance_inputs(lmax)
+    i, j, p, q = ws.field_names
+    N_ = ps.covariance.NULL
+    W = lambda *k: ps.window_function_W(ws, *k).parent
+    inp = {
+        "M00": dict(V=V[(0, 1)]),
+        "Mpp_Mmm": dict(V=V[(1, 1)]),
+        "TTTT": dict(
+            sp=[sp["TT", i, p].parent, sp["TT", j, q].parent, sp["TT", i, q].parent, sp["TT", j, p].parent],
+            rt=[rt["TT", i, p].parent, rt["TT", j, q].parent, rt["TT", i, q].parent, rt["TT", j, p].parent],
+            W=[W(N_, N_, i, p, "TT", j, q, "TT"), W(N_, N_, i, q, "TT", j, p, "TT"),
+               W(N_, "TT", i, p, "TT", j, q, "TT"), W(N_, "TT", j, q, "TT", i, p, "TT"),
+               W(N_, "TT", i, q, "TT", j, p, "TT"), W(N_, "TT", j, p, "TT", i, q, "TT"),
+               W("TT", "TT", i, p, "TT", j, q, "TT"), W("TT", "TT", i, q, "TT", j, p, "TT")]),
+        "EEEE": dict(
+            sp=[sp["EE", i, p].parent, sp["EE", j, q].parent, sp["EE", i, q].parent, sp["EE", j, p].parent],
+            rt=[rt["EE", i, p].parent, rt["EE", j, q].parent, rt["EE", i, q].parent, rt["EE", j, p].parent],
+            W=[W(N_, N_, i, p, "PP", j, q, "PP"), W(N_, N_, i, q, "PP", j, p, "PP"),
+               W(N_, "PP", i, p, "PP", j, q, "PP"), W(N_, "PP", j, q, "PP", i, p, "PP"),
+               W(N_, "PP", i, q, "PP", j, p, "PP"), W(N_, "PP", j, p, "PP", i, q, "PP"),
+               W("PP", "PP", i, p, "PP", j, q, "PP"), W("PP", "PP", i, q, "PP", j, p, "PP")]),
+        "TETE": dict(
+            sp=[sp["TT", i, p].parent, sp["EE", j, q].parent, sp["TE", i, q].parent, sp["TE", j, p].parent],
+            rt=[rt["TT", i, p].parent, rt["EE", j, q].parent],
+            W=[W(N_, N_, i, p, "TT", j, q, "PP"), W(N_, N_, i, q, "TP", j, p, "PT"),
+               W(N_, "PP", i, p, "TT", j, q, "PP"), W(N_, "TT", j, q, "PP", i, p, "TT"),
+               W("TT", "PP", i, p, "TT", j, q, "PP")]),
+    }
+    return inp
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference-shaped oracle (C/OpenMP restatement; Julia is not installed anywhere)
+# ------------------------------------------------------------------------------------------
+def cpu_sample(inp, lmax, rstep, threads=None):
+    """One bounded sample of the step on the CPU: rows l1 = rstep//2, +rstep, ... of every job.
+    Returns (terms evaluated, seconds)."""
+    from oracle import psoracle as po
+    row0 = rstep // 2
+    t0 = time.perf_counter()
+    terms = 0
+    for name, api, code, fam, _ in JOBS:
+        a = inp[name]
+        if api == "mcm":
+            if code == 4:      # the reference evaluates the (0,-2,2) family once per block
+                for k in (2, 3):
+                    _, t = po.mcm(k, 0, lmax, a["V"], row0=row0, rstep=rstep, threads=threads, return_terms=True)
+                    terms += t
+            else:
+                _, t = po.mcm(code, 0, lmax, a["V"], row0=row0, rstep=rstep, threads=threads, return_terms=True)
+                terms += t
+        else:
+            _, t = po.cov(code, 0, lmax, a["sp"], a["rt"], a["W"], row0=row0, rstep=rstep, threads=threads,
+                          return_terms=True)
+            terms += t
+    return terms, time.perf_counter() - t0
+
+
+def pick_rstep(inp, lmax, target_s):
+    """Probe with a sparse sample, then choose the row stride so one sample costs ~target_s."""
+    probe = 1024 if lmax >= 4096 else 64
+    terms, dt = cpu_sample(inp, lmax, probe)
+    rate = terms / dt
+    full_terms = sum(j[3] for j in JOBS) * t_fam(lmax)
+    want = max(1, int(round(full_terms / (rate * target_s))))
+    return max(4, want), rate
+
+
+def run_reference(args, lmax):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import psoracle as po
+    po.build()
+    inp = make_inputs(lmax)
+    cores = po.max_threads()
+    rstep, _ = pick_rstep(inp, lmax, target_s=max(4.0, min(20.0, 150.0 / (args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        cpu_sample(inp, lmax, rstep)
+    tt, tn = 0.0, 0
+    for _ in range(args.steps):
+        n, dt = cpu_sample(inp, lmax, rstep)
+        tt += dt
+        tn += n
+    value = tn / tt
+    full_terms = sum(j[3] for j in JOBS) * t_fam(lmax)
+    sample = f"every {rstep}th l1 row (from row {rstep // 2}) of each of the 5 calls, {tn // args.steps:.3e} terms per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * full_terms / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"lmax={lmax}: MCM TT + EE/BB(M++,M--), coupledcov TTTT+EEEE+TETE",
+                   "note": "C/OpenMP restatement of the reference CPU path (oracle/psoracle.c), not Julia; "
+                           "ms_per_step is the full-step time extrapolated from the row sample by exact term count"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+def run_gpu(args, lmax):
+    import torch
+    import torch.distributed as dist
+
+    import powerspectra_jl_b200 as ps
+    from powerspectra_jl_b200 import device as dev
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    N = lmax + 1
+    inp = make_inputs(lmax)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = {k: {kk: (pin(v) if isinstance(v, np.ndarray) else [pin(x) for x in v]) for kk, v in d.items()}
+            for k, d in inp.items()}
+    to_dev = lambda d: {kk: (v.cuda(non_blocking=True) if torch.is_tensor(v) else [x.cuda(non_blocking=True) for x in v])
+                        for kk, v in d.items()}
+    edges = dev.band_edges(0, lmax, world)
+    lo, hi = edges[rank], edges[rank + 1]
+
+    # output buffers: full matrix on every rank (N^2 x 8 B = 302 MB each at lmax 6143)
+    outs = {}
+    for name, api, code, fam, _ in JOBS:
+        outs[name] = [torch.empty((N, N), dtype=torch.float64, device="cuda") for _ in range(2 if code == 4 and api == "mcm" else 1)]
+    h2d_bytes = sum(v.numel() * 8 if torch.is_tensor(v) else sum(x.numel() * 8 for x in v)
+                    for d in host.values() for v in d.values())
+    d2h_bytes = sum(len(v) for v in outs.values()) * N * N * 8
+    host_out = None
+    launches = {"n": 0}
+    kernel_events = []          # (job name, start, end) of the pair kernels of the timed steps
+
+    def compute(dinp, record):
+        for name, api, code, fam, _ in JOBS:
+            a = dinp[name]
+            X = outs[name]
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if api == "mcm":
+                dev.mcm_slab(code, 0, lmax, a["V"], X[0], X[1] if len(X) > 1 else None, lo, hi)
+            else:
+                dev.cov_slab(code, 0, lmax, a["sp"], a["rt"], a["W"], X[0], lo, hi)
+            launches["n"] += 1
+            if record:
+                e1.record()
+                kernel_events.append((name, e0, e1))
+        for name, api, code, fam, _ in JOBS:
+            for X in outs[name]:
+                dev.gather_bands(X, edges, 0, rank, world)
+                if rank == 0:
+                    dev.finish(X, 0, lmax, api == "mcm")
+                    launches["n"] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- kernel-resident measurement: inputs already in HBM ----
+    dinp = {k: to_dev(d) for k, d in host.items()}
+    for _ in range(args.warmup):
+        compute(dinp, False)
+    launches["n"] = 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(lambda: compute(dinp, True), args.steps)
+    n_launch = launches["n"]
+    clocks = sampler.stop() if sampler else None
+    torch.cuda.synchronize()
+    per_job = {}
+    for name, e0, e1 in kernel_events:
+        per_job.setdefault(name, []).append(e0.elapsed_time(e1))
+
+    # ---- end to end: host buffers in, host buffers out, through the public entry points ----
+    if world == 1:
+        # the C-ABI host-level calls (what the Julia shim ccalls): pageable numpy in, pinned host out
+        L = ps.lib()
+        DP = ps._lib.DP
+        host_out = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in v] for name, v in outs.items()}
+
+        def ptrs(arrs):
+            return (DP * max(len(arrs), 1))(*[a.ctypes.data_as(DP) for a in arrs])
+
+        def e2e_step():
+            for name, api, code, fam, _ in JOBS:
+                a = inp[name]
+                O = host_out[name]
+                if api == "mcm":
+                    rc = L.psb200_mcm(code, 0, lmax, a["V"].ctypes.data_as(DP), a["V"].size, O[0].ctypes.data_as(DP), N,
+                                      O[1].ctypes.data_as(DP) if len(O) > 1 else None, 1)
+                else:
+                    rc = L.psb200_cov(code, 0, lmax, ptrs(a["sp"]), len(a["sp"]), ptrs(a["rt"]), len(a["rt"]),
+                                      ptrs(a["W"]), len(a["W"]), a["W"][0].size, O[0].ctypes.data_as(DP), N, 1)
+                ps._lib.check(rc)
+    else:
+        host_out0 = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory() for _ in v] for name, v in outs.items()} if rank == 0 else None
+
+        def e2e_step():
+            d = {k: to_dev(dd) for k, dd in host.items()}
+            compute(d, False)
+            if rank == 0:
+                for name in outs:
+                    for X, H in zip(outs[name], host_out0[name]):
+                        H.copy_(X, non_blocking=True)
+
+    e2e_step()                                   # warm-up (allocations inside the library)
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e_ev = timed(e2e_step, e2e_steps)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e_ev, 0.0)
+    if world == 1:
+        ms_e2e = wall_e2e                        # blocking host calls: wall clock brackets the whole call
+
+    if rank == 0:
+        terms_step = sum(j[3] for j in JOBS) * t_fam(lmax)
+        ms_step = ms_total / args.steps
+        value = terms_step / (ms_step * 1e-3)
+        e2e_value = terms_step / (ms_e2e / e2e_steps * 1e-3)
+        # dominant kernel + roofline (FP64 pipe): declared flops of this rank's band / mean launch time
+        mean_ms = {k: float(np.mean(v)) for k, v in per_job.items()}
+        dom = max(mean_ms, key=mean_ms.get)
+        dj = [j for j in JOBS if j[0] == dom][0]
+        band_tfam = t_fam(lmax, lo, hi)
+        flops = job_flops_per_tfam(dj) * band_tfam
+        achieved = flops / (mean_ms[dom] * 1e-3) / 1e12
+        peak = dev.dfma_peak(1 << 14) / 1e12
+        all_flops = sum(job_flops_per_tfam(j) for j in JOBS) * band_tfam
+        all_kernel_ms = sum(mean_ms.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"lmax={lmax}: MCM TT + EE/BB(M++,M--), coupledcov TTTT+EEEE+TETE "
+                                   f"(7 reference families x T_fam={t_fam(lmax):.4e} terms per step)",
+                       "parallelism": f"l1 row bands x{world}, NCCL gather to rank 0" if world > 1 else "1 GPU",
+                       "l2": "outputs (6 x N^2 x 8 B = 1.8 GB per step) exceed L2; inputs are O(lmax) vectors",
+                       "kernel": os.environ.get("PSB200_KERNEL", "default")},
+            "gpu_launches": n_launch,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / e2e_steps,
+                    "path": "psb200_mcm / psb200_cov C-ABI host calls (pinned host outputs)" if world == 1
+                            else "pinned host -> H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0"},
+            "roofline": {"bound": "fp64", "kernel": f"pair kernel of job {dom}", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": "psb200_dfma_peak DFMA microbenchmark measured in this run "
+                                        f"(MEASURED_PEAKS.json has no FP64 entry; nominal {NOMINAL_FP64_TFLOPS})",
+                         "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+                         "flops_model": "F = 20 + 2 n_acc declared flops per 3j term over full families (SURVEY.md 8d)",
+                         "traffic": None,
+                         "all_kernels": {"declared_tflops": all_flops / (all_kernel_ms * 1e-3) / 1e12,
+                                         "ms": mean_ms}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import psoracle as po
+            po.build()
+            rstep, _ = pick_rstep(inp, lmax, target_s=15.0)
+            n, dt = cpu_sample(inp, lmax, rstep)
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": po.max_threads(), "kind": "port",
+                                    "sample": f"every {rstep}th l1 row of each of the 5 calls ({n:.3e} terms, {dt:.1f} s); "
+                                              "C/OpenMP restatement of the reference CPU path, not Julia"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lmax", type=int, default=6143)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args, args.lmax)
+    else:
+        run_gpu(args, args.lmax)
+
+
+if __name__ == "__main__":
+    main()

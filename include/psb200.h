@@ -1,0 +1,128 @@
+/*
+ * psb200.h -- C ABI of libpsb200.so, the B200 (sm_100a) replacement for the
+ * Wigner-3j hot path of PowerSpectra.jl.
+ *
+ * The reference has no FFI seam of its own (pure Julia).  The seam this library
+ * fills is the set of Julia inner-loop methods that `mcm` and `coupledcov` call;
+ * a Julia shim overrides exactly those with `ccall`s:
+ *
+ *   psb200_mcm  replaces  inner_mcm00!   /root/reference/src/modecoupling.jl:78-95
+ *                         inner_mcm02!   src/modecoupling.jl:99-119
+ *                         inner_mcm++!   src/modecoupling.jl:123-139
+ *                         inner_mcm--!   src/modecoupling.jl:143-159
+ *                         (+ fill_3j! :69-75, Xi_TT/EE/EB/TE :3-66, and the
+ *                          WignerFamilies.jl calls WignerF / wigner3j_f! they make)
+ *   psb200_cov  replaces  loop_covTTTT!        src/covariance.jl:92-122
+ *                         loop_covEEEE!        src/covariance.jl:153-183
+ *                         loop_covTTTE!        src/covariance.jl:208-235
+ *                         loop_covTETE!        src/covariance.jl:261-302
+ *                         loop_covTEEE_planck! src/covariance.jl:376-402
+ *                         loop_covTEEE!        src/covariance.jl:337-372
+ *                         loop_covTTEE!        src/covariance.jl:422-446
+ *
+ * Conventions
+ *   - Every `double*` of the host-level calls is caller-owned HOST memory, alive for
+ *     the duration of the (blocking) call; nothing is retained after return.
+ *   - Vectors are 0-based in l: x[l], l = 0..len-1 (a Julia SpectralVector over 0:len-1).
+ *   - Matrices are column-major with leading dimension ld >= N, N = lmax-lmin+1:
+ *     element (l1,l2) lives at A[(l1-lmin) + (l2-lmin)*ld]   (= parent(SpectralArray)).
+ *     Both triangles are written:  M[l1,l2] = (2 l2+1) Xi, M[l2,l1] = (2 l1+1) Xi
+ *     (src/modecoupling.jl:90-91);  C[l2,l1] = C[l1,l2]  (src/covariance.jl:119).
+ *   - The l3 sum runs over [|l1-l2|, min(l1+l2, len-1)] of the window vector
+ *     (src/modecoupling.jl:6-8); lmin only crops rows/columns.
+ *   - Return value: 0 ok; 1 bad argument (maps to ArgumentError / the @assert at
+ *     src/modecoupling.jl:80,225); 2 CUDA error; 3 collective error; 4 out of memory;
+ *     5 no usable CUDA device.  psb200_last_error() gives the message.  There is
+ *     NO CPU fallback: without a B200-class device every compute call fails with 5.
+ *   - Thread safety: calls may come from any OS thread; they are serialised inside.
+ */
+#ifndef PSB200_H
+#define PSB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* psb200_mcm kinds */
+enum {
+    PSB200_M00 = 0,      /* :TT, :M00                         inner_mcm00! */
+    PSB200_M02 = 1,      /* :TE :ET :TB :BT :M02 :M20         inner_mcm02! */
+    PSB200_MPP = 2,      /* :M++                              inner_mcm++! */
+    PSB200_MMM = 3,      /* :M--                              inner_mcm--! */
+    PSB200_MPP_MMM = 4   /* both from ONE evaluation of the (0,-2,2) family: M -> M++, M2 -> M-- */
+};
+
+/* psb200_cov blocks (positional order of spectra / ratios / W = the reference signatures) */
+enum {
+    PSB200_TTTT = 0,        /* sp TTip TTjq TTiq TTjp | r ip jq iq jp | W1..W8 */
+    PSB200_EEEE = 1,        /* sp EEip EEjq EEiq EEjp | r ip jq iq jp | W1..W8 */
+    PSB200_TTTE = 2,        /* sp TTip TTjp TEiq TEjq | r ip jp       | W1..W4 */
+    PSB200_TETE = 3,        /* sp TTip EEjq TEiq TEjp | r TTip PPjq   | W1..W5 */
+    PSB200_TEEE_PLANCK = 4, /* sp EEjq EEjp TEip TEiq | r EEjq EEjp   | W1..W4 */
+    PSB200_TEEE = 5,        /* same arguments, f00*f22 instead of f22^2 */
+    PSB200_TTEE = 6         /* sp TEip TEiq TEjq TEjp | (no ratios)   | W1 W2  */
+};
+
+/* ---- host-level entry points (what the Julia shim ccalls) ------------------------- */
+
+/* Mode-coupling matrix.  V[0..nV-1] = mask cross-spectrum (reference passes nV = lmax+1,
+ * src/modecoupling.jl:197).  M is fully overwritten; M2 only for kind 4 (else NULL).
+ * ngpus: 1, 2, 4, 8 ... row bands across that many devices of this box; 0 = all visible. */
+int psb200_mcm(int kind, int lmin, int lmax, const double* V, int nV,
+               double* M, long ldM, double* M2, int ngpus);
+
+/* Coupled covariance block.  spectra[k], ratios[k]: length >= lmax+1; W[k]: length lenW
+ * (reference: workspace.lmax+1, src/workspace.jl:197).  nspec/nratio/nW must equal the
+ * block's arity: TTTT/EEEE 4/4/8, TTTE 4/2/4, TETE 4/2/5, TEEE* 4/2/4, TTEE 4/0/2. */
+int psb200_cov(int block, int lmin, int lmax,
+               const double* const* spectra, int nspec,
+               const double* const* ratios, int nratio,
+               const double* const* W, int nW, int lenW,
+               double* C, long ldC, int ngpus);
+
+const char* psb200_last_error(void);   /* message of the last non-zero return on this thread */
+int psb200_device_count(void);         /* CUDA devices visible to the library (0 if none) */
+const char* psb200_version(void);
+
+/* ---- device-level entry points ------------------------------------------------------
+ * Same computations on buffers already resident in HBM of the CURRENT device; used by the
+ * one-process-per-GPU driver (bench.py under torchrun) and by the kernel-only timings.
+ * All pointers are DEVICE pointers; `stream` is a cudaStream_t (NULL = default stream).
+ * Calls are asynchronous with respect to the host.
+ *
+ * Stage 1 writes raw Xi for the rows l1 in [row_lo, row_hi) (absolute l, lmin <= row_lo):
+ *     X[(l1-lmin)*ldX + (l2-lmin)],  l2 = l1..lmax      (other entries untouched)
+ * i.e. row l1 of the upper triangle is contiguous -- it is column l1 of the final
+ * column-major matrix, so a band of rows is ONE contiguous slab that can be sent to
+ * rank 0 as is.  For MCM kinds X holds Xi; for covariance blocks X holds C[l1,l2].
+ * Stage 2 (psb200_finish_dev, on the rank that owns the whole matrix) fills both
+ * triangles in place: scale = 1 applies the (2l+1) factors of the MCM, scale = 0 copies.
+ */
+int psb200_mcm_dev(int kind, int lmin, int lmax, const double* dV, int nV,
+                   double* dX, long ldX, double* dX2,
+                   int row_lo, int row_hi, void* stream);
+
+int psb200_cov_dev(int block, int lmin, int lmax,
+                   const double* const* d_spectra, int nspec,   /* host array of device ptrs */
+                   const double* const* d_ratios, int nratio,
+                   const double* const* d_W, int nW, int lenW,
+                   double* dX, long ldX,
+                   int row_lo, int row_hi, void* stream);
+
+int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void* stream);
+
+/* Work-balanced contiguous l1 bands: edges[0..nbands] with edges[0] = lmin,
+ * edges[nbands] = lmax+1, equalising sum (2 l1+1)(lmax-l1+1) (the 3j terms of a row). */
+int psb200_band_edges(int lmin, int lmax, int nbands, int* edges);
+
+/* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
+long long psb200_terms(int families, int lmax, int row_lo, int row_hi);
+
+/* FP64 pipe microbenchmark: dependent-free DFMA streams on every SM for `iters` iterations;
+ * returns achieved FLOP/s (2 per DFMA) on the current device, <0 on error. */
+double psb200_dfma_peak(int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB200_H */

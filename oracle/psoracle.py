@@ -1,0 +1,125 @@
+"""ctypes front-end of the CPU oracle (oracle/psoracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the CPU
+arm of bench.py; never by the product package.  See oracle/psoracle_impl.h for the
+reference file:line map of every function.
+
+All matrices are returned as numpy arrays A[l1 - lmin, l2 - lmin] (the memory handed
+to C is column-major like a Julia `parent(SpectralArray)`; the results are symmetric
+up to the (2l+1) factors so the layout is made explicit with order="F").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libpsoracle.so")
+
+MCM_KINDS = {"M00": 0, "M02": 1, "Mpp": 2, "Mmm": 3}
+COV_BLOCKS = {"TTTT": 0, "EEEE": 1, "TTTE": 2, "TETE": 3, "TEEE_planck": 4, "TEEE": 5, "TTEE": 6}
+COV_NEED = {  # block -> (n spectra, n ratios, n W)
+    0: (4, 4, 8), 1: (4, 4, 8), 2: (4, 2, 4), 3: (4, 2, 5), 4: (4, 2, 4), 5: (4, 2, 4), 6: (4, 0, 2),
+}
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc -O3 -fopenmp)."""
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("psoracle.c", "psoracle_impl.h", "Makefile"))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_m:
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        dpp = C.POINTER(dp)
+        ip = C.POINTER(C.c_int)
+        for suf in ("", "_ld"):
+            f = getattr(L, "pso_mcm" + suf)
+            f.restype = C.c_longlong
+            f.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, C.c_long, C.c_int, C.c_int]
+            f = getattr(L, "pso_cov" + suf)
+            f.restype = C.c_longlong
+            f.argtypes = [C.c_int, C.c_int, C.c_int, dpp, C.c_int, dpp, C.c_int, dpp, C.c_int, C.c_int,
+                          dp, C.c_long, C.c_int, C.c_int]
+            f = getattr(L, "pso_w3j_family" + suf)
+            f.restype = C.c_int
+            f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, ip, ip]
+        L.pso_max_threads.restype = C.c_int
+        L.pso_set_threads.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _vecs(vs):
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in vs]
+    ptrs = (C.POINTER(C.c_double) * max(len(arrs), 1))(*[_dp(a) for a in arrs])
+    return arrs, ptrs
+
+
+def w3j_family(l1, l2, m2, m3, ld=False):
+    """f(j) = (j l1 l2; -m2-m3 m2 m3), j = nmin..nmax.  Returns (nmin, values)."""
+    n = 2 * min(l1, l2) + 1
+    out = np.zeros(max(n, 1))
+    nmin, nmax = C.c_int(), C.c_int()
+    f = lib().pso_w3j_family_ld if ld else lib().pso_w3j_family
+    k = f(l1, l2, m2, m3, _dp(out), out.size, C.byref(nmin), C.byref(nmax))
+    if k < 0:
+        raise ValueError("w3j_family: buffer too small")
+    return nmin.value, out[:k].copy()
+
+
+def mcm(kind, lmin, lmax, V, ld=False, row0=0, rstep=1, threads=None, return_terms=False):
+    """inner_mcm00!/02!/++!/--! (src/modecoupling.jl:78-159).  kind: 0..3 or a name."""
+    kind = MCM_KINDS.get(kind, kind)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    N = lmax - lmin + 1
+    M = np.zeros((N, N), order="F")
+    if threads:
+        lib().pso_set_threads(int(threads))
+    f = lib().pso_mcm_ld if ld else lib().pso_mcm
+    t = f(kind, lmin, lmax, _dp(V), V.size, _dp(M), N, row0, rstep)
+    if t < 0:
+        raise ValueError("oracle mcm: bad arguments")
+    return (M, t) if return_terms else M
+
+
+def cov(block, lmin, lmax, spectra, ratios, W, ld=False, row0=0, rstep=1, threads=None, return_terms=False):
+    """loop_cov*! (src/covariance.jl:92-446); positional order of the reference."""
+    block = COV_BLOCKS.get(block, block)
+    sa, sp = _vecs(spectra)
+    ra, rp = _vecs(ratios)
+    wa, wp = _vecs(W)
+    lenW = min(w.size for w in wa)
+    for a in sa + ra:
+        if a.size < lmax + 1:
+            raise ValueError("spectrum / ratio shorter than lmax+1")
+    N = lmax - lmin + 1
+    Cm = np.zeros((N, N), order="F")
+    if threads:
+        lib().pso_set_threads(int(threads))
+    f = lib().pso_cov_ld if ld else lib().pso_cov
+    t = f(block, lmin, lmax, sp, len(sa), rp, len(ra), wp, len(wa), lenW, _dp(Cm), N, row0, rstep)
+    if t < 0:
+        raise ValueError("oracle cov: bad arguments")
+    return (Cm, t) if return_terms else Cm
+
+
+def max_threads() -> int:
+    return lib().pso_max_threads()

@@ -1,0 +1,74 @@
+"""ctypes binding of libpsb200.so (include/psb200.h).
+
+The library is the product; this module only loads it and declares the prototypes.
+There is no fallback of any kind: if the shared object is missing, or no CUDA device
+is visible at call time, the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsb200.so")
+
+DP = C.POINTER(C.c_double)
+DPP = C.POINTER(DP)
+
+# symbol -> (restype, argtypes); must list every function include/psb200.h declares
+PROTOTYPES = {
+    "psb200_mcm": (C.c_int, [C.c_int, C.c_int, C.c_int, DP, C.c_int, DP, C.c_long, DP, C.c_int]),
+    "psb200_cov": (C.c_int, [C.c_int, C.c_int, C.c_int, DPP, C.c_int, DPP, C.c_int, DPP, C.c_int, C.c_int,
+                             DP, C.c_long, C.c_int]),
+    "psb200_last_error": (C.c_char_p, []),
+    "psb200_device_count": (C.c_int, []),
+    "psb200_version": (C.c_char_p, []),
+    "psb200_mcm_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_long,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "psb200_cov_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                 C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                 C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
+    "psb200_finish_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "psb200_band_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "psb200_terms": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "psb200_dfma_peak": (C.c_double, [C.c_int]),
+}
+
+
+class PSB200Error(RuntimeError):
+    """Non-zero return of a libpsb200 call (codes 2..5 of include/psb200.h)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpsb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libpsb200.so (built in-tree by csrc/build.sh / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with powerspectra.jl_b200/csrc/build.sh "
+                "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    """Map a return code to the reference's error behaviour: 1 -> ValueError (the Python
+    counterpart of Julia's ArgumentError / failed @assert, src/modecoupling.jl:80,225)."""
+    if rc == 0:
+        return
+    msg = lib().psb200_last_error().decode("utf-8", "replace")
+    if rc == 1:
+        raise ValueError(msg)
+    raise PSB200Error(rc, msg)

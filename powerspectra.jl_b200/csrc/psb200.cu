@@ -1,0 +1,462 @@
+// psb200.cu -- C ABI (include/psb200.h) + host plumbing of libpsb200.so.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU path in this file: every compute entry point launches CUDA kernels and
+// fails with PSB200_ERR_NODEVICE when no device is present.
+#include "../../include/psb200.h"
+#include "psb200_common.cuh"
+#include "psb200_pair_v1.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+enum { OK = 0, ERR_ARG = 1, ERR_CUDA = 2, ERR_COLL = 3, ERR_OOM = 4, ERR_NODEVICE = 5 };
+
+thread_local std::string g_err;
+std::mutex g_mutex;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(e_ == cudaErrorMemoryAllocation ? ERR_OOM : ERR_CUDA, "%s: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+    } while (0)
+
+int device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// finish kernel: X holds, for l1 <= l2, x = X[(l1-lmin)*ld + (l2-lmin)] (row l1 of the upper
+// triangle contiguous = column l1 of the column-major result).  Writes, in place,
+//   A[l2,l1] (same address)            = scale ? (2 l1+1) x : x
+//   A[l1,l2] (address l1 + l2*ld)      = scale ? (2 l2+1) x : x
+// 32x32 tiles through shared memory so both sides are coalesced.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finish_kernel(double* __restrict__ X, long ld, int lmin, int N, int scale)
+{
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;      // tile row (l1) and tile column (l2)
+    if (bi > bj) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;          // i = l1-lmin, j = l2-lmin
+        double v = 0.0;
+        if (i < N && j < N && i <= j) v = X[(long)i * ld + j];
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    // lower-triangle side: same addresses, factor (2 l1 + 1)
+    if (scale) {
+        for (int r = ty; r < 32; r += 8) {
+            const int i = bi * 32 + r, j = bj * 32 + tx;
+            if (i < N && j < N && i <= j) X[(long)i * ld + j] = (double)(2 * (i + lmin) + 1) * tile[r][tx];
+        }
+    }
+    // upper-triangle side: transposed addresses, factor (2 l2 + 1); skip the diagonal (done above)
+    for (int r = ty; r < 32; r += 8) {
+        const int j = bj * 32 + r, i = bi * 32 + tx;          // write A[i, j] at i + j*ld, contiguous in i
+        if (i < N && j < N && i < j) {
+            const double v = tile[tx][r];
+            X[(long)j * ld + i] = scale ? (double)(2 * (j + lmin) + 1) * v : v;
+        }
+    }
+}
+
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch of one job on the current device
+// ---------------------------------------------------------------------------------------
+int kernel_version()
+{
+    static int v = [] {
+        const char* e = getenv("PSB200_KERNEL");
+        if (e && strcmp(e, "v2") == 0) return 2;
+        return 1;
+    }();
+    return v;
+}
+
+template <int JOB>
+int launch_job(const psb::PairArgs& A, cudaStream_t st)
+{
+    const int rows = A.row_hi - A.row_lo;
+    if (rows <= 0) return OK;
+    if (kernel_version() == 1) {
+        const int maxcols = A.lmax - A.row_lo + 1;
+        dim3 grid((maxcols + psb::V1_THREADS - 1) / psb::V1_THREADS, rows);
+        psb::pair_kernel_v1<JOB><<<grid, psb::V1_THREADS, 0, st>>>(A);
+    } else {
+        return fail(ERR_ARG, "kernel v2 not built");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return OK;
+}
+
+int launch_any(int job, const psb::PairArgs& A, cudaStream_t st)
+{
+    using namespace psb;
+    switch (job) {
+        case JOB_M00: return launch_job<JOB_M00>(A, st);
+        case JOB_M02: return launch_job<JOB_M02>(A, st);
+        case JOB_MPP: return launch_job<JOB_MPP>(A, st);
+        case JOB_MMM: return launch_job<JOB_MMM>(A, st);
+        case JOB_MPPMMM: return launch_job<JOB_MPPMMM>(A, st);
+        case JOB_TTTT: return launch_job<JOB_TTTT>(A, st);
+        case JOB_EEEE: return launch_job<JOB_EEEE>(A, st);
+        case JOB_TTTE: return launch_job<JOB_TTTE>(A, st);
+        case JOB_TETE: return launch_job<JOB_TETE>(A, st);
+        case JOB_TEEEP: return launch_job<JOB_TEEEP>(A, st);
+        case JOB_TEEE: return launch_job<JOB_TEEE>(A, st);
+        case JOB_TTEE: return launch_job<JOB_TTEE>(A, st);
+    }
+    return fail(ERR_ARG, "unknown job %d", job);
+}
+
+const int kMcmJob[5] = {psb::JOB_M00, psb::JOB_M02, psb::JOB_MPP, psb::JOB_MMM, psb::JOB_MPPMMM};
+const int kCovJob[7] = {psb::JOB_TTTT, psb::JOB_EEEE, psb::JOB_TTTE, psb::JOB_TETE,
+                        psb::JOB_TEEEP, psb::JOB_TEEE, psb::JOB_TTEE};
+const int kCovNeedSp[7] = {4, 4, 4, 4, 4, 4, 4};
+const int kCovNeedRt[7] = {4, 4, 2, 2, 2, 2, 0};
+const int kCovNeedW[7] = {8, 8, 4, 5, 4, 4, 2};
+
+int check_common(int lmin, int lmax, long ld, int row_lo, int row_hi)
+{
+    if (lmin < 0 || lmax < lmin) return fail(ERR_ARG, "need 0 <= lmin <= lmax (got %d, %d)", lmin, lmax);
+    if (lmax > 32767) return fail(ERR_ARG, "lmax %d above the supported 32767", lmax);
+    if (ld < (long)(lmax - lmin + 1)) return fail(ERR_ARG, "leading dimension %ld < N=%d", ld, lmax - lmin + 1);
+    if (row_lo < lmin || row_hi > lmax + 1 || row_lo > row_hi)
+        return fail(ERR_ARG, "row band [%d,%d) outside [%d,%d]", row_lo, row_hi, lmin, lmax);
+    return OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-device scratch for the host-level calls (grown on demand, kept between calls)
+// ---------------------------------------------------------------------------------------
+struct DeviceScratch {
+    double* X[2] = {nullptr, nullptr};
+    size_t capX[2] = {0, 0};
+    double* vec = nullptr;      // packed input vectors
+    size_t capVec = 0;
+    cudaStream_t stream = nullptr;
+};
+DeviceScratch g_scratch[16];
+
+int scratch_reserve(int dev, int which, size_t n)
+{
+    DeviceScratch& s = g_scratch[dev];
+    if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (which < 2) {
+        if (s.capX[which] < n) {
+            if (s.X[which]) cudaFree(s.X[which]);
+            s.X[which] = nullptr; s.capX[which] = 0;
+            CUDA_TRY(cudaMalloc(&s.X[which], n * sizeof(double)));
+            s.capX[which] = n;
+        }
+    } else {
+        if (s.capVec < n) {
+            if (s.vec) cudaFree(s.vec);
+            s.vec = nullptr; s.capVec = 0;
+            CUDA_TRY(cudaMalloc(&s.vec, n * sizeof(double)));
+            s.capVec = n;
+        }
+    }
+    return OK;
+}
+
+int resolve_ngpus(int ngpus, int* out)
+{
+    const int have = device_count();
+    if (have <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    if (ngpus < 0) return fail(ERR_ARG, "ngpus must be >= 0");
+    if (ngpus == 0) ngpus = have;
+    if (ngpus > have) return fail(ERR_ARG, "ngpus=%d but only %d device(s) visible", ngpus, have);
+    if (ngpus > 16) return fail(ERR_ARG, "ngpus=%d above the supported 16", ngpus);
+    *out = ngpus;
+    return OK;
+}
+
+// Shared body of psb200_mcm / psb200_cov on host buffers.
+//   vecs[k] / lens[k]: input vectors to upload, in the order W..., spectra..., ratios...
+struct HostJob {
+    int job;
+    int lmin, lmax, lenW;
+    int nW, nsp, nrt;
+    const double* vecs[16];
+    size_t lens[16];
+    double* out[2];
+    long ldo;
+    int nout;
+    int scale;
+};
+
+int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0, double* X1, long ldX)
+{
+    // Upload the (small) inputs and launch stage 1 for one band on device `dev`.
+    CUDA_TRY(cudaSetDevice(dev));
+    DeviceScratch& s = g_scratch[dev];
+    size_t tot = 0;
+    const int nv = hj.nW + hj.nsp + hj.nrt;
+    for (int k = 0; k < nv; ++k) tot += (hj.lens[k] + 3) & ~size_t(3);
+    if (int rc = scratch_reserve(dev, 2, tot)) return rc;
+    psb::PairArgs A{};
+    A.lmin = hj.lmin; A.lmax = hj.lmax; A.lenW = hj.lenW;
+    A.row_lo = row_lo; A.row_hi = row_hi; A.ld = ldX;
+    A.out0 = X0; A.out1 = X1;
+    size_t off = 0;
+    for (int k = 0; k < nv; ++k) {
+        CUDA_TRY(cudaMemcpyAsync(s.vec + off, hj.vecs[k], hj.lens[k] * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        const double* p = s.vec + off;
+        if (k < hj.nW) A.W[k] = p;
+        else if (k < hj.nW + hj.nsp) A.sp[k - hj.nW] = p;
+        else A.rt[k - hj.nW - hj.nsp] = p;
+        off += (hj.lens[k] + 3) & ~size_t(3);
+    }
+    return launch_any(hj.job, A, s.stream);
+}
+
+int run_host_job(const HostJob& hj, int ngpus)
+{
+    const int N = hj.lmax - hj.lmin + 1;
+    const long ldX = N;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::vector<int> edges(ngpus + 1);
+    psb200_band_edges(hj.lmin, hj.lmax, ngpus, edges.data());
+
+    // device 0 owns the full matrix; the others own their band slab only
+    for (int o = 0; o < hj.nout; ++o)
+        if (int rc = (cudaSetDevice(0), scratch_reserve(0, o, (size_t)N * N))) return rc;
+    for (int g = 1; g < ngpus; ++g) {
+        const size_t rows = (size_t)(edges[g + 1] - edges[g]);
+        CUDA_TRY(cudaSetDevice(g));
+        for (int o = 0; o < hj.nout; ++o)
+            if (int rc = scratch_reserve(g, o, std::max<size_t>(rows * N, 1))) return rc;
+    }
+    // stage 1 on every device (asynchronous launches, one stream per device)
+    for (int g = 0; g < ngpus; ++g) {
+        DeviceScratch& s = g_scratch[g];
+        const long rowoff = (g == 0) ? 0 : (long)(edges[g] - hj.lmin);   // slab starts at its first row
+        double* X0 = s.X[0] - rowoff * ldX;
+        double* X1 = hj.nout > 1 ? s.X[1] - rowoff * ldX : nullptr;
+        if (int rc = run_on_device(hj, g, edges[g], edges[g + 1], X0, X1, ldX)) return rc;
+    }
+    // gather the slabs into device 0's matrix over NVLink (peer copies; rows are contiguous)
+    for (int g = 1; g < ngpus; ++g) {
+        DeviceScratch& s = g_scratch[g];
+        CUDA_TRY(cudaSetDevice(g));
+        const size_t rows = (size_t)(edges[g + 1] - edges[g]);
+        for (int o = 0; o < hj.nout && rows; ++o)
+            CUDA_TRY(cudaMemcpyPeerAsync(g_scratch[0].X[o] + (size_t)(edges[g] - hj.lmin) * ldX, 0,
+                                         s.X[o], g, rows * N * sizeof(double), s.stream));
+    }
+    for (int g = 1; g < ngpus; ++g) {
+        CUDA_TRY(cudaSetDevice(g));
+        CUDA_TRY(cudaStreamSynchronize(g_scratch[g].stream));
+    }
+    // stage 2 + D2H on device 0
+    CUDA_TRY(cudaSetDevice(0));
+    DeviceScratch& s0 = g_scratch[0];
+    for (int o = 0; o < hj.nout; ++o) {
+        if (int rc = psb200_finish_dev(s0.X[o], ldX, hj.lmin, hj.lmax, hj.scale, s0.stream)) return rc;
+        CUDA_TRY(cudaMemcpy2DAsync(hj.out[o], hj.ldo * sizeof(double), s0.X[o], ldX * sizeof(double),
+                                   (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost, s0.stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s0.stream));
+    cudaSetDevice(cur);
+    return OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* psb200_last_error(void) { return g_err.c_str(); }
+const char* psb200_version(void) { return "psb200 0.1 (sm_100a)"; }
+int psb200_device_count(void) { return device_count(); }
+
+int psb200_band_edges(int lmin, int lmax, int nbands, int* edges)
+{
+    if (lmin < 0 || lmax < lmin || nbands < 1 || !edges) return fail(ERR_ARG, "band_edges: bad arguments");
+    // cost(l1) = (2 l1+1)(lmax-l1+1): 3j terms of row l1 of the upper triangle
+    long double total = 0;
+    for (int l = lmin; l <= lmax; ++l) total += (long double)(2 * l + 1) * (lmax - l + 1);
+    edges[0] = lmin;
+    long double run = 0;
+    int b = 1;
+    for (int l = lmin; l <= lmax && b < nbands; ++l) {
+        run += (long double)(2 * l + 1) * (lmax - l + 1);
+        while (b < nbands && run >= total * b / nbands) edges[b++] = l + 1;
+    }
+    while (b <= nbands) edges[b++] = lmax + 1;
+    return OK;
+}
+
+long long psb200_terms(int families, int lmax, int row_lo, int row_hi)
+{
+    long long t = 0;
+    for (int l = row_lo; l < row_hi; ++l) t += (long long)(2 * l + 1) * (lmax - l + 1);
+    return t * families;
+}
+
+int psb200_mcm_dev(int kind, int lmin, int lmax, const double* dV, int nV, double* dX, long ldX,
+                   double* dX2, int row_lo, int row_hi, void* stream)
+{
+    if (kind < 0 || kind > 4) return fail(ERR_ARG, "unknown mcm kind %d", kind);
+    if (int rc = check_common(lmin, lmax, ldX, row_lo, row_hi)) return rc;
+    if (!dV || nV < 1 || !dX) return fail(ERR_ARG, "null / empty buffer");
+    if (kind == 4 && !dX2) return fail(ERR_ARG, "kind 4 needs a second output");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::PairArgs A{};
+    A.lmin = lmin; A.lmax = lmax; A.lenW = nV; A.row_lo = row_lo; A.row_hi = row_hi; A.ld = ldX;
+    A.W[0] = dV; A.out0 = dX; A.out1 = dX2;
+    return launch_any(kMcmJob[kind], A, (cudaStream_t)stream);
+}
+
+int psb200_cov_dev(int block, int lmin, int lmax, const double* const* dsp, int nspec,
+                   const double* const* drt, int nratio, const double* const* dW, int nW, int lenW,
+                   double* dX, long ldX, int row_lo, int row_hi, void* stream)
+{
+    if (block < 0 || block > 6) return fail(ERR_ARG, "unknown covariance block %d", block);
+    if (int rc = check_common(lmin, lmax, ldX, row_lo, row_hi)) return rc;
+    if (nspec != kCovNeedSp[block] || nratio != kCovNeedRt[block] || nW != kCovNeedW[block])
+        return fail(ERR_ARG, "block %d takes %d spectra, %d ratios, %d W (got %d, %d, %d)", block,
+                    kCovNeedSp[block], kCovNeedRt[block], kCovNeedW[block], nspec, nratio, nW);
+    if (!dX || lenW < 1 || !dsp || !dW || (nratio && !drt)) return fail(ERR_ARG, "null / empty buffer");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::PairArgs A{};
+    A.lmin = lmin; A.lmax = lmax; A.lenW = lenW; A.row_lo = row_lo; A.row_hi = row_hi; A.ld = ldX;
+    for (int k = 0; k < nW; ++k) { if (!dW[k]) return fail(ERR_ARG, "W[%d] is null", k); A.W[k] = dW[k]; }
+    for (int k = 0; k < nspec; ++k) { if (!dsp[k]) return fail(ERR_ARG, "spectra[%d] is null", k); A.sp[k] = dsp[k]; }
+    for (int k = 0; k < nratio; ++k) { if (!drt[k]) return fail(ERR_ARG, "ratios[%d] is null", k); A.rt[k] = drt[k]; }
+    A.out0 = dX;
+    return launch_any(kCovJob[block], A, (cudaStream_t)stream);
+}
+
+int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void* stream)
+{
+    if (int rc = check_common(lmin, lmax, ldX, lmin, lmax + 1)) return rc;
+    if (!dX) return fail(ERR_ARG, "null buffer");
+    const int N = lmax - lmin + 1;
+    const int nt = (N + 31) / 32;
+    finish_kernel<<<dim3(nt, nt), 256, 0, (cudaStream_t)stream>>>(dX, ldX, lmin, N, scale ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return OK;
+}
+
+int psb200_mcm(int kind, int lmin, int lmax, const double* V, int nV, double* M, long ldM,
+               double* M2, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (kind < 0 || kind > 4) return fail(ERR_ARG, "unknown mcm kind %d", kind);
+    if (int rc = check_common(lmin, lmax, ldM, lmin, lmax + 1)) return rc;
+    if (!V || nV < 1 || !M) return fail(ERR_ARG, "null / empty buffer");
+    if (kind == 4 && !M2) return fail(ERR_ARG, "kind 4 needs a second output");
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    HostJob hj{};
+    hj.job = kMcmJob[kind];
+    hj.lmin = lmin; hj.lmax = lmax; hj.lenW = nV;
+    hj.nW = 1; hj.nsp = 0; hj.nrt = 0;
+    hj.vecs[0] = V; hj.lens[0] = (size_t)nV;
+    hj.out[0] = M; hj.out[1] = M2; hj.ldo = ldM; hj.nout = kind == 4 ? 2 : 1;
+    hj.scale = 1;
+    return run_host_job(hj, ng);
+}
+
+int psb200_cov(int block, int lmin, int lmax, const double* const* spectra, int nspec,
+               const double* const* ratios, int nratio, const double* const* W, int nW, int lenW,
+               double* C, long ldC, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (block < 0 || block > 6) return fail(ERR_ARG, "unknown covariance block %d", block);
+    if (int rc = check_common(lmin, lmax, ldC, lmin, lmax + 1)) return rc;
+    if (nspec != kCovNeedSp[block] || nratio != kCovNeedRt[block] || nW != kCovNeedW[block])
+        return fail(ERR_ARG, "block %d takes %d spectra, %d ratios, %d W (got %d, %d, %d)", block,
+                    kCovNeedSp[block], kCovNeedRt[block], kCovNeedW[block], nspec, nratio, nW);
+    if (!C || lenW < 1 || !spectra || !W || (nratio && !ratios)) return fail(ERR_ARG, "null / empty buffer");
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    HostJob hj{};
+    hj.job = kCovJob[block];
+    hj.lmin = lmin; hj.lmax = lmax; hj.lenW = lenW;
+    hj.nW = nW; hj.nsp = nspec; hj.nrt = nratio;
+    int k = 0;
+    for (int i = 0; i < nW; ++i, ++k) { if (!W[i]) return fail(ERR_ARG, "W[%d] is null", i); hj.vecs[k] = W[i]; hj.lens[k] = (size_t)lenW; }
+    for (int i = 0; i < nspec; ++i, ++k) { if (!spectra[i]) return fail(ERR_ARG, "spectra[%d] is null", i); hj.vecs[k] = spectra[i]; hj.lens[k] = (size_t)lmax + 1; }
+    for (int i = 0; i < nratio; ++i, ++k) { if (!ratios[i]) return fail(ERR_ARG, "ratios[%d] is null", i); hj.vecs[k] = ratios[i]; hj.lens[k] = (size_t)lmax + 1; }
+    hj.out[0] = C; hj.out[1] = nullptr; hj.ldo = ldC; hj.nout = 1;
+    hj.scale = 0;
+    return run_host_job(hj, ng);
+}
+
+double psb200_dfma_peak(int iters)
+{
+    if (device_count() <= 0) { fail(ERR_NODEVICE, "no CUDA device visible"); return -1.0; }
+    if (iters < 1) iters = 1;
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { fail(ERR_CUDA, "cudaGetDeviceProperties failed"); return -1.0; }
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) { fail(ERR_OOM, "cudaMalloc failed"); return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_kernel<<<blocks, threads>>>(out, iters / 4 + 1, 1.0);   // warm-up
+    cudaEventRecord(e0);
+    dfma_kernel<<<blocks, threads>>>(out, iters, 1.0);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) { fail(ERR_CUDA, "dfma kernel: %s", cudaGetErrorString(e)); return -1.0; }
+    const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+    return flops / (ms * 1e-3);
+}
+
+}  // extern "C"

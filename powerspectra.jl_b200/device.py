@@ -1,0 +1,118 @@
+"""Device-resident driver of the hot path: buffers live in HBM (torch tensors are used only
+as device memory + streams + torch.distributed plumbing), the kernels are libpsb200's.
+
+One process per GPU.  Each rank computes the Xi slab of its work-balanced l1 band
+(psb200_mcm_dev / psb200_cov_dev), slabs are gathered to rank 0 with NCCL send/recv over
+NVLink (a band of rows is one contiguous slab of the column-major result, see
+include/psb200.h), and rank 0 runs the finish kernel that fills both triangles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MCM_KINDS = {"M00": 0, "M02": 1, "Mpp": 2, "Mmm": 3, "Mpp_Mmm": 4}
+COV_BLOCKS = {"TTTT": 0, "EEEE": 1, "TTTE": 2, "TETE": 3, "TEEE_planck": 4, "TEEE": 5, "TTEE": 6}
+REF_FAMILIES = {"M00": 1, "M02": 2, "Mpp": 1, "Mmm": 1, "Mpp_Mmm": 2,
+                "TTTT": 1, "EEEE": 1, "TTTE": 1, "TETE": 2, "TEEE_planck": 1, "TEEE": 2, "TTEE": 1}
+
+
+def band_edges(lmin: int, lmax: int, nbands: int):
+    e = (C.c_int * (nbands + 1))()
+    _lib.check(_lib.lib().psb200_band_edges(lmin, lmax, nbands, e))
+    return list(e)
+
+
+def terms(name: str, lmax: int, row_lo: int, row_hi: int) -> int:
+    """3j terms, counted as the reference evaluates them (full families)."""
+    return int(_lib.lib().psb200_terms(REF_FAMILIES[name], lmax, row_lo, row_hi))
+
+
+def _require_cuda(t: torch.Tensor):
+    if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+        raise ValueError("device API needs contiguous float64 CUDA tensors")
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _vptrs(ts):
+    arr = (C.c_void_p * max(len(ts), 1))()
+    for k, t in enumerate(ts):
+        _require_cuda(t)
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def mcm_slab(kind, lmin, lmax, V: torch.Tensor, X: torch.Tensor, X2: torch.Tensor | None = None,
+             row_lo=None, row_hi=None):
+    """Stage 1 for one band: X is the FULL (N, N) buffer (X[l1-lmin, l2-lmin], torch row-major =
+    the column-major result's transpose) or any view whose data_ptr is row `lmin` of it."""
+    kind = MCM_KINDS.get(kind, kind)
+    N = lmax - lmin + 1
+    row_lo = lmin if row_lo is None else row_lo
+    row_hi = lmax + 1 if row_hi is None else row_hi
+    _require_cuda(V)
+    _require_cuda(X)
+    x2 = None
+    if X2 is not None:
+        _require_cuda(X2)
+        x2 = C.c_void_p(X2.data_ptr())
+    rc = _lib.lib().psb200_mcm_dev(kind, lmin, lmax, C.c_void_p(V.data_ptr()), V.numel(),
+                                   C.c_void_p(X.data_ptr()), N, x2, row_lo, row_hi, _stream_ptr())
+    _lib.check(rc)
+
+
+def cov_slab(block, lmin, lmax, spectra, ratios, W, X: torch.Tensor, row_lo=None, row_hi=None):
+    block = COV_BLOCKS.get(block, block)
+    N = lmax - lmin + 1
+    row_lo = lmin if row_lo is None else row_lo
+    row_hi = lmax + 1 if row_hi is None else row_hi
+    _require_cuda(X)
+    lenW = min(int(w.numel()) for w in W)
+    rc = _lib.lib().psb200_cov_dev(block, lmin, lmax, _vptrs(spectra), len(spectra), _vptrs(ratios), len(ratios),
+                                   _vptrs(W), len(W), lenW, C.c_void_p(X.data_ptr()), N, row_lo, row_hi,
+                                   _stream_ptr())
+    _lib.check(rc)
+
+
+def finish(X: torch.Tensor, lmin, lmax, scale: bool):
+    """Stage 2 in place: both triangles, (2l+1) factors when scale (MCM), plain mirror otherwise."""
+    _require_cuda(X)
+    N = lmax - lmin + 1
+    _lib.check(_lib.lib().psb200_finish_dev(C.c_void_p(X.data_ptr()), N, lmin, lmax, 1 if scale else 0,
+                                            _stream_ptr()))
+
+
+def gather_bands(X: torch.Tensor, edges, lmin, rank, world, group=None):
+    """Send each rank's contiguous band slab X[e_r-lmin : e_{r+1}-lmin, :] to rank 0 (variable
+    sizes => grouped send/recv, there is no gatherv).  Works for NCCL (cuda) and gloo (cpu)."""
+    import torch.distributed as dist
+    if world == 1:
+        return
+    ops = []
+    if rank == 0:
+        for r in range(1, world):
+            a, b = edges[r] - lmin, edges[r + 1] - lmin
+            if b > a:
+                ops.append(dist.P2POp(dist.irecv, X[a:b], r, group))
+    else:
+        a, b = edges[rank] - lmin, edges[rank + 1] - lmin
+        if b > a:
+            ops.append(dist.P2POp(dist.isend, X[a:b], 0, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def dfma_peak(iters: int = 4096) -> float:
+    """Measured FP64 DFMA throughput (FLOP/s) of the current device."""
+    v = float(_lib.lib().psb200_dfma_peak(iters))
+    if v < 0:
+        _lib.check(2)
+    return v

@@ -1,0 +1,140 @@
+"""`mcm` and the inner mode-coupling loops, mirroring /root/reference/src/modecoupling.jl:78-256.
+
+Only the callees (`inner_mcm00!` ...) run on the GPU; the dispatcher keeps the
+reference's behaviour: same spec names, `lmin` / `lmax` keywords, ValueError (Julia:
+ArgumentError, src/modecoupling.jl:225) on an unknown spec, 2x2 block assembly for
+`EE_BB` / `EB_BE` (src/modecoupling.jl:210-223, 235-244).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .spectral import BlockSpectralMatrix, SpectralArray, SpectralVector, spectralzeros
+
+# spec -> kind of include/psb200.h.  Julia symbols with superscripts are accepted as strings.
+_M00 = ("TT", "M00", "M⁰⁰")
+_M02 = ("TE", "ET", "TB", "BT", "M02", "M20", "M⁰²", "M²⁰")
+_MPP = ("M++", "Mpp", "M⁺⁺")
+_MMM = ("M--", "Mmm", "M⁻⁻")
+
+
+class Alm:
+    """Minimal stand-in for Healpix.Alm: complex a_lm, m-major (healpy) ordering,
+    index(l, m) = m (2 lmax + 1 - m) / 2 + l, 0 <= m <= mmax <= lmax."""
+
+    def __init__(self, lmax, mmax, alm):
+        self.lmax, self.mmax = int(lmax), int(mmax)
+        self.alm = np.asarray(alm, dtype=np.complex128)
+        n = (self.mmax + 1) * (self.lmax + 1) - self.mmax * (self.mmax + 1) // 2
+        if self.alm.size != n:
+            raise ValueError(f"expected {n} coefficients for lmax={lmax}, mmax={mmax}")
+
+    @classmethod
+    def zonal(cls, al0):
+        """Alm of an azimuthally symmetric field: only a_l0 non-zero."""
+        al0 = np.asarray(al0, dtype=np.float64)
+        return cls(al0.size - 1, 0, al0.astype(np.complex128))
+
+
+def alm2cl(a: Alm, b: Alm) -> np.ndarray:
+    """Cross-spectrum C_l = [a_l0 b_l0 + 2 sum_{m>0} Re(a_lm conj b_lm)] / (2l+1) (Healpix.alm2cl)."""
+    lmax = min(a.lmax, b.lmax)
+    mmax = min(a.mmax, b.mmax)
+    cl = np.zeros(lmax + 1)
+    for m in range(mmax + 1):
+        ia = m * (2 * a.lmax + 1 - m) // 2
+        ib = m * (2 * b.lmax + 1 - m) // 2
+        ls = np.arange(m, lmax + 1)
+        prod = (a.alm[ia + ls] * np.conj(b.alm[ib + ls])).real
+        cl[ls] += prod if m == 0 else 2.0 * prod
+    return cl / (2.0 * np.arange(lmax + 1) + 1.0)
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.DP)
+
+
+def _inner(kind, M: SpectralArray, V: SpectralArray, M2: SpectralArray | None = None, ngpus=1):
+    if M.ndim != 2 or M.axes(0) != M.axes(1):
+        raise ValueError("mode-coupling matrix must have identical row and column multipoles")  # @assert :80
+    if V.ndim != 1 or V.offsets[0] != 0:
+        raise ValueError("mask spectrum must be a 0-indexed SpectralVector")
+    lmin, lmax = M.firstindex(0), M.lastindex(0)
+    v = np.ascontiguousarray(V.parent, dtype=np.float64)
+    out2 = _dp(M2.parent) if M2 is not None else None
+    rc = _lib.lib().psb200_mcm(kind, lmin, lmax, _dp(v), v.size, _dp(M.parent), M.parent.shape[0], out2, ngpus)
+    _lib.check(rc)
+    return M
+
+
+def inner_mcm00(M, V, ngpus=1):
+    """inner_mcm⁰⁰! (src/modecoupling.jl:78-95)."""
+    return _inner(0, M, V, ngpus=ngpus)
+
+
+def inner_mcm02(M, V, ngpus=1):
+    """inner_mcm⁰²! (src/modecoupling.jl:99-119)."""
+    return _inner(1, M, V, ngpus=ngpus)
+
+
+def inner_mcmpp(M, V, ngpus=1):
+    """inner_mcm⁺⁺! (src/modecoupling.jl:123-139)."""
+    return _inner(2, M, V, ngpus=ngpus)
+
+
+def inner_mcmmm(M, V, ngpus=1):
+    """inner_mcm⁻⁻! (src/modecoupling.jl:143-159)."""
+    return _inner(3, M, V, ngpus=ngpus)
+
+
+def inner_mcmpp_mcmmm(Mpp, Mmm, V, ngpus=1):
+    """Both spin-2 blocks from one evaluation of the (0,-2,2) family (the reference calls
+    inner_mcm⁺⁺! and inner_mcm⁻⁻! back to back, src/modecoupling.jl:213-214)."""
+    _inner(4, Mpp, V, M2=Mmm, ngpus=ngpus)
+    return Mpp, Mmm
+
+
+def _mask_spectrum(alm1, alm2, lmax):
+    if isinstance(alm1, SpectralArray) and alm2 is None:      # already a cross-spectrum V
+        if lmax is None:
+            lmax = alm1.lastindex(0)
+        return SpectralVector(alm1.zero_based(lmax)), lmax
+    if lmax is None:
+        lmax = min(alm1.lmax, alm2.lmax)                       # src/modecoupling.jl:194-196
+    return SpectralVector(alm2cl(alm1, alm2)[: lmax + 1]), lmax  # :197
+
+
+def mcm(spec, alm1, alm2=None, *, lmin=0, lmax=None, ngpus=1):
+    """Mode-coupling matrix (src/modecoupling.jl:192-246).
+
+    spec: "TT" | "TE"/"ET"/"TB"/"BT" | "M++" | "M--" | "EE_BB" | "EB_BE" | ("EE_BB", "EB_BE").
+    alm1, alm2: mask Alm's (or one 0-indexed SpectralVector holding their cross-spectrum).
+    Returns a SpectralArray over lmin:lmax, or BlockSpectralMatrix(es) for the 2x2 specs.
+    """
+    V, lmax = _mask_spectrum(alm1, alm2, lmax)
+    r = range(lmin, lmax + 1)
+    if isinstance(spec, tuple):
+        if spec == ("EE_BB", "EB_BE"):
+            Mpp, Mmm = inner_mcmpp_mcmmm(spectralzeros(r, r), spectralzeros(r, r), V, ngpus)
+            neg = SpectralArray(-Mmm.parent, Mmm.offsets)
+            return (BlockSpectralMatrix([[Mpp, Mmm], [Mmm, Mpp]]),
+                    BlockSpectralMatrix([[Mpp, neg], [neg, Mpp]]))
+        raise ValueError(f"{spec} not a valid spectrum.")
+    if spec in _M00:
+        return inner_mcm00(spectralzeros(r, r), V, ngpus)
+    if spec in _M02:
+        return inner_mcm02(spectralzeros(r, r), V, ngpus)
+    if spec in _MPP:
+        return inner_mcmpp(spectralzeros(r, r), V, ngpus)
+    if spec in _MMM:
+        return inner_mcmmm(spectralzeros(r, r), V, ngpus)
+    if spec in ("EE_BB", "EB_BE"):
+        Mpp, Mmm = inner_mcmpp_mcmmm(spectralzeros(r, r), spectralzeros(r, r), V, ngpus)
+        if spec == "EE_BB":
+            return BlockSpectralMatrix([[Mpp, Mmm], [Mmm, Mpp]])
+        neg = SpectralArray(-Mmm.parent, Mmm.offsets)
+        return BlockSpectralMatrix([[Mpp, neg], [neg, Mpp]])
+    raise ValueError(f"{spec} not a valid spectrum.")

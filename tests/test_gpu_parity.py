@@ -1,0 +1,286 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (host-level entry points via
+the Python mirror of the reference interface, and the device-level entry points), against
+the CPU oracle on the same seeded inputs.  Criterion (BASELINE.json north_star): relative
+error <= 1e-10 on every entry above 1e-30 of its row maximum.  Spin-2 rows/columns with
+l < 2 are the reference's don't-care region (never pinned by its tests)
+and are compared from l = 2.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, parity_error
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+KINDS = {"TT": 0, "TE": 1, "M++": 2, "M--": 3}
+
+
+@pytest.fixture(scope="module")
+def masks767(ps):
+    from powerspectra_jl_b200 import synthetic as syn
+    return syn.mask_spectra(767, seeds=(1001, 1002))
+
+
+def _cmp(M, R, spin2):
+    lo = 2 if spin2 else 0
+    return parity_error(M[lo:, lo:], R[lo:, lo:])
+
+
+@pytest.mark.parametrize("spec", ["TT", "TE", "M++", "M--"])
+@pytest.mark.parametrize("which", [(0, 0), (0, 1)])
+def test_mcm_lmax767(ps, oracle, masks767, spec, which):
+    """configs[0] of BASELINE.json (TT, nside 256) plus the other kinds; auto and cross masks
+    (the cross-spectrum changes sign => cancelling sums)."""
+    V = masks767[which]
+    M = ps.mcm(spec, ps.SpectralVector(V)).parent
+    R = oracle.mcm(KINDS[spec], 0, 767, V)
+    RL = oracle.mcm(KINDS[spec], 0, 767, V, ld=True)
+    spin2 = spec != "TT"
+    assert _cmp(M, R, spin2) < TOL
+    assert _cmp(M, RL, spin2) < TOL
+    assert np.all(np.isfinite(M))
+
+
+def test_mcm_fused_spin2_blocks(ps, oracle, masks767):
+    V = masks767[(0, 1)]
+    ee_bb, eb_be = ps.mcm(("EE_BB", "EB_BE"), ps.SpectralVector(V), lmin=2)
+    Rp = oracle.mcm(2, 2, 767, V)
+    Rm = oracle.mcm(3, 2, 767, V)
+    assert parity_error(ee_bb.getblock(0, 0).parent, Rp) < TOL
+    assert parity_error(ee_bb.getblock(0, 1).parent, Rm) < TOL
+    assert np.array_equal(ee_bb.getblock(1, 1).parent, ee_bb.getblock(0, 0).parent)
+    assert np.array_equal(eb_be.getblock(0, 1).parent, -ee_bb.getblock(0, 1).parent)
+    # the fused kind must agree with the separate kinds bit for bit
+    assert np.array_equal(ps.mcm("M++", ps.SpectralVector(V), lmin=2).parent, ee_bb.getblock(0, 0).parent)
+    assert np.array_equal(ps.mcm("M--", ps.SpectralVector(V), lmin=2).parent, ee_bb.getblock(1, 0).parent)
+
+
+@pytest.mark.parametrize("lmin,lmax,nV", [(0, 0, 1), (0, 1, 2), (0, 2, 3), (1, 1, 5), (5, 5, 3), (3, 40, 41),
+                                          (0, 130, 20), (0, 100, 201), (0, 100, 400), (17, 300, 301)])
+def test_mcm_edge_shapes(ps, oracle, lmin, lmax, nV):
+    """ragged / degenerate shapes: single multipole, nV shorter and longer than the family."""
+    rng = np.random.default_rng(lmax * 7 + nV)
+    V = rng.normal(size=nV)
+    lib = ps.lib()
+    N = lmax - lmin + 1
+    for kind in range(4):
+        ld = N + 3                                          # leading dimension larger than N
+        M = np.full((ld, N), np.nan, order="F")
+        rc = lib.psb200_mcm(kind, lmin, lmax, V.ctypes.data_as(ps._lib.DP), nV,
+                            M.ctypes.data_as(ps._lib.DP), ld, None, 1)
+        assert rc == 0, lib.psb200_last_error()
+        assert np.all(np.isnan(M[N:, :]))                   # padding rows untouched
+        R = oracle.mcm(kind, lmin, lmax, V)
+        lo = max(2 - lmin, 0) if kind else 0
+        if lo < N:
+            assert parity_error(M[:N][lo:, lo:], R[lo:, lo:]) < TOL
+
+
+def test_mcm_identities_full_size(ps):
+    """lmax = 6143 (BASELINE metric size) through size-independent properties."""
+    lmax = 6143
+    n = lmax + 1
+    V = np.zeros(n)
+    V[0] = 4 * np.pi                                        # full-sky mask => identity
+    M = ps.mcm("TT", ps.SpectralVector(V)).parent
+    assert np.max(np.abs(M - np.eye(n))) < 1e-12
+    both = ps.mcm("EE_BB", ps.SpectralVector(V), lmin=2)
+    assert np.max(np.abs(both.getblock(0, 0).parent - np.eye(n - 2))) < 1e-12
+    assert np.max(np.abs(both.getblock(0, 1).parent)) < 1e-12
+    del M, both
+    V = np.ones(2 * lmax + 1)                               # completeness: Xi = 1/4pi for every pair
+    M = ps.mcm("TT", ps.SpectralVector(V), lmax=lmax).parent
+    expect = (2 * np.arange(n) + 1) / (4 * np.pi)
+    assert np.max(np.abs(M / expect[None, :] - 1)) < 1e-11
+    # symmetry M[l1,l2]/(2 l2+1) = M[l2,l1]/(2 l1+1)
+    S = M / expect[None, :]
+    assert np.max(np.abs(S - S.T)) < 1e-15
+    del M, S
+    both = ps.mcm("EE_BB", ps.SpectralVector(V), lmin=2, lmax=lmax)
+    T = both.getblock(0, 0).parent + both.getblock(0, 1).parent
+    assert np.max(np.abs(T / expect[None, 2:] - 1)) < 1e-11
+
+
+@pytest.mark.parametrize("kind", [0, 1, 4])
+def test_mcm_sampled_rows_full_size(ps, oracle, kind):
+    """lmax = 6143, two distinct masks: every 192nd row of the GPU matrix against the oracle."""
+    from powerspectra_jl_b200 import synthetic as syn
+    lmax = 6143
+    V = syn.mask_spectra(lmax, seeds=(1001, 1002))[(0, 1)]
+    rstep, row0 = 192, 5
+    rows = np.arange(row0, lmax + 1, rstep)
+    if kind == 4:
+        ee_bb = ps.mcm("EE_BB", ps.SpectralVector(V))
+        got = [ee_bb.getblock(0, 0).parent, ee_bb.getblock(0, 1).parent]
+        refs = [oracle.mcm(2, 0, lmax, V, row0=row0, rstep=rstep), oracle.mcm(3, 0, lmax, V, row0=row0, rstep=rstep)]
+    else:
+        got = [ps.mcm("TT" if kind == 0 else "TE", ps.SpectralVector(V)).parent]
+        refs = [oracle.mcm(kind, 0, lmax, V, row0=row0, rstep=rstep)]
+    for G, R in zip(got, refs):
+        for r in rows:
+            assert parity_error(G[r:r + 1, max(r, 2):], R[r:r + 1, max(r, 2):]) < TOL, r
+
+
+COV_ARGS = {
+    # block -> (spectra keys, ratio keys, W keys) in the positional order of the reference signatures
+    "TTTT": ([("TT", "i", "p"), ("TT", "j", "q"), ("TT", "i", "q"), ("TT", "j", "p")],
+             [("TT", "i", "p"), ("TT", "j", "q"), ("TT", "i", "q"), ("TT", "j", "p")]),
+    "EEEE": ([("EE", "i", "p"), ("EE", "j", "q"), ("EE", "i", "q"), ("EE", "j", "p")],
+             [("EE", "i", "p"), ("EE", "j", "q"), ("EE", "i", "q"), ("EE", "j", "p")]),
+}
+
+
+def _cov_case(ps, lmax, use_theory=False):
+    from powerspectra_jl_b200 import synthetic as syn
+    ws, sp, rt = syn.covariance_inputs(lmax)
+    if use_theory:
+        g = np.load(os.path.join(GOLDEN, "theory_noise_767.npz"))
+        omega = 4 * np.pi / (12 * 256 ** 2)
+        for (s, a, b) in list(sp):
+            sp[s, a, b] = ps.SpectralVector(np.maximum(g["cl" + s.lower()], 1e-12) if s != "TE" else g["clte"])
+        for (s, a, b) in list(rt):
+            nl = g["nltt"] if s == "TT" else g["nlee"]
+            rt[s, a, b] = ps.SpectralVector(np.sqrt(nl / omega) if a == b else np.ones(768))
+    return ws, sp, rt
+
+
+class _Capture:
+    """Records the positional arguments the coupledcovXXYY wrappers hand to the loop so the
+    oracle gets exactly the same vectors."""
+
+    def __init__(self):
+        self.args = None
+
+
+def _oracle_cov(oracle, ps, name, ws, sp, rt, lmin, lmax, planck=True, ld=False):
+    import powerspectra_jl_b200.covariance as cv
+    cap = {}
+    real = cv._loop
+
+    def fake(block, Cm, spectra, ratios, Ws, ngpus=1):
+        cap["a"] = (block, [s.zero_based(lmax) for s in spectra], [r.zero_based(lmax) for r in ratios],
+                    [w.parent for w in Ws])
+        return Cm
+    cv._loop = fake
+    try:
+        Cm = ps.spectralzeros(range(lmin, lmax + 1), range(lmin, lmax + 1))
+        fn = {"TTTT": cv.coupledcovTTTT, "EEEE": cv.coupledcovEEEE, "TTTE": cv.coupledcovTTTE,
+              "TETE": cv.coupledcovTETE, "TTEE": cv.coupledcovTTEE}.get(name)
+        if fn is None:
+            cv.coupledcovTEEE(Cm, ws, sp, rt, planck=planck)
+        else:
+            fn(Cm, ws, sp, rt)
+    finally:
+        cv._loop = real
+    block, S, R, W = cap["a"]
+    return oracle.cov(block, lmin, lmax, S, R, W, ld=ld)
+
+
+@pytest.mark.parametrize("chans", [("TT", "TT"), ("EE", "EE"), ("TE", "TE"), ("TT", "TE"), ("TT", "EE"), ("TE", "EE")])
+def test_coupledcov_blocks_lmax255(ps, oracle, chans):
+    lmax = 255
+    ws, sp, rt = _cov_case(ps, lmax)
+    C = ps.coupledcov(chans[0], chans[1], ws, sp, rt)
+    name = chans[0] + chans[1]
+    R = _oracle_cov(oracle, ps, name, ws, sp, rt, 0, lmax)
+    lo = 0 if name in ("TTTT", "TTTE", "TTEE") else 2
+    assert parity_error(C.parent[lo:, lo:], R[lo:, lo:]) < TOL
+    assert np.array_equal(C.parent, C.parent.T)             # C[l2,l1] = C[l1,l2] bit for bit
+
+
+def test_coupledcov_teee_non_planck_and_default_ratios(ps, oracle):
+    import powerspectra_jl_b200.covariance as cv
+    lmax = 200
+    ws, sp, rt = _cov_case(ps, lmax)
+    Cm = ps.spectralzeros(range(2, lmax + 1), range(2, lmax + 1))
+    cv.coupledcovTEEE(Cm, ws, sp, rt, planck=False)
+    R = _oracle_cov(oracle, ps, "TEEE", ws, sp, rt, 2, lmax, planck=False)
+    assert parity_error(Cm.parent, R) < TOL
+    # default noise ratios == 1 (src/covariance.jl:41-45)
+    C1 = ps.coupledcov("TT", "TT", ws, sp)
+    ones = ps.ConstantDict(ps.spectralones(range(0, lmax + 1)))
+    R1 = _oracle_cov(oracle, ps, "TTTT", ws, sp, ones, 0, lmax)
+    assert parity_error(C1.parent, R1) < TOL
+    assert ps.coupledcov("BB", "BB", ws, sp) is None        # prints "not implemented", returns nothing
+
+
+@pytest.mark.parametrize("chans", [("TT", "TT"), ("EE", "EE"), ("TE", "TE")])
+def test_coupledcov_lmax767_reference_spectra(ps, oracle, chans):
+    """The reference's covariance test set-up (test/test_covmat.jl:28-77): theory.csv / noise.csv
+    spectra, r = sqrt(nl / Omega_pix), workspace (m1, m2, m1, m2)."""
+    lmax = 767
+    ws, sp, rt = _cov_case(ps, lmax, use_theory=True)
+    C = ps.coupledcov(chans[0], chans[1], ws, sp, rt, lmin=2)
+    R = _oracle_cov(oracle, ps, chans[0] + chans[1], ws, sp, rt, 2, lmax)
+    assert parity_error(C.parent, R) < TOL
+
+
+def test_covariance_ties_to_mcm_on_gpu(ps):
+    """SURVEY.md 8c item 7, GPU against GPU, at a size the oracle is not needed for."""
+    lmax = 1023
+    rng = np.random.default_rng(11)
+    V = rng.normal(size=lmax + 1)
+    one, zero = ps.SpectralVector(np.ones(lmax + 1)), ps.SpectralVector(np.zeros(lmax + 1))
+    scale = 2 * np.arange(lmax + 1) + 1.0
+    r = range(0, lmax + 1)
+    Vs = ps.SpectralVector(V)
+    C = ps.loop_covTTTT(ps.spectralzeros(r, r), one, one, one, one, zero, zero, zero, zero, Vs, *([zero] * 7)).parent
+    assert parity_error(C, ps.mcm("TT", Vs).parent / scale) < 1e-12
+    C = ps.loop_covEEEE(ps.spectralzeros(r, r), one, one, one, one, zero, zero, zero, zero, Vs, *([zero] * 7)).parent
+    assert parity_error(C[2:, 2:], (ps.mcm("M++", Vs).parent / scale)[2:, 2:]) < 1e-12
+    C = ps.loop_covTETE(ps.spectralzeros(r, r), one, one, zero, zero, zero, zero, Vs, *([zero] * 4)).parent
+    assert parity_error(C[2:, 2:], (ps.mcm("TE", Vs).parent / scale)[2:, 2:]) < 1e-12
+
+
+def test_namaster_golden_diagonals_on_gpu(ps):
+    g = np.load(os.path.join(GOLDEN, "namaster_diag.npz"))
+    V = np.zeros(768)
+    V[0::2] = g["V_even"]
+    ells = np.arange(2, 767)
+    for spec, key in (("TT", "tt"), ("M++", "ee"), ("TE", "te")):
+        d = np.diag(ps.mcm(spec, ps.SpectralVector(V)).parent)[ells]
+        assert np.max(np.abs(d / g[key] - 1.0)) < 1e-12, key
+
+
+def test_band_sharding_device_api(ps, oracle):
+    """Row bands computed independently into one buffer + finish == the one-call result."""
+    import torch
+    from powerspectra_jl_b200 import device as dev
+    from powerspectra_jl_b200 import synthetic as syn
+    lmin, lmax = 2, 500
+    V = syn.mask_spectra(lmax, seeds=(1003, 1004))[(0, 1)]
+    N = lmax - lmin + 1
+    Vd = torch.tensor(V, device="cuda")
+    for kind, spec in ((0, "TT"), (4, None)):
+        X = torch.zeros((N, N), dtype=torch.float64, device="cuda")
+        X2 = torch.zeros_like(X) if kind == 4 else None
+        edges = dev.band_edges(lmin, lmax, 5)
+        assert edges[0] == lmin and edges[-1] == lmax + 1 and all(b >= a for a, b in zip(edges, edges[1:]))
+        for a, b in zip(edges[::-1][1:], edges[::-1][:-1]):      # any order
+            dev.mcm_slab(kind, lmin, lmax, Vd, X, X2, a, b)
+        dev.finish(X, lmin, lmax, True)
+        got = X.cpu().numpy().T                                  # torch row-major == column-major transposed
+        if kind == 0:
+            assert np.array_equal(got, ps.mcm("TT", ps.SpectralVector(V), lmin=lmin).parent)
+        else:
+            dev.finish(X2, lmin, lmax, True)
+            assert parity_error(got, oracle.mcm(2, lmin, lmax, V)) < TOL
+            assert parity_error(X2.cpu().numpy().T, oracle.mcm(3, lmin, lmax, V)) < TOL
+
+
+def test_error_codes(ps):
+    lib = ps.lib()
+    V = np.ones(8)
+    M = np.zeros((8, 8), order="F")
+    vp, mp = V.ctypes.data_as(ps._lib.DP), M.ctypes.data_as(ps._lib.DP)
+    assert lib.psb200_mcm(9, 0, 7, vp, 8, mp, 8, None, 1) == 1          # unknown kind
+    assert lib.psb200_mcm(0, 5, 3, vp, 8, mp, 8, None, 1) == 1          # lmin > lmax
+    assert lib.psb200_mcm(0, 0, 7, vp, 8, mp, 4, None, 1) == 1          # ld < N
+    assert lib.psb200_mcm(4, 0, 7, vp, 8, mp, 8, None, 1) == 1          # fused kind without M2
+    assert lib.psb200_mcm(0, 0, 7, vp, 8, mp, 8, None, 99) == 1         # more GPUs than visible
+    assert b"device" in lib.psb200_last_error()
+    with pytest.raises(ValueError):
+        ps.mcm("XX", ps.SpectralVector(V))
+    assert lib.psb200_mcm(0, 0, 7, vp, 8, mp, 8, None, 1) == 0

@@ -1,0 +1,120 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/psb200.h declares,
+argument checking and the no-device error, host containers, band partitioning."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(ps):
+    hdr = open(os.path.join(ROOT, "include", "psb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(psb200_\w+)\s*\(", hdr))
+    assert declared == set(ps._lib.PROTOTYPES), declared ^ set(ps._lib.PROTOTYPES)
+    L = ps.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.psb200_version().startswith(b"psb200")
+
+
+def test_no_cpu_fallback(ps):
+    """Without a device every compute call fails loudly (code 5); bad arguments give 1 first."""
+    L = ps.lib()
+    V = np.ones(8)
+    M = np.zeros((8, 8), order="F")
+    vp, mp = V.ctypes.data_as(ps._lib.DP), M.ctypes.data_as(ps._lib.DP)
+    assert L.psb200_mcm(7, 0, 7, vp, 8, mp, 8, None, 1) == 1
+    assert L.psb200_mcm(0, 3, 2, vp, 8, mp, 8, None, 1) == 1
+    assert L.psb200_mcm(0, 0, 7, vp, 8, mp, 2, None, 1) == 1
+    if L.psb200_device_count() == 0:
+        assert L.psb200_mcm(0, 0, 7, vp, 8, mp, 8, None, 1) == 5
+        assert b"no CPU fallback" in L.psb200_last_error()
+        with pytest.raises(ps.PSB200Error):
+            ps.mcm("TT", ps.SpectralVector(V))
+        assert np.all(M == 0.0)
+    with pytest.raises(ValueError):
+        ps.mcm("TT", ps.SpectralVector(V), lmin=5, lmax=3)
+
+
+def test_cov_arity_checked(ps):
+    L = ps.lib()
+    v = np.ones(8)
+    p = (ps._lib.DP * 8)(*[v.ctypes.data_as(ps._lib.DP)] * 8)
+    Cm = np.zeros((8, 8), order="F")
+    cp = Cm.ctypes.data_as(ps._lib.DP)
+    assert L.psb200_cov(0, 0, 7, p, 4, p, 4, p, 7, 8, cp, 8, 1) == 1     # TTTT needs 8 W
+    assert L.psb200_cov(6, 0, 7, p, 4, p, 2, p, 2, 8, cp, 8, 1) == 1     # TTEE takes no ratios
+    assert L.psb200_cov(7, 0, 7, p, 4, p, 4, p, 8, 8, cp, 8, 1) == 1     # unknown block
+
+
+def test_band_edges_balance(ps):
+    from powerspectra_jl_b200 import device as dev
+    for lmin, lmax, nb in [(0, 6143, 8), (2, 767, 4), (0, 12287, 8), (0, 5, 8), (10, 10, 3)]:
+        e = dev.band_edges(lmin, lmax, nb)
+        assert e[0] == lmin and e[-1] == lmax + 1 and len(e) == nb + 1
+        assert all(b >= a for a, b in zip(e, e[1:]))
+        cost = [dev.terms("M00", lmax, a, b) for a, b in zip(e, e[1:])]
+        assert sum(cost) == dev.terms("M00", lmax, lmin, lmax + 1)
+        if lmax - lmin > 100 * nb:
+            assert max(cost) / (sum(cost) / nb) < 1.02           # row granularity only
+    assert dev.terms("M00", 6143, 0, 6144) == 77328286720
+    assert dev.terms("M00", 767, 0, 768) == 151289984
+
+
+def test_spectral_array_semantics(ps):
+    """subset of /root/reference/test/test_spectralarray.jl: offsets, slicing, inverse."""
+    A = ps.SpectralArray(np.arange(16.0).reshape(4, 4))
+    assert A[0, 0] == 0.0 and A[3, 3] == 15.0
+    B = ps.spectralzeros(range(2, 6), range(2, 6))
+    B[2, 3] = 7.0
+    assert B.parent[0, 1] == 7.0 and B.firstindex(0) == 2 and B.lastindex(1) == 5
+    v = ps.SpectralVector(np.arange(10.0))
+    s = v[2:5]
+    assert isinstance(s, ps.SpectralArray) and s.offsets == (2,) and s[2] == 2.0
+    with pytest.raises(IndexError):
+        v[10]
+    M = ps.SpectralArray(np.array([[2.0, 1.0], [1.0, 3.0]]), (2, 2))
+    x = M.solve(ps.SpectralVector(np.array([1.0, 2.0]), 2))
+    assert np.allclose(M.parent @ x.parent, [1.0, 2.0]) and x.offsets == (2,)
+    assert np.allclose(M.inv().parent @ M.parent, np.eye(2))
+    z = ps.SpectralVector(np.arange(2.0, 8.0), 2).zero_based(6)
+    assert np.array_equal(z, [0, 0, 2, 3, 4, 5, 6])
+
+
+def test_block_matrix_and_decouple(ps):
+    rng = np.random.default_rng(0)
+    a = ps.SpectralArray(rng.normal(size=(3, 3)) + 4 * np.eye(3), (2, 2))
+    b = ps.SpectralArray(0.1 * rng.normal(size=(3, 3)), (2, 2))
+    blk = ps.BlockSpectralMatrix([[a, b], [b, a]])
+    assert blk.parent.shape == (6, 6) and np.array_equal(blk.getblock(1, 0).parent, b.parent)
+    e, bb = ps.SpectralVector(rng.normal(size=3), 2), ps.SpectralVector(rng.normal(size=3), 2)
+    x, y = blk.solve([e, bb])
+    assert np.allclose(blk.parent @ np.concatenate([x.parent, y.parent]), np.concatenate([e.parent, bb.parent]))
+    # decouple_covmat == inv(B1) A inv(B2)'   (test/test_covmat.jl:11-18)
+    A = np.array([[1.0, 0.2, 0.3], [0.4, 2.0, 0.15], [0.3, 0.1, 1.44]])
+    B1 = np.array([[1.2, 0.6, 0.1], [0.3, 1.4, 0.5], [0.44, 0.2, 1.3]])
+    B2 = np.array([[1.6, 0.4, 0.1], [0.3, 1.4, 0.9], [0.45, 0.8, 1.7]])
+    Cd = ps.decouple_covmat(ps.SpectralArray(A), ps.SpectralArray(B1), ps.SpectralArray(B2))
+    assert np.allclose(Cd.parent, np.linalg.inv(B1) @ A @ np.linalg.inv(B2).T)
+
+
+def test_alm2cl_and_workspace(ps):
+    a = ps.Alm.zonal([1.0, 2.0, 3.0])
+    b = ps.Alm.zonal([2.0, 1.0, -1.0])
+    assert np.allclose(ps.alm2cl(a, b), [2.0, 2.0 / 3, -3.0 / 5])
+    rng = np.random.default_rng(1)
+    full = ps.Alm(2, 2, rng.normal(size=6) + 1j * rng.normal(size=6))
+    cl = ps.alm2cl(full, full)
+    assert np.isclose(cl[2], (abs(full.alm[2]) ** 2 + 2 * abs(full.alm[4]) ** 2 + 2 * abs(full.alm[5]) ** 2) / 5)
+    ws = ps.CovarianceWorkspace(("a", "b", "a", "b"), 4)
+    with pytest.raises(KeyError):
+        ps.window_function_W(ws, "TT", "TT", "a", "a", "TT", "b", "b", "TT")
+    calls = []
+    ws = ps.CovarianceWorkspace(("a", "b", "a", "b"), 4, provider=lambda *k: calls.append(k) or np.ones(5))
+    w1 = ps.window_function_W(ws, "TT", "TT", "a", "a", "TT", "b", "b", "TT")
+    w2 = ps.window_function_W(ws, "TT", "TT", "a", "a", "TT", "b", "b", "TT")
+    assert w1 is w2 and len(calls) == 1                      # cached like workspace.W_spectra
