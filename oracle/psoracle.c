@@ -29,6 +29,12 @@
 #include <omp.h>
 #endif
 
+/* 0: the reference computation.  1: every l3 term and every additive term of a covariance
+ * formula enters with its absolute value -- the "condition sum" S_abs that scales the
+ * Float64 noise floor of a cancelling entry in the parity tests.  Never used when timing. */
+static int pso_abs_mode = 0;
+void pso_set_abs_mode(int on) { pso_abs_mode = on ? 1 : 0; }
+
 #define PSO_CAT_(a, b) a##b
 #define PSO_CAT(a, b) PSO_CAT_(a, b)
 

@@ -57,6 +57,7 @@ def lib():
             f = getattr(L, "pso_w3j_family" + suf)
             f.restype = C.c_int
             f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, ip, ip]
+        L.pso_set_abs_mode.argtypes = [C.c_int]
         L.pso_max_threads.restype = C.c_int
         L.pso_set_threads.argtypes = [C.c_int]
         _lib = L
@@ -119,6 +120,16 @@ def cov(block, lmin, lmax, spectra, ratios, W, ld=False, row0=0, rstep=1, thread
     if t < 0:
         raise ValueError("oracle cov: bad arguments")
     return (Cm, t) if return_terms else Cm
+
+
+class abs_mode:
+    """Context manager: inside it mcm()/cov() return the condition sums S_abs (sum of |terms|)."""
+
+    def __enter__(self):
+        lib().pso_set_abs_mode(1)
+
+    def __exit__(self, *a):
+        lib().pso_set_abs_mode(0)
 
 
 def max_threads() -> int:

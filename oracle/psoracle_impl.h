@@ -182,8 +182,13 @@ static inline REAL FN(xi)(const double* W, int lenW, const REAL* w, int nmin, in
     if (par == 1) { if ((l1 + l2 + s) & 1) ++s; step = 2; }
     if (par == 2) { if (!((l1 + l2 + s) & 1)) ++s; step = 2; }
     REAL acc = 0;
-    for (int l3 = s; l3 <= e; l3 += step)
-        acc += (REAL)(2 * l3 + 1) * w[l3 - nmin] * (REAL)W[l3];
+    if (pso_abs_mode) {       /* condition sum: sum |term|, used only to scale test tolerances */
+        for (int l3 = s; l3 <= e; l3 += step)
+            acc += FABS((REAL)(2 * l3 + 1) * w[l3 - nmin] * (REAL)W[l3]);
+    } else {
+        for (int l3 = s; l3 <= e; l3 += step)
+            acc += (REAL)(2 * l3 + 1) * w[l3 - nmin] * (REAL)W[l3];
+    }
     return acc / (4 * PI_R);
 }
 
@@ -257,6 +262,7 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                 int nmin, nmax, n;
                 REAL c = 0;
 #define S(k, l) ((REAL)sp[k][l])
+#define AT(x) (pso_abs_mode ? FABS(x) : (x))   /* each additive term of the block formula */
 #define R(k, l) ((REAL)rt[k][l])
                 if (block == 0 || block == 1) {
                     /* spectra: ip, jq, iq, jp ; ratios: ip, jq, iq, jp */
@@ -267,14 +273,14 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                     terms += n;
                     REAL x[8];
                     for (int k = 0; k < 8; ++k) x[k] = FN(xi)(W[k], lenW, b0, nmin, nmax, l1, l2, par);
-                    c = SQRT(S(0, l1) * S(0, l2) * S(1, l1) * S(1, l2)) * x[0] +
-                        SQRT(S(2, l1) * S(2, l2) * S(3, l1) * S(3, l2)) * x[1] +
-                        SQRT(S(0, l1) * S(0, l2)) * x[2] * R(1, l1) * R(1, l2) +
-                        SQRT(S(1, l1) * S(1, l2)) * x[3] * R(0, l1) * R(0, l2) +
-                        SQRT(S(2, l1) * S(2, l2)) * x[4] * R(3, l1) * R(3, l2) +
-                        SQRT(S(3, l1) * S(3, l2)) * x[5] * R(2, l1) * R(2, l2) +
-                        x[6] * R(0, l1) * R(1, l1) * R(0, l2) * R(1, l2) +
-                        x[7] * R(2, l1) * R(3, l1) * R(2, l2) * R(3, l2);
+                    c = AT(SQRT(S(0, l1) * S(0, l2) * S(1, l1) * S(1, l2)) * x[0]) +
+                        AT(SQRT(S(2, l1) * S(2, l2) * S(3, l1) * S(3, l2)) * x[1]) +
+                        AT(SQRT(S(0, l1) * S(0, l2)) * x[2] * R(1, l1) * R(1, l2)) +
+                        AT(SQRT(S(1, l1) * S(1, l2)) * x[3] * R(0, l1) * R(0, l2)) +
+                        AT(SQRT(S(2, l1) * S(2, l2)) * x[4] * R(3, l1) * R(3, l2)) +
+                        AT(SQRT(S(3, l1) * S(3, l2)) * x[5] * R(2, l1) * R(2, l2)) +
+                        AT(x[6] * R(0, l1) * R(1, l1) * R(0, l2) * R(1, l2)) +
+                        AT(x[7] * R(2, l1) * R(3, l1) * R(2, l2) * R(3, l2));
                 } else if (block == 2) {
                     /* TTTE: spectra TTip, TTjp, TEiq, TEjq ; ratios ip, jp */
                     n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
@@ -282,10 +288,10 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                     terms += n;
                     REAL x[4];
                     for (int k = 0; k < 4; ++k) x[k] = FN(xi)(W[k], lenW, b0, nmin, nmax, l1, l2, 0);
-                    c = (SQRT(S(0, l1) * S(0, l2)) * (S(3, l1) + S(3, l2)) * x[0] +
-                         SQRT(S(1, l1) * S(1, l2)) * (S(2, l1) + S(2, l2)) * x[1] +
-                         (S(3, l1) + S(3, l2)) * x[2] * R(0, l1) * R(0, l2) +
-                         (S(2, l1) + S(2, l2)) * x[3] * R(1, l1) * R(1, l2)) / 2;
+                    c = (AT(SQRT(S(0, l1) * S(0, l2)) * (S(3, l1) + S(3, l2)) * x[0]) +
+                         AT(SQRT(S(1, l1) * S(1, l2)) * (S(2, l1) + S(2, l2)) * x[1]) +
+                         AT((S(3, l1) + S(3, l2)) * x[2] * R(0, l1) * R(0, l2)) +
+                         AT((S(2, l1) + S(2, l2)) * x[3] * R(1, l1) * R(1, l2))) / 2;
                 } else if (block == 3) {
                     /* TETE: spectra TTip, EEjq, TEiq, TEjp ; ratios TT_ip, PP_jq */
                     n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
@@ -297,11 +303,11 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                     REAL x3 = FN(xi)(W[2], lenW, b2, nmin, nmax, l1, l2, 1);
                     REAL x4 = FN(xi)(W[3], lenW, b2, nmin, nmax, l1, l2, 1);
                     REAL x5 = FN(xi)(W[4], lenW, b2, nmin, nmax, l1, l2, 1);
-                    c = SQRT(S(0, l1) * S(0, l2) * S(1, l1) * S(1, l2)) * x1 +
-                        (REAL)0.5 * (S(2, l1) * S(3, l2) + S(3, l1) * S(2, l2)) * x2 +
-                        SQRT(S(0, l1) * S(0, l2)) * x3 * R(1, l1) * R(1, l2) +
-                        SQRT(S(1, l1) * S(1, l2)) * x4 * R(0, l1) * R(0, l2) +
-                        x5 * R(0, l1) * R(0, l2) * R(1, l1) * R(1, l2);
+                    c = AT(SQRT(S(0, l1) * S(0, l2) * S(1, l1) * S(1, l2)) * x1) +
+                        AT((REAL)0.5 * (S(2, l1) * S(3, l2) + S(3, l1) * S(2, l2)) * x2) +
+                        AT(SQRT(S(0, l1) * S(0, l2)) * x3 * R(1, l1) * R(1, l2)) +
+                        AT(SQRT(S(1, l1) * S(1, l2)) * x4 * R(0, l1) * R(0, l2)) +
+                        AT(x5 * R(0, l1) * R(0, l2) * R(1, l1) * R(1, l2));
                 } else if (block == 4 || block == 5) {
                     /* TEEE: spectra EEjq, EEjp, TEip, TEiq ; ratios EE_jq, EE_jp */
                     if (block == 4) {
@@ -316,10 +322,10 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                     }
                     REAL x[4];
                     for (int k = 0; k < 4; ++k) x[k] = FN(xi)(W[k], lenW, b2, nmin, nmax, l1, l2, 1);
-                    c = (SQRT(S(0, l1) * S(0, l2)) * (S(2, l1) + S(2, l2)) * x[0] +
-                         SQRT(S(1, l1) * S(1, l2)) * (S(3, l1) + S(3, l2)) * x[1] +
-                         (S(2, l1) + S(2, l2)) * x[2] * R(0, l1) * R(0, l2) +
-                         (S(3, l1) + S(3, l2)) * x[3] * R(1, l1) * R(1, l2)) / 2;
+                    c = (AT(SQRT(S(0, l1) * S(0, l2)) * (S(2, l1) + S(2, l2)) * x[0]) +
+                         AT(SQRT(S(1, l1) * S(1, l2)) * (S(3, l1) + S(3, l2)) * x[1]) +
+                         AT((S(2, l1) + S(2, l2)) * x[2] * R(0, l1) * R(0, l2)) +
+                         AT((S(3, l1) + S(3, l2)) * x[3] * R(1, l1) * R(1, l2))) / 2;
                 } else {
                     /* TTEE: spectra TEip, TEiq, TEjq, TEjp */
                     n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
@@ -327,10 +333,11 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                     terms += n;
                     REAL x1 = FN(xi)(W[0], lenW, b0, nmin, nmax, l1, l2, 0);
                     REAL x2 = FN(xi)(W[1], lenW, b0, nmin, nmax, l1, l2, 0);
-                    c = ((S(0, l1) * S(2, l2) + S(2, l1) * S(0, l2)) * x1 +
-                         (S(1, l1) * S(3, l2) + S(3, l1) * S(1, l2)) * x2) / 2;
+                    c = (AT((S(0, l1) * S(2, l2) + S(2, l1) * S(0, l2)) * x1) +
+                         AT((S(1, l1) * S(3, l2) + S(3, l1) * S(1, l2)) * x2)) / 2;
                 }
 #undef S
+#undef AT
 #undef R
                 C[(long)(l1 - lmin) + (long)(l2 - lmin) * ld] = (double)c;
                 C[(long)(l2 - lmin) + (long)(l1 - lmin) * ld] = (double)c;

@@ -6,12 +6,16 @@
 #include "../../include/psb200.h"
 #include "psb200_common.cuh"
 #include "psb200_pair_v1.cuh"
+#include "psb200_pair_v2.cuh"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+#include <map>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -108,12 +112,100 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 // ---------------------------------------------------------------------------------------
 int kernel_version()
 {
-    static int v = [] {
-        const char* e = getenv("PSB200_KERNEL");
-        if (e && strcmp(e, "v2") == 0) return 2;
-        return 1;
-    }();
-    return v;
+    // read on every call so a test can switch kernels inside one process
+    const char* e = getenv("PSB200_KERNEL");
+    return (e && strcmp(e, "v1") == 0) ? 1 : 2;
+}
+
+// ---------------------------------------------------------------------------------------
+// v2 support: per-device constant tables, cached block lists, per-call W' buffer
+// ---------------------------------------------------------------------------------------
+struct DevTables {
+    int lmax = -1;
+    int nS = 0;
+    double *S = nullptr, *IS = nullptr, *INV = nullptr, *gam = nullptr;
+};
+DevTables g_tables[16];
+std::mutex g_tab_mutex;
+
+int ensure_tables(int dev, int lmax, DevTables** out)
+{
+    std::lock_guard<std::mutex> lk(g_tab_mutex);
+    DevTables& t = g_tables[dev];
+    if (t.lmax >= lmax) { *out = &t; return OK; }
+    const int want = std::max(lmax, 1024);
+    const int nS = 4 * want + 4096;
+    const int ng = want + 2;
+    std::vector<double> S(nS), IS(nS), INV(nS), G(ng);
+    for (int n = 0; n < nS; ++n) {
+        const long double r = sqrtl((long double)n);
+        S[n] = (double)r;
+        IS[n] = n ? (double)(1.0L / r) : 0.0;
+        INV[n] = n ? (double)(1.0L / (long double)n) : 0.0;
+    }
+    long double g = 1.0L;                       // binom(2n,n)/4^n = prod (2i-1)/(2i)
+    G[0] = 1.0;
+    for (int n = 1; n < ng; ++n) { g *= (long double)(2 * n - 1) / (long double)(2 * n); G[n] = (double)g; }
+    if (t.S) {                                   // growing: nothing may still be reading the old tables
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(t.S); cudaFree(t.IS); cudaFree(t.INV); cudaFree(t.gam);
+        t = DevTables{};
+    }
+    CUDA_TRY(cudaMalloc(&t.S, nS * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.IS, nS * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.INV, nS * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.gam, ng * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(t.S, S.data(), nS * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.IS, IS.data(), nS * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.INV, INV.data(), nS * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.gam, G.data(), ng * sizeof(double), cudaMemcpyHostToDevice));
+    t.lmax = want; t.nS = nS;
+    *out = &t;
+    return OK;
+}
+
+// Block list of one launch: (l1, d_lo) tiles of the band's upper triangle, heaviest first
+// (longest-processing-time order keeps the 148 SMs balanced to the last wave).
+struct BlockList { int2* d = nullptr; int n = 0; unsigned long stamp = 0; };
+typedef std::tuple<int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi
+std::map<BlockKey, BlockList> g_blocks;
+unsigned long g_block_stamp = 0;
+
+int ensure_blocks(int dev, const psb::PairArgs& A, BlockList* out)
+{
+    std::lock_guard<std::mutex> lk(g_tab_mutex);
+    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi);
+    auto it = g_blocks.find(key);
+    if (it != g_blocks.end()) { it->second.stamp = ++g_block_stamp; *out = it->second; return OK; }
+    std::vector<std::pair<long, int2>> v;
+    for (int l1 = A.row_lo; l1 < A.row_hi; ++l1) {
+        const int nd = A.lmax - l1 + 1;
+        for (int d_lo = 0; d_lo < nd; d_lo += psb::V2_PB) {
+            const long steps = std::max(0, std::min(psb::V2_SPAN - 1 + 2 * l1, A.lenW - 1 - d_lo) + 1);
+            const long warps = (std::min(nd - d_lo, psb::V2_PB) + psb::V2_SPAN - 1) / psb::V2_SPAN;
+            v.push_back({steps * warps, make_int2(l1, d_lo)});
+        }
+    }
+    std::stable_sort(v.begin(), v.end(), [](const std::pair<long, int2>& a, const std::pair<long, int2>& b) { return a.first > b.first; });
+    std::vector<int2> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = v[i].second;
+    if (g_blocks.size() >= 64) {                 // drop the least recently used list
+        auto old = g_blocks.begin();
+        for (auto jt = g_blocks.begin(); jt != g_blocks.end(); ++jt) if (jt->second.stamp < old->second.stamp) old = jt;
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(old->second.d);
+        g_blocks.erase(old);
+    }
+    BlockList bl;
+    bl.n = (int)h.size();
+    bl.stamp = ++g_block_stamp;
+    if (bl.n) {
+        CUDA_TRY(cudaMalloc(&bl.d, h.size() * sizeof(int2)));
+        CUDA_TRY(cudaMemcpy(bl.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    g_blocks[key] = bl;
+    *out = bl;
+    return OK;
 }
 
 template <int JOB>
@@ -125,10 +217,30 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
         const int maxcols = A.lmax - A.row_lo + 1;
         dim3 grid((maxcols + psb::V1_THREADS - 1) / psb::V1_THREADS, rows);
         psb::pair_kernel_v1<JOB><<<grid, psb::V1_THREADS, 0, st>>>(A);
-    } else {
-        return fail(ERR_ARG, "kernel v2 not built");
+        CUDA_TRY(cudaGetLastError());
+        return OK;
     }
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    DevTables* t = nullptr;
+    if (int rc = ensure_tables(dev, A.lmax, &t)) return rc;
+    BlockList bl;
+    if (int rc = ensure_blocks(dev, A, &bl)) return rc;
+    // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
+    constexpr int nqp = psb::v2_nqp(JOB);
+    const int rows_w = A.lenW + psb::V2_TC + psb::V2_NW * psb::V2_SPAN;
+    double* Wp = nullptr;
+    CUDA_TRY(cudaMallocAsync(&Wp, (size_t)rows_w * nqp * sizeof(double), st));
+    psb::v2_prep_w<<<(rows_w + 255) / 256, 256, 0, st>>>(Wp, rows_w, nqp, psb::job_nw(JOB), A.lenW,
+        A.W[0], A.W[1], A.W[2], A.W[3], A.W[4], A.W[5], A.W[6], A.W[7]);
     CUDA_TRY(cudaGetLastError());
+    psb::V2Tables T{};
+    T.S = t->S; T.IS = t->IS; T.INV = t->INV; T.gam = t->gam; T.nS = t->nS;
+    T.blocks = bl.d; T.Wp = Wp;
+    const int e = psb::launch_pair_v2<JOB>(A, T, bl.n, st);
+    if (e != 0) return fail(ERR_CUDA, "pair kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    CUDA_TRY(cudaFreeAsync(Wp, st));
     return OK;
 }
 

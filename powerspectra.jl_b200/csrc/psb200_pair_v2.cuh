@@ -1,0 +1,338 @@
+// psb200_pair_v2.cuh -- tuned pair kernel for sm_100a (FP64-pipe bound by design).
+//
+// Work decomposition
+//   block  = one l1 row x V2_PB = 512 consecutive d = l2-l1;   thread = R = 4 consecutive d.
+//   All pairs of a warp advance l3 = j in LOCKSTEP (j = tau + d_w, d_w = first d of the warp), so
+//   every window spectrum read W'_q[j] is a warp-uniform shared-memory broadcast and feeds all
+//   pairs with no per-pair loads.  A pair becomes live when j reaches its own jmin = d
+//   (injection of the closed-form start value), and dies by itself at jmax (tables are 0 there).
+//
+// Recurrence (reduced Schulten-Gordon, m1 = 0), t = j-d, m = j+d, L = 2 l1+1:
+//   a(j)^2 = (j^2-d^2)(s^2-j^2) = [t (L-t)] * [m (m+L)]   =>   a(j) = U[t] * V[m]
+//   with PER-ROW one-dimensional tables U[t] = sqrt(t(L-t)) (index falls along a thread's pairs)
+//   and V[m] = sqrt(m(m+L)) (index rises).  f22: f(j+1) = -(4(2j+1) f(j) + a(j) f(j-1)) / a(j+1)
+//   costs 5 FP64 ops per term: no sqrt, no divide.  f00^2 obeys the two-step rational relation
+//   g(j+2) = g(j) a(j+1)^2 / a(j+2)^2 = g(j) RT[t+1] RV[m+1]  (2 ops per two terms).
+//   Tables are staged per chunk of V2_TC steps into shared memory (products of the global
+//   sqrt(n), 1/sqrt(n), 1/n tables) in a layout de-interleaved modulo R so that the one new
+//   value each thread needs per step is a conflict-free 64-bit load; the other R-1 values a
+//   thread's pairs need are the ones its neighbours used one step earlier (register rotation).
+//   W' = (2j+1) W / 4pi is pre-multiplied once per call and staged with cp.async.
+//
+// Normalisation: instead of running the family to jmax and dividing by sum (2j+1) f^2 (what the
+// reference's dependency does), the start value is the closed-form "stretched" symbol
+//   f00(d)^2 = g(d) g(l1) / (g(l2) (2 l2+1)),  g(n) = binom(2n,n) / 4^n,
+//   f22(d)^2 = f00(d)^2 * (l2+1)(l2+2)(l1-1) l1 / ((l2-1) l2 (l1+1)(l1+2)),   same sign,
+// so terms with l3 > lenW-1 (25% of every family at nV = lmax+1) are never evaluated.
+#pragma once
+#include "psb200_common.cuh"
+
+namespace psb {
+
+constexpr int V2_R = 4;                         // pairs per thread
+constexpr int V2_NW = 4;                        // warps per block
+constexpr int V2_TC = 256;                      // steps per staged chunk
+constexpr int V2_THREADS = V2_NW * 32;
+constexpr int V2_SPAN = 32 * V2_R;              // pairs per warp
+constexpr int V2_PB = V2_THREADS * V2_R;        // pairs per block
+constexpr int V2_SZU = V2_TC + V2_SPAN + V2_R;  // falling-index table entries per chunk
+constexpr int V2_SZV = V2_TC + (2 * V2_NW - 1) * V2_SPAN + V2_R;   // rising-index table entries
+constexpr int V2_SZW = V2_TC + (V2_NW - 1) * V2_SPAN;               // W' rows per chunk
+constexpr int V2_SUBU = V2_SZU / V2_R + 1;      // de-interleaved sub-table strides (+1: skew banks)
+constexpr int V2_SUBV = V2_SZV / V2_R + 1;
+
+__host__ __device__ constexpr int v2_nqp(int job) { return (job_nw(job) + 1) & ~1; }   // W' columns (even)
+__host__ __device__ constexpr int v2_ntab(int job) { return job_family(job) == FAM_00 ? 1 : 2; }
+__host__ __device__ constexpr int v2_smem_doubles(int job)
+{
+    return v2_ntab(job) * V2_R * (V2_SUBU + V2_SUBV) + V2_SZW * v2_nqp(job)
+         + V2_PB * (job_family(job) == FAM_02 ? 2 : 1);
+}
+
+struct V2Tables {
+    const double* S;      // sqrt(n)
+    const double* IS;     // 1/sqrt(n), IS[0] = 0
+    const double* INV;    // 1/n, INV[0] = 0
+    const double* gam;    // binom(2n,n)/4^n
+    int nS;
+    const int2* blocks;   // (l1, d_lo), heaviest first
+    const double* Wp;     // [row j][v2_nqp columns] = (2j+1) W_q[j] / 4pi, zero rows past lenW
+};
+
+// W'[j][q] for one call (interleaved so a step's window values are one or a few 128-bit loads)
+__global__ void v2_prep_w(double* __restrict__ Wp, int rows, int nqp, int nw, int lenW,
+                          const double* w0, const double* w1, const double* w2, const double* w3,
+                          const double* w4, const double* w5, const double* w6, const double* w7)
+{
+    const double* W[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rows) return;
+    const double k = (double)(2 * j + 1) * INV_4PI;
+    for (int q = 0; q < nqp; ++q)
+        Wp[(size_t)j * nqp + q] = (q < nw && j < lenW) ? k * W[q][j] : 0.0;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int JOB>
+__global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, const V2Tables T)
+{
+    constexpr int FAM = job_family(JOB);
+    constexpr int NWQ = job_nw(JOB);
+    constexpr int NACC = job_nacc(JOB);
+    constexpr int NQP = v2_nqp(JOB);
+    constexpr int R = V2_R;
+    constexpr int NTAB = v2_ntab(JOB);       // F00: ratio tables only; F22/F02: value + (negated) inverse
+
+    extern __shared__ __align__(16) double smem[];
+    double* shU0 = smem;                                  // falling index: U   | RT
+    double* shU1 = shU0 + (NTAB > 1 ? R * V2_SUBU : 0);   //                -1/U
+    double* shV0 = shU1 + R * V2_SUBU;                    // rising index:  V   | RV
+    double* shV1 = shV0 + (NTAB > 1 ? R * V2_SUBV : 0);   //                1/V
+    double* shW = shV1 + R * V2_SUBV;                     // [V2_SZW][NQP]
+    double* shF = shW + V2_SZW * NQP;                     // start values f22(d) | g(d)
+    double* shH = shF + V2_PB;                            // start values f00(d)     (F02 only)
+
+    const int2 blk = T.blocks[blockIdx.x];
+    const int l1 = blk.x, d_lo = blk.y;
+    const int L = 2 * l1 + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int woff = warp * V2_SPAN;                      // d_w - d_lo
+    const int e = lane * R;
+    const int cV = 2 * woff + e;
+    const int dmax = A.lmax - l1;                         // last valid d of this row
+    const int tau_end = min(V2_SPAN - 1 + 2 * l1, A.lenW - 1 - d_lo);   // block-uniform, may be < 0
+
+    // ---- start values (closed form), one per pair, parked in shared memory ----
+    {
+        const double gl1 = T.gam[l1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int d = d_lo + woff + e + r;
+            double g00 = 0.0, g22 = 0.0;
+            if (d <= dmax) {
+                const int l2 = l1 + d;
+                g00 = T.gam[d] * gl1 / (T.gam[l2] * (double)(2 * l2 + 1));
+                if (l1 >= 2) {
+                    const double num = (double)(l2 + 1) * (double)(l2 + 2) * ((double)(l1 - 1) * (double)l1);
+                    const double den = (double)(l2 - 1) * (double)l2 * ((double)(l1 + 1) * (double)(l1 + 2));
+                    g22 = g00 * (num / den);
+                }
+            }
+            if constexpr (FAM == FAM_00) shF[tid * R + r] = g00;
+            if constexpr (FAM == FAM_22) shF[tid * R + r] = sqrt(g22);
+            if constexpr (FAM == FAM_02) { shF[tid * R + r] = sqrt(g22); shH[tid * R + r] = sqrt(g00); }
+        }
+    }
+
+    // ---- per-pair state ----
+    double f[R], fm[R], b[R], hv[R];
+    double acc[R][NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        f[r] = 0.0; fm[r] = 0.0; b[r] = 0.0; hv[r] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) acc[r][q] = 0.0;
+    }
+    // rotating windows (2R-1 live entries each)
+    double wU0[2 * R - 1], wU1[2 * R - 1], wV0[2 * R - 1], wV1[2 * R - 1];
+#pragma unroll
+    for (int k = 0; k < 2 * R - 1; ++k) { wU0[k] = 0.0; wU1[k] = 0.0; wV0[k] = 0.0; wV1[k] = 0.0; }
+
+    double k4 = 4.0 * (double)(2 * (d_lo + woff) + 1);    // 4 (2j+1) at tau = 0
+    const bool warp_live = (d_lo + woff) <= dmax;
+
+    for (int tau0 = 0; tau0 <= tau_end; tau0 += V2_TC) {
+        __syncthreads();
+        // ================= stage this chunk's tables =================
+        // falling-index tables, entry idx <-> n = tau0 - SPAN + idx  (n = t+1 of the step that uses it)
+        for (int idx = tid; idx < V2_SZU; idx += V2_THREADS) {
+            const int n = tau0 - V2_SPAN + idx;
+            const int pos = (idx % R) * V2_SUBU + idx / R;
+            if constexpr (FAM == FAM_00) {
+                double v = 0.0;
+                if (n >= 1 && n <= L - 2)
+                    v = ((double)n * (double)(L - n)) * (__ldg(T.INV + n + 1) * __ldg(T.INV + (L - n - 1)));
+                shU0[pos] = v;
+            } else {
+                double u = 0.0, iu = 0.0;
+                if (n >= 1 && n <= L - 1) {
+                    u = __ldg(T.S + n) * __ldg(T.S + (L - n));
+                    iu = -(__ldg(T.IS + n) * __ldg(T.IS + (L - n)));
+                }
+                shU0[pos] = u;
+                shU1[pos] = iu;
+            }
+        }
+        // rising-index tables, entry idx <-> m' = tau0 + idx + 2 d_lo  (m' = m+1 of the step that uses it)
+        for (int idx = tid; idx < V2_SZV; idx += V2_THREADS) {
+            const int mp = tau0 + idx + 2 * d_lo;
+            const int pos = (idx % R) * V2_SUBV + idx / R;
+            if constexpr (FAM == FAM_00) {
+                double v = 0.0;
+                if (mp >= 1)
+                    v = ((double)mp * (double)(mp + L)) * (__ldg(T.INV + mp + 1) * __ldg(T.INV + (mp + L + 1)));
+                shV0[pos] = v;
+            } else {
+                double v = 0.0, iv = 0.0;
+                if (mp >= 1) {
+                    v = __ldg(T.S + mp) * __ldg(T.S + (mp + L));
+                    iv = __ldg(T.IS + mp) * __ldg(T.IS + (mp + L));
+                }
+                shV0[pos] = v;
+                shV1[pos] = iv;
+            }
+        }
+        // W' rows j = tau0 + d_lo + row, row < SZW   (16-byte cp.async; rows past lenW are zero)
+        {
+            const double* src = T.Wp + (size_t)(tau0 + d_lo) * NQP;
+            constexpr int NCH = V2_SZW * NQP / 2;
+            for (int c = tid; c < NCH; c += V2_THREADS) cp_async16(shW + 2 * c, src + 2 * c);
+            cp_async_wait_all();
+        }
+        __syncthreads();
+
+        if (!warp_live) continue;            // dead warps only help staging
+
+        if (tau0 == 0) {
+            // prime the carried part of the rising windows (k = 0..R-2 <-> idx = 1 + cV + k)
+#pragma unroll
+            for (int k = 0; k < R - 1; ++k) {
+                const int idx = 1 + cV + k;
+                const int pos = (idx % R) * V2_SUBV + idx / R;
+                wV0[k] = shV0[pos];
+                if constexpr (NTAB > 1) wV1[k] = shV1[pos];
+            }
+        }
+
+        const int tg_end = min(V2_TC, tau_end - tau0 + 1);
+        for (int tg = 0; tg < tg_end; tg += R) {
+            // ---- the R new entries of every window ----
+            {
+                const int bu = (tg - e + V2_SPAN) / R;     // idx = tg + 1 - e + u + SPAN
+                const int bv = (tg + cV) / R + 1;          // idx = tg + cV + R + u
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const int pu = ((1 + u) % R) * V2_SUBU + bu + (1 + u) / R;
+                    const int pv = u * V2_SUBV + bv;
+                    wU0[R - 1 + u] = shU0[pu];
+                    wV0[R - 1 + u] = shV0[pv];
+                    if constexpr (NTAB > 1) { wU1[R - 1 + u] = shU1[pu]; wV1[R - 1 + u] = shV1[pv]; }
+                }
+            }
+            const bool inject = ((tau0 + tg) == e);        // this group holds t = 0 of my pairs
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                // window spectra of this step: warp-uniform broadcast reads
+                double w[NQP];
+                {
+                    const double* wr = shW + (size_t)(tg + s + woff) * NQP;
+#pragma unroll
+                    for (int q = 0; q < NQP; q += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(wr + q);
+                        w[q] = v.x; w[q + 1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const bool even = ((r + s) & 1) == 0;          // parity of l1+l2+l3, static
+                    const int kU = s - r + R - 1, kV = r + s;
+                    if (r == s) {                                   // t == 0 happens at sub-step s == r
+                        if (inject) {
+                            if constexpr (FAM == FAM_00) f[r] = shF[tid * R + r];
+                            else f[r] = shF[tid * R + r];
+                            if constexpr (FAM == FAM_02) hv[r] = shH[tid * R + r];
+                        }
+                    }
+                    if constexpr (FAM == FAM_00) {
+                        // f[r] holds g = f00^2 at even parity steps
+                        if (even) {
+#pragma unroll
+                            for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(f[r], w[q], acc[r][q]);
+                            f[r] *= wU0[kU] * wV0[kV];
+                        }
+                    } else {
+                        const double ee = f[r] * f[r];
+                        if constexpr (JOB == JOB_MPP) { if (even) acc[r][0] = fma(ee, w[0], acc[r][0]); }
+                        else if constexpr (JOB == JOB_MMM) { if (!even) acc[r][0] = fma(ee, w[0], acc[r][0]); }
+                        else if constexpr (JOB == JOB_MPPMMM) {
+                            if (even) acc[r][0] = fma(ee, w[0], acc[r][0]);
+                            else acc[r][1] = fma(ee, w[0], acc[r][1]);
+                        } else if constexpr (JOB == JOB_EEEE || JOB == JOB_TEEEP) {
+                            if (even) {
+#pragma unroll
+                                for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(ee, w[q], acc[r][q]);
+                            }
+                        } else if constexpr (JOB == JOB_M02 || JOB == JOB_TEEE) {
+                            if (even) {
+                                const double pr = hv[r] * f[r];
+#pragma unroll
+                                for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(pr, w[q], acc[r][q]);
+                            }
+                        } else if constexpr (JOB == JOB_TETE) {
+                            if (even) {
+                                const double pr = hv[r] * f[r];
+                                acc[r][0] = fma(pr, w[0], acc[r][0]);
+                                acc[r][1] = fma(hv[r] * hv[r], w[1], acc[r][1]);
+                                acc[r][2] = fma(pr, w[2], acc[r][2]);
+                                acc[r][3] = fma(pr, w[3], acc[r][3]);
+                                acc[r][4] = fma(pr, w[4], acc[r][4]);
+                            }
+                        }
+                        const double an = wU0[kU] * wV0[kV];        // a(j+1)
+                        const double ian = wU1[kU] * wV1[kV];       // -1/a(j+1)
+                        if constexpr (FAM == FAM_02) {
+                            if (!even) hv[r] = (b[r] * hv[r]) * ian;    // f00(j+1) = -a(j) f00(j-1)/a(j+1)
+                        }
+                        const double q2 = fma(k4, f[r], b[r] * fm[r]);
+                        fm[r] = f[r];
+                        f[r] = q2 * ian;
+                        b[r] = an;
+                    }
+                }
+                k4 += 8.0;
+            }
+            // ---- rotate: next group's carried entries ----
+#pragma unroll
+            for (int k = 0; k < R - 1; ++k) {
+                wU0[k] = wU0[k + R]; wV0[k] = wV0[k + R];
+                if constexpr (NTAB > 1) { wU1[k] = wU1[k + R]; wV1[k] = wV1[k + R]; }
+            }
+        }
+    }
+
+    // ---- epilogue: one stored value (two for MPPMMM) per valid pair ----
+    if (!warp_live) return;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int d = d_lo + woff + e + r;
+        if (d <= dmax) epilogue<JOB>(A, l1, l1 + d, acc[r]);
+    }
+}
+
+// host side of one launch; returns a cudaError_t value (0 = ok)
+template <int JOB>
+int launch_pair_v2(const PairArgs& A, const V2Tables& T, int nblocks, cudaStream_t st)
+{
+    constexpr int smem = v2_smem_doubles(JOB) * (int)sizeof(double);
+    static bool attr_done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pair_kernel_v2<JOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done[dev] = true;
+    }
+    if (nblocks > 0) pair_kernel_v2<JOB><<<nblocks, V2_THREADS, smem, st>>>(A, T);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace psb
