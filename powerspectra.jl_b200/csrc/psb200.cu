@@ -9,6 +9,7 @@
 #include "psb200_pair_v2.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -117,6 +118,27 @@ int kernel_version()
     return (e && strcmp(e, "v1") == 0) ? 1 : 2;
 }
 
+// PSB200_TRACE=1: per-phase wall-clock of the host-level calls on stderr (adds stream syncs)
+bool trace_on()
+{
+    const char* e = getenv("PSB200_TRACE");
+    return e && *e && *e != '0';
+}
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(trace_on()), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, int dev, cudaStream_t st)
+    {
+        if (!on) return;
+        cudaSetDevice(dev);
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[psb200] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // v2 support: per-device constant tables, cached block lists, per-call W' buffer
 // ---------------------------------------------------------------------------------------
@@ -208,6 +230,32 @@ int ensure_blocks(int dev, const psb::PairArgs& A, BlockList* out)
     return OK;
 }
 
+// W' scratch: one persistent buffer per (device, stream); reuse on one stream is stream-ordered
+// and therefore safe without synchronisation (and avoids a cudaMallocAsync per call).
+struct WpBuf { double* p = nullptr; size_t cap = 0; unsigned long stamp = 0; };
+std::map<std::pair<int, cudaStream_t>, WpBuf> g_wp;
+
+int wp_reserve(int dev, cudaStream_t st, size_t n, double** out)
+{
+    std::lock_guard<std::mutex> lk(g_tab_mutex);
+    WpBuf& b = g_wp[{dev, st}];
+    b.stamp = ++g_block_stamp;
+    if (b.cap < n) {
+        if (b.p) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        if (g_wp.size() > 32) {                  // forget the stalest stream's buffer
+            auto old = g_wp.end();
+            for (auto it = g_wp.begin(); it != g_wp.end(); ++it)
+                if (&it->second != &b && (old == g_wp.end() || it->second.stamp < old->second.stamp)) old = it;
+            if (old != g_wp.end()) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(old->second.p); g_wp.erase(old); }
+        }
+        const size_t want = n + n / 4;
+        CUDA_TRY(cudaMalloc(&b.p, want * sizeof(double)));
+        b.cap = want;
+    }
+    *out = b.p;
+    return OK;
+}
+
 template <int JOB>
 int launch_job(const psb::PairArgs& A, cudaStream_t st)
 {
@@ -223,6 +271,8 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    Trace tr;
+    tr.mark("  (inputs uploaded)", dev, st);
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, &t)) return rc;
     BlockList bl;
@@ -231,16 +281,18 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     constexpr int nqp = psb::v2_nqp(JOB);
     const int rows_w = A.lenW + psb::V2_TC + psb::V2_NW * psb::V2_SPAN;
     double* Wp = nullptr;
-    CUDA_TRY(cudaMallocAsync(&Wp, (size_t)rows_w * nqp * sizeof(double), st));
+    tr.mark("  tables + block list", dev, st);
+    if (int rc = wp_reserve(dev, st, (size_t)rows_w * nqp, &Wp)) return rc;
     psb::v2_prep_w<<<(rows_w + 255) / 256, 256, 0, st>>>(Wp, rows_w, nqp, psb::job_nw(JOB), A.lenW,
         A.W[0], A.W[1], A.W[2], A.W[3], A.W[4], A.W[5], A.W[6], A.W[7]);
     CUDA_TRY(cudaGetLastError());
+    tr.mark("  prep W' kernel", dev, st);
     psb::V2Tables T{};
     T.S = t->S; T.IS = t->IS; T.INV = t->INV; T.gam = t->gam; T.nS = t->nS;
     T.blocks = bl.d; T.Wp = Wp;
     const int e = psb::launch_pair_v2<JOB>(A, T, bl.n, st);
     if (e != 0) return fail(ERR_CUDA, "pair kernel launch: %s", cudaGetErrorString((cudaError_t)e));
-    CUDA_TRY(cudaFreeAsync(Wp, st));
+    tr.mark("  pair kernel", dev, st);
     return OK;
 }
 
@@ -368,6 +420,7 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0
 
 int run_host_job(const HostJob& hj, int ngpus)
 {
+    Trace tr;
     const int N = hj.lmax - hj.lmin + 1;
     const long ldX = N;
     int cur = 0;
@@ -392,6 +445,7 @@ int run_host_job(const HostJob& hj, int ngpus)
         double* X1 = hj.nout > 1 ? s.X[1] - rowoff * ldX : nullptr;
         if (int rc = run_on_device(hj, g, edges[g], edges[g + 1], X0, X1, ldX)) return rc;
     }
+    tr.mark("alloc + H2D + stage-1 kernels", 0, g_scratch[0].stream);
     // gather the slabs into device 0's matrix over NVLink (peer copies; rows are contiguous)
     for (int g = 1; g < ngpus; ++g) {
         DeviceScratch& s = g_scratch[g];
@@ -408,10 +462,16 @@ int run_host_job(const HostJob& hj, int ngpus)
     // stage 2 + D2H on device 0
     CUDA_TRY(cudaSetDevice(0));
     DeviceScratch& s0 = g_scratch[0];
+    tr.mark("gather", 0, s0.stream);
     for (int o = 0; o < hj.nout; ++o) {
         if (int rc = psb200_finish_dev(s0.X[o], ldX, hj.lmin, hj.lmax, hj.scale, s0.stream)) return rc;
-        CUDA_TRY(cudaMemcpy2DAsync(hj.out[o], hj.ldo * sizeof(double), s0.X[o], ldX * sizeof(double),
-                                   (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost, s0.stream));
+        tr.mark("finish kernel", 0, s0.stream);
+        if (hj.ldo == ldX)
+            CUDA_TRY(cudaMemcpyAsync(hj.out[o], s0.X[o], (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(hj.out[o], hj.ldo * sizeof(double), s0.X[o], ldX * sizeof(double),
+                                       (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost, s0.stream));
+        tr.mark("D2H", 0, s0.stream);
     }
     CUDA_TRY(cudaStreamSynchronize(s0.stream));
     cudaSetDevice(cur);

@@ -1,7 +1,10 @@
 // psb200_pair_v2.cuh -- tuned pair kernel for sm_100a (FP64-pipe bound by design).
 //
 // Work decomposition
-//   block  = one l1 row x V2_PB = 512 consecutive d = l2-l1;   thread = R = 4 consecutive d.
+//   block  = ONE WARP = one l1 row x V2_PB = 128 consecutive d = l2-l1;  thread = R = 4 consecutive d.
+//   (Warp-sized blocks: table staging needs only __syncwarp, so the ~12 resident warps of an SM
+//   drift apart and hide each other's staging latency; ncu showed 9-12% barrier stalls with
+//   4-warp blocks.)
 //   All pairs of a warp advance l3 = j in LOCKSTEP (j = tau + d_w, d_w = first d of the warp), so
 //   every window spectrum read W'_q[j] is a warp-uniform shared-memory broadcast and feeds all
 //   pairs with no per-pair loads.  A pair becomes live when j reaches its own jmin = d
@@ -30,8 +33,8 @@
 namespace psb {
 
 constexpr int V2_R = 4;                         // pairs per thread
-constexpr int V2_NW = 4;                        // warps per block
-constexpr int V2_TC = 256;                      // steps per staged chunk
+constexpr int V2_NW = 1;                        // warps per block: staging is warp-private, no block barriers
+constexpr int V2_TC = 128;                      // steps per staged chunk
 constexpr int V2_THREADS = V2_NW * 32;
 constexpr int V2_SPAN = 32 * V2_R;              // pairs per warp
 constexpr int V2_PB = V2_THREADS * V2_R;        // pairs per block
@@ -46,7 +49,7 @@ __host__ __device__ constexpr int v2_ntab(int job) { return job_family(job) == F
 __host__ __device__ constexpr int v2_smem_doubles(int job)
 {
     return v2_ntab(job) * V2_R * (V2_SUBU + V2_SUBV) + V2_SZW * v2_nqp(job)
-         + V2_PB * (job_family(job) == FAM_02 ? 2 : 1);
+         + V2_PB * (job_family(job) == FAM_02 ? 2 : 1) + 2;
 }
 
 struct V2Tables {
@@ -77,6 +80,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void block_sync()
+{
+    if constexpr (V2_NW == 1) __syncwarp(); else __syncthreads();
+}
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -92,12 +99,12 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
     constexpr int R = V2_R;
     constexpr int NTAB = v2_ntab(JOB);       // F00: ratio tables only; F22/F02: value + (negated) inverse
 
+    // F22/F02 tables hold (value, inverse) pairs so one 128-bit load fetches both; F00 holds ratios.
     extern __shared__ __align__(16) double smem[];
-    double* shU0 = smem;                                  // falling index: U   | RT
-    double* shU1 = shU0 + (NTAB > 1 ? R * V2_SUBU : 0);   //                -1/U
-    double* shV0 = shU1 + R * V2_SUBU;                    // rising index:  V   | RV
-    double* shV1 = shV0 + (NTAB > 1 ? R * V2_SUBV : 0);   //                1/V
-    double* shW = shV1 + R * V2_SUBV;                     // [V2_SZW][NQP]
+    double* shU = smem;                                   // falling index: (U, -1/U) | RT
+    double* shV = shU + NTAB * R * V2_SUBU;               // rising index:  (V, 1/V)  | RV
+    double* shW = shV + NTAB * R * V2_SUBV;               // [V2_SZW][NQP]
+    if ((NTAB * R * (V2_SUBU + V2_SUBV)) & 1) shW += 1;   // keep W' rows 16-byte aligned
     double* shF = shW + V2_SZW * NQP;                     // start values f22(d) | g(d)
     double* shH = shF + V2_PB;                            // start values f00(d)     (F02 only)
 
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
     const bool warp_live = (d_lo + woff) <= dmax;
 
     for (int tau0 = 0; tau0 <= tau_end; tau0 += V2_TC) {
-        __syncthreads();
+        block_sync();
         // ================= stage this chunk's tables =================
         // falling-index tables, entry idx <-> n = tau0 - SPAN + idx  (n = t+1 of the step that uses it)
         for (int idx = tid; idx < V2_SZU; idx += V2_THREADS) {
@@ -161,15 +168,14 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
                 double v = 0.0;
                 if (n >= 1 && n <= L - 2)
                     v = ((double)n * (double)(L - n)) * (__ldg(T.INV + n + 1) * __ldg(T.INV + (L - n - 1)));
-                shU0[pos] = v;
+                shU[pos] = v;
             } else {
                 double u = 0.0, iu = 0.0;
                 if (n >= 1 && n <= L - 1) {
                     u = __ldg(T.S + n) * __ldg(T.S + (L - n));
                     iu = -(__ldg(T.IS + n) * __ldg(T.IS + (L - n)));
                 }
-                shU0[pos] = u;
-                shU1[pos] = iu;
+                reinterpret_cast<double2*>(shU)[pos] = make_double2(u, iu);
             }
         }
         // rising-index tables, entry idx <-> m' = tau0 + idx + 2 d_lo  (m' = m+1 of the step that uses it)
@@ -180,15 +186,14 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
                 double v = 0.0;
                 if (mp >= 1)
                     v = ((double)mp * (double)(mp + L)) * (__ldg(T.INV + mp + 1) * __ldg(T.INV + (mp + L + 1)));
-                shV0[pos] = v;
+                shV[pos] = v;
             } else {
                 double v = 0.0, iv = 0.0;
                 if (mp >= 1) {
                     v = __ldg(T.S + mp) * __ldg(T.S + (mp + L));
                     iv = __ldg(T.IS + mp) * __ldg(T.IS + (mp + L));
                 }
-                shV0[pos] = v;
-                shV1[pos] = iv;
+                reinterpret_cast<double2*>(shV)[pos] = make_double2(v, iv);
             }
         }
         // W' rows j = tau0 + d_lo + row, row < SZW   (16-byte cp.async; rows past lenW are zero)
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
             for (int c = tid; c < NCH; c += V2_THREADS) cp_async16(shW + 2 * c, src + 2 * c);
             cp_async_wait_all();
         }
-        __syncthreads();
+        block_sync();
 
         if (!warp_live) continue;            // dead warps only help staging
 
@@ -208,8 +213,12 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
             for (int k = 0; k < R - 1; ++k) {
                 const int idx = 1 + cV + k;
                 const int pos = (idx % R) * V2_SUBV + idx / R;
-                wV0[k] = shV0[pos];
-                if constexpr (NTAB > 1) wV1[k] = shV1[pos];
+                if constexpr (NTAB > 1) {
+                    const double2 v = reinterpret_cast<const double2*>(shV)[pos];
+                    wV0[k] = v.x; wV1[k] = v.y;
+                } else {
+                    wV0[k] = shV[pos];
+                }
             }
         }
 
@@ -223,9 +232,16 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
                 for (int u = 0; u < R; ++u) {
                     const int pu = ((1 + u) % R) * V2_SUBU + bu + (1 + u) / R;
                     const int pv = u * V2_SUBV + bv;
-                    wU0[R - 1 + u] = shU0[pu];
-                    wV0[R - 1 + u] = shV0[pv];
-                    if constexpr (NTAB > 1) { wU1[R - 1 + u] = shU1[pu]; wV1[R - 1 + u] = shV1[pv]; }
+                    if constexpr (NTAB > 1) {
+                        const double2 a = reinterpret_cast<const double2*>(shU)[pu];
+                        const double2 c = reinterpret_cast<const double2*>(shV)[pv];
+                        wU0[R - 1 + u] = a.x; wU1[R - 1 + u] = a.y;
+                        wV0[R - 1 + u] = c.x; wV1[R - 1 + u] = c.y;
+                    } else {
+                        // f00^2 only ever touches kU odd / kV even (its pairs are live on (r+s) even)
+                        if (((R - 1 + u) & 1) == 1) wU0[R - 1 + u] = shU[pu];
+                        if (((R - 1 + u) & 1) == 0) wV0[R - 1 + u] = shV[pv];
+                    }
                 }
             }
             const bool inject = ((tau0 + tg) == e);        // this group holds t = 0 of my pairs
