@@ -89,8 +89,15 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// Resident warps per SM the register allocation must allow (one warp per block): 16 = 4 per
+// SMSP for the light jobs, 12 = 3 per SMSP for the 8-accumulator covariance jobs.
+__host__ __device__ constexpr int v2_min_blocks(int job)
+{
+    return (job == JOB_EEEE || job == JOB_TETE) ? 12 : (job == JOB_M00 ? 32 : 16);
+}
+
 template <int JOB>
-__global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, const V2Tables T)
+__global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2(const PairArgs A, const V2Tables T)
 {
     constexpr int FAM = job_family(JOB);
     constexpr int NWQ = job_nw(JOB);
@@ -141,11 +148,13 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
     }
 
     // ---- per-pair state ----
-    double f[R], fm[R], b[R], hv[R];
+    // f = f22(j) (or g = f00(j)^2 for FAM_00); p = a(j) f22(j-1); hv = f00 chain (FAM_02 only):
+    // f00(j) on even-parity steps, a(j) f00(j-1) on odd ones.
+    double f[R], p[R], hv[R];
     double acc[R][NACC];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        f[r] = 0.0; fm[r] = 0.0; b[r] = 0.0; hv[r] = 0.0;
+        f[r] = 0.0; p[r] = 0.0; hv[r] = 0.0;
 #pragma unroll
         for (int q = 0; q < NACC; ++q) acc[r][q] = 0.0;
     }
@@ -251,10 +260,14 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
                 double w[NQP];
                 {
                     const double* wr = shW + (size_t)(tg + s + woff) * NQP;
+                    if constexpr (NWQ == 1) {
+                        w[0] = wr[0];
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < NQP; q += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(wr + q);
-                        w[q] = v.x; w[q + 1] = v.y;
+                        for (int q = 0; q < NQP; q += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(wr + q);
+                            w[q] = v.x; w[q + 1] = v.y;
+                        }
                     }
                 }
 #pragma unroll
@@ -306,12 +319,12 @@ __global__ void __launch_bounds__(V2_THREADS) pair_kernel_v2(const PairArgs A, c
                         const double an = wU0[kU] * wV0[kV];        // a(j+1)
                         const double ian = wU1[kU] * wV1[kV];       // -1/a(j+1)
                         if constexpr (FAM == FAM_02) {
-                            if (!even) hv[r] = (b[r] * hv[r]) * ian;    // f00(j+1) = -a(j) f00(j-1)/a(j+1)
+                            // f00(j+2) = -a(j+1) f00(j) / a(j+2): one factor per step
+                            hv[r] *= even ? an : ian;
                         }
-                        const double q2 = fma(k4, f[r], b[r] * fm[r]);
-                        fm[r] = f[r];
+                        const double q2 = fma(k4, f[r], p[r]);     // 4(2j+1) f(j) + a(j) f(j-1)
+                        p[r] = an * f[r];
                         f[r] = q2 * ian;
-                        b[r] = an;
                     }
                 }
                 k4 += 8.0;
