@@ -111,9 +111,11 @@ int psb200_cov_dev(int block, int lmin, int lmax,
 
 int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void* stream);
 
-/* Work-balanced contiguous l1 bands: edges[0..nbands] with edges[0] = lmin,
- * edges[nbands] = lmax+1, equalising sum (2 l1+1)(lmax-l1+1) (the 3j terms of a row). */
-int psb200_band_edges(int lmin, int lmax, int nbands, int* edges);
+/* Work-balanced contiguous l1 bands: edges[0..nbands] with edges[0] = lmin, edges[nbands] = lmax+1.
+ * Row cost = the l3 steps the kernel runs for that row: families truncated at the window length
+ * lenW (pass the nV / lenW of the call); lenW <= 0 balances the reference's full-family count
+ * (2 l1+1)(lmax-l1+1) instead. */
+int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges);
 
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);

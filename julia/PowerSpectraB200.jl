@@ -1,0 +1,132 @@
+# PowerSpectraB200.jl -- drop-in shim: routes PowerSpectra.jl's Wigner-3j inner loops to libpsb200.so.
+#
+#   using PowerSpectra
+#   include("julia/PowerSpectraB200.jl")      # after PowerSpectra is loaded
+#   PowerSpectraB200.enable!("/path/to/libpsb200.so"; ngpus = 1)
+#   M = mcm(:TT, alm1, alm2)                   # unchanged user code; the (l1,l2) loops now run on the GPU
+#
+# What is overridden (method re-definition, same signatures as the reference):
+#   inner_mcm⁰⁰!  inner_mcm⁰²!  inner_mcm⁺⁺!  inner_mcm⁻⁻!          src/modecoupling.jl:78,99,123,143
+#   loop_covTTTT! loop_covEEEE! loop_covTTTE! loop_covTETE!
+#   loop_covTEEE! loop_covTEEE_planck! loop_covTTEE!                 src/covariance.jl:92,153,208,261,337,376,422
+# Everything else -- mcm, coupledcov, CovarianceWorkspace, window_function_W!, SpectralArray, `\`,
+# decouple_covmat, master -- is the reference's own code and keeps running on the host.
+#
+# STATUS: UNTESTED.  No Julia toolchain exists in the build image or on the GPU boxes, so this file
+# has never been executed.  The C ABI it binds is exercised (same argument order, same memory
+# layout) by the ctypes mirror in powerspectra.jl_b200/ and its tests.
+
+module PowerSpectraB200
+
+using PowerSpectra
+import PowerSpectra: SpectralArray, SpectralVector
+
+const LIB = Ref{String}("libpsb200.so")
+const NGPUS = Ref{Cint}(1)
+
+"0-based contiguous x[l], l = 0..lmax (entries below the first stored multipole are never read)."
+function zero_based(x::SpectralVector{Float64}, lmax::Int)
+    out = zeros(Float64, lmax + 1)
+    lo = max(firstindex(x), 0)
+    lastindex(x) >= lmax || throw(ArgumentError("vector ends at l=$(lastindex(x)), need lmax=$lmax"))
+    @inbounds for l in lo:lmax
+        out[l + 1] = x[l]
+    end
+    return out
+end
+
+function check(rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:psb200_last_error, LIB[]), Cstring, ()))
+    rc == 1 ? throw(ArgumentError(msg)) : error("libpsb200 error $rc: $msg")
+end
+
+function mcm_call!(kind::Int, 𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64};
+                   𝐌2::Union{Nothing,SpectralArray{Float64,2}} = nothing)
+    @assert axes(𝐌, 1) == axes(𝐌, 2)
+    lmin, lmax = first(axes(𝐌, 1)), last(axes(𝐌, 1))
+    v = collect(parent(V))                       # V is 0-indexed: SpectralVector(alm2cl(...)[1:lmax+1])
+    P = parent(𝐌)                                # dense column-major N x N
+    p2 = 𝐌2 === nothing ? Ptr{Cdouble}(C_NULL) : pointer(parent(𝐌2))
+    GC.@preserve v P 𝐌2 begin
+        rc = ccall((:psb200_mcm, LIB[]), Cint,
+                   (Cint, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Clong, Ptr{Cdouble}, Cint),
+                   kind, lmin, lmax, v, length(v), P, stride(P, 2), p2, NGPUS[])
+    end
+    check(rc)
+    return 𝐌
+end
+
+function cov_call!(block::Int, 𝐂::SpectralArray{Float64,2}, spectra, ratios, Ws)
+    @assert axes(𝐂, 1) == axes(𝐂, 2)
+    lmin, lmax = first(axes(𝐂, 1)), last(axes(𝐂, 1))
+    sp = [zero_based(s, lmax) for s in spectra]
+    rt = [zero_based(r, lmax) for r in ratios]
+    ws = [collect(parent(w)) for w in Ws]        # 0-indexed, length workspace.lmax + 1
+    lenW = minimum(length, ws)
+    psp, prt, pws = pointer.(sp), pointer.(rt), pointer.(ws)
+    P = parent(𝐂)
+    GC.@preserve sp rt ws psp prt pws P begin
+        rc = ccall((:psb200_cov, LIB[]), Cint,
+                   (Cint, Cint, Cint, Ptr{Ptr{Cdouble}}, Cint, Ptr{Ptr{Cdouble}}, Cint,
+                    Ptr{Ptr{Cdouble}}, Cint, Cint, Ptr{Cdouble}, Clong, Cint),
+                   block, lmin, lmax, psp, length(sp), prt, length(rt), pws, length(ws), lenW,
+                   P, stride(P, 2), NGPUS[])
+    end
+    check(rc)
+    return 𝐂
+end
+
+"""
+    enable!(libpath = "libpsb200.so"; ngpus = 1)
+
+Re-define the inner loops of PowerSpectra to call the B200 library.  `ngpus = 0` uses every
+visible GPU of the box (work-balanced l1 row bands, gathered on GPU 0).
+"""
+function enable!(libpath::AbstractString = "libpsb200.so"; ngpus::Integer = 1)
+    LIB[] = String(libpath)
+    NGPUS[] = Cint(ngpus)
+    ccall((:psb200_device_count, LIB[]), Cint, ()) > 0 ||
+        error("libpsb200: no CUDA device visible (there is no CPU fallback; keep the stock PowerSpectra loops instead)")
+    @eval PowerSpectra begin
+        inner_mcm⁰⁰!(𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64}) = $(mcm_call!)(0, 𝐌, V)
+        inner_mcm⁰²!(𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64}) = $(mcm_call!)(1, 𝐌, V)
+        inner_mcm⁺⁺!(𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64}) = $(mcm_call!)(2, 𝐌, V)
+        inner_mcm⁻⁻!(𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64}) = $(mcm_call!)(3, 𝐌, V)
+
+        loop_covTTTT!(𝐂::SpectralArray{Float64,2}, TTip, TTjq, TTiq, TTjp, r_ip, r_jq, r_iq, r_jp,
+                      W1, W2, W3, W4, W5, W6, W7, W8) =
+            $(cov_call!)(0, 𝐂, (TTip, TTjq, TTiq, TTjp), (r_ip, r_jq, r_iq, r_jp), (W1, W2, W3, W4, W5, W6, W7, W8))
+        loop_covEEEE!(𝐂::SpectralArray{Float64,2}, EEip, EEjq, EEiq, EEjp, r_ip, r_jq, r_iq, r_jp,
+                      W1, W2, W3, W4, W5, W6, W7, W8) =
+            $(cov_call!)(1, 𝐂, (EEip, EEjq, EEiq, EEjp), (r_ip, r_jq, r_iq, r_jp), (W1, W2, W3, W4, W5, W6, W7, W8))
+        loop_covTTTE!(𝐂::SpectralArray{Float64,2}, TTip, TTjp, TEiq, TEjq, r_ip, r_jp, W1, W2, W3, W4) =
+            $(cov_call!)(2, 𝐂, (TTip, TTjp, TEiq, TEjq), (r_ip, r_jp), (W1, W2, W3, W4))
+        loop_covTETE!(𝐂::SpectralArray{Float64,2}, TTip, EEjq, TEiq, TEjp, r_TT_ip, r_PP_jq, W1, W2, W3, W4, W5) =
+            $(cov_call!)(3, 𝐂, (TTip, EEjq, TEiq, TEjp), (r_TT_ip, r_PP_jq), (W1, W2, W3, W4, W5))
+        loop_covTEEE_planck!(𝐂::SpectralArray{Float64,2}, EEjq, EEjp, TEip, TEiq, r_EE_jq, r_EE_jp, W1, W2, W3, W4) =
+            $(cov_call!)(4, 𝐂, (EEjq, EEjp, TEip, TEiq), (r_EE_jq, r_EE_jp), (W1, W2, W3, W4))
+        loop_covTEEE!(𝐂::SpectralArray{Float64,2}, EEjq, EEjp, TEip, TEiq, r_EE_jq, r_EE_jp, W1, W2, W3, W4) =
+            $(cov_call!)(5, 𝐂, (EEjq, EEjp, TEip, TEiq), (r_EE_jq, r_EE_jp), (W1, W2, W3, W4))
+        loop_covTTEE!(𝐂::SpectralArray{Float64,2}, TEip, TEiq, TEjq, TEjp, W1, W2) =
+            $(cov_call!)(6, 𝐂, (TEip, TEiq, TEjq, TEjp), (), (W1, W2))
+    end
+    return nothing
+end
+
+"""
+    mcm_EE_BB_fused(alm₁, alm₂; lmin = 0, lmax = nothing) -> (𝐌⁺⁺, 𝐌⁻⁻)
+
+Optional extra entry point: both spin-2 blocks from ONE evaluation of the (0,-2,2) family
+(`mcm(:EE_BB, ...)` in the reference evaluates it twice, src/modecoupling.jl:213-214).
+"""
+function mcm_EE_BB_fused(alm₁, alm₂; lmin = 0, lmax = nothing)
+    lmax = isnothing(lmax) ? min(alm₁.lmax, alm₂.lmax) : lmax
+    V = SpectralVector(PowerSpectra.alm2cl(alm₁, alm₂)[1:(lmax + 1)])
+    𝐌⁺⁺ = PowerSpectra.spectralzeros(lmin:lmax, lmin:lmax)
+    𝐌⁻⁻ = PowerSpectra.spectralzeros(lmin:lmax, lmin:lmax)
+    mcm_call!(4, 𝐌⁺⁺, V; 𝐌2 = 𝐌⁻⁻)
+    return 𝐌⁺⁺, 𝐌⁻⁻
+end
+
+end # module

@@ -426,7 +426,7 @@ int run_host_job(const HostJob& hj, int ngpus)
     int cur = 0;
     cudaGetDevice(&cur);
     std::vector<int> edges(ngpus + 1);
-    psb200_band_edges(hj.lmin, hj.lmax, ngpus, edges.data());
+    psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, ngpus, edges.data());
 
     // device 0 owns the full matrix; the others own their band slab only
     for (int o = 0; o < hj.nout; ++o)
@@ -489,17 +489,32 @@ const char* psb200_last_error(void) { return g_err.c_str(); }
 const char* psb200_version(void) { return "psb200 0.1 (sm_100a)"; }
 int psb200_device_count(void) { return device_count(); }
 
-int psb200_band_edges(int lmin, int lmax, int nbands, int* edges)
+// Cost of row l1 as the tuned kernel executes it: every pair d = l2-l1 runs l3 from d to
+// min(d + 2 l1, lenW-1) (the family truncated at the window length) plus the warp's start skew.
+static long double row_cost(int l1, int lmax, int lenW)
+{
+    const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
+    if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
+    const long full = std::min<long>(std::max<long>(lenW - n + 1, 0), D + 1);   // pairs with the whole family inside
+    const long last = std::min<long>(D, lenW - 1);               // last pair with any term
+    long double c = (long double)full * n;
+    if (last >= full) {                                          // truncated pairs: lenW - d terms each
+        const long double a = lenW - full, b = lenW - last;
+        c += (a + b) * (last - full + 1) / 2;
+    }
+    return c + (long double)(D + 1) * 32;                        // skew / staging overhead per pair
+}
+
+int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges)
 {
     if (lmin < 0 || lmax < lmin || nbands < 1 || !edges) return fail(ERR_ARG, "band_edges: bad arguments");
-    // cost(l1) = (2 l1+1)(lmax-l1+1): 3j terms of row l1 of the upper triangle
     long double total = 0;
-    for (int l = lmin; l <= lmax; ++l) total += (long double)(2 * l + 1) * (lmax - l + 1);
+    for (int l = lmin; l <= lmax; ++l) total += row_cost(l, lmax, lenW);
     edges[0] = lmin;
     long double run = 0;
     int b = 1;
     for (int l = lmin; l <= lmax && b < nbands; ++l) {
-        run += (long double)(2 * l + 1) * (lmax - l + 1);
+        run += row_cost(l, lmax, lenW);
         while (b < nbands && run >= total * b / nbands) edges[b++] = l + 1;
     }
     while (b <= nbands) edges[b++] = lmax + 1;

@@ -21,9 +21,11 @@ REF_FAMILIES = {"M00": 1, "M02": 2, "Mpp": 1, "Mmm": 1, "Mpp_Mmm": 2,
                 "TTTT": 1, "EEEE": 1, "TTTE": 1, "TETE": 2, "TEEE_planck": 1, "TEEE": 2, "TTEE": 1}
 
 
-def band_edges(lmin: int, lmax: int, nbands: int):
+def band_edges(lmin: int, lmax: int, nbands: int, lenW: int | None = None):
+    """Work-balanced l1 bands; lenW = window length of the call (default lmax+1, what `mcm` passes);
+    lenW = 0 balances the reference's full-family term count instead."""
     e = (C.c_int * (nbands + 1))()
-    _lib.check(_lib.lib().psb200_band_edges(lmin, lmax, nbands, e))
+    _lib.check(_lib.lib().psb200_band_edges(lmin, lmax, lmax + 1 if lenW is None else lenW, nbands, e))
     return list(e)
 
 

@@ -54,13 +54,22 @@ def test_cov_arity_checked(ps):
 def test_band_edges_balance(ps):
     from powerspectra_jl_b200 import device as dev
     for lmin, lmax, nb in [(0, 6143, 8), (2, 767, 4), (0, 12287, 8), (0, 5, 8), (10, 10, 3)]:
-        e = dev.band_edges(lmin, lmax, nb)
+        e = dev.band_edges(lmin, lmax, nb, lenW=0)          # balance the reference's full-family terms
         assert e[0] == lmin and e[-1] == lmax + 1 and len(e) == nb + 1
         assert all(b >= a for a, b in zip(e, e[1:]))
         cost = [dev.terms("M00", lmax, a, b) for a, b in zip(e, e[1:])]
         assert sum(cost) == dev.terms("M00", lmax, lmin, lmax + 1)
         if lmax - lmin > 100 * nb:
             assert max(cost) / (sum(cost) / nb) < 1.02           # row granularity only
+    # default: rows costed as the kernel runs them (l3 truncated at lenW = lmax+1): upper rows are cheap
+    et = dev.band_edges(0, 6143, 2)
+    ef = dev.band_edges(0, 6143, 2, lenW=0)
+    assert et[1] < ef[1]
+    l = np.arange(0, 6144)
+
+    def kcost(a, b):
+        return sum(int(np.minimum(2 * l1 + 1, 6144 - np.arange(0, 6144 - l1)).sum()) for l1 in range(a, b))
+    assert abs(kcost(et[0], et[1]) / kcost(et[1], et[2]) - 1) < 0.03
     assert dev.terms("M00", 6143, 0, 6144) == 77328286720
     assert dev.terms("M00", 767, 0, 768) == 151289984
 
