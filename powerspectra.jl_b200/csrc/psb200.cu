@@ -62,10 +62,11 @@ int device_count()
 //   A[l1,l2] (address l1 + l2*ld)      = scale ? (2 l2+1) x : x
 // 32x32 tiles through shared memory so both sides are coalesced.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finish_kernel(double* __restrict__ X, long ld, int lmin, int N, int scale)
+__global__ void __launch_bounds__(256) finish_kernel(double* __restrict__ X, long ld, int lmin, int N, int scale,
+                                                     int tile_lo)
 {
     __shared__ double tile[32][33];
-    const int bi = blockIdx.y, bj = blockIdx.x;      // tile row (l1) and tile column (l2)
+    const int bi = blockIdx.y + tile_lo, bj = blockIdx.x;      // tile row (l1) and tile column (l2)
     if (bi > bj) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     for (int r = ty; r < 32; r += 8) {
@@ -189,23 +190,28 @@ int ensure_tables(int dev, int lmax, DevTables** out)
 // Block list of one launch: (l1, d_lo) tiles of the band's upper triangle, heaviest first
 // (longest-processing-time order keeps the 148 SMs balanced to the last wave).
 struct BlockList { int2* d = nullptr; int n = 0; unsigned long stamp = 0; };
-typedef std::tuple<int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi
+typedef std::tuple<int, int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi, d stride
 std::map<BlockKey, BlockList> g_blocks;
 unsigned long g_block_stamp = 0;
 
-int ensure_blocks(int dev, const psb::PairArgs& A, BlockList* out)
+int ensure_blocks(int dev, const psb::PairArgs& A, int ds, BlockList* out)
 {
+    // ds = 1: a warp takes 128 consecutive d.  ds = 2 ((0,0,0)-only jobs): 128 d of one parity.
     std::lock_guard<std::mutex> lk(g_tab_mutex);
-    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi);
+    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi, ds);
     auto it = g_blocks.find(key);
     if (it != g_blocks.end()) { it->second.stamp = ++g_block_stamp; *out = it->second; return OK; }
     std::vector<std::pair<long, int2>> v;
     for (int l1 = A.row_lo; l1 < A.row_hi; ++l1) {
         const int nd = A.lmax - l1 + 1;
-        for (int d_lo = 0; d_lo < nd; d_lo += psb::V2_PB) {
-            const long steps = std::max(0, std::min(psb::V2_SPAN - 1 + 2 * l1, A.lenW - 1 - d_lo) + 1);
-            const long warps = (std::min(nd - d_lo, psb::V2_PB) + psb::V2_SPAN - 1) / psb::V2_SPAN;
-            v.push_back({steps * warps, make_int2(l1, d_lo)});
+        for (int base = 0; base < nd; base += ds * psb::V2_PB) {
+            for (int par = 0; par < ds; ++par) {
+                const int d_lo = base + par;
+                if (d_lo >= nd) continue;
+                const long last = A.lenW - 1 - d_lo;
+                const long steps = last < 0 ? 0 : std::min<long>(psb::V2_SPAN - 1 + (2 * l1) / ds, last / ds) + 1;
+                v.push_back({steps, make_int2(l1, d_lo)});
+            }
         }
     }
     std::stable_sort(v.begin(), v.end(), [](const std::pair<long, int2>& a, const std::pair<long, int2>& b) { return a.first > b.first; });
@@ -276,10 +282,10 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, &t)) return rc;
     BlockList bl;
-    if (int rc = ensure_blocks(dev, A, &bl)) return rc;
+    if (int rc = ensure_blocks(dev, A, psb::job_family(JOB) == psb::FAM_00 ? 2 : 1, &bl)) return rc;
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
     constexpr int nqp = psb::v2_nqp(JOB);
-    const int rows_w = A.lenW + psb::V2_TC + psb::V2_NW * psb::V2_SPAN;
+    const int rows_w = A.lenW + 2 * (psb::V2_TC + psb::V2_NW * psb::V2_SPAN);
     double* Wp = nullptr;
     tr.mark("  tables + block list", dev, st);
     if (int rc = wp_reserve(dev, st, (size_t)rows_w * nqp, &Wp)) return rc;
@@ -342,13 +348,19 @@ struct DeviceScratch {
     double* vec = nullptr;      // packed input vectors
     size_t capVec = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // D2H of finished column bands, overlapped with compute
+    cudaEvent_t ev[16] = {};
 };
 DeviceScratch g_scratch[16];
 
 int scratch_reserve(int dev, int which, size_t n)
 {
     DeviceScratch& s = g_scratch[dev];
-    if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!s.stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+        for (auto& e : s.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     if (which < 2) {
         if (s.capX[which] < n) {
             if (s.X[which]) cudaFree(s.X[which]);
@@ -393,7 +405,8 @@ struct HostJob {
     int scale;
 };
 
-int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0, double* X1, long ldX)
+int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0, double* X1, long ldX,
+                  psb::PairArgs* keep = nullptr)
 {
     // Upload the (small) inputs and launch stage 1 for one band on device `dev`.
     CUDA_TRY(cudaSetDevice(dev));
@@ -415,11 +428,75 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0
         else A.rt[k - hj.nW - hj.nsp] = p;
         off += (hj.lens[k] + 3) & ~size_t(3);
     }
+    if (keep) { *keep = A; return OK; }          // caller launches sub-bands itself
     return launch_any(hj.job, A, s.stream);
+}
+
+// Single-GPU pipeline: the band is cut into NSUB cost-balanced sub-bands of rows (edges on 32-row
+// tile boundaries), processed in increasing l1.  After sub-band k and its finish pass, every
+// COLUMN below its upper edge is final (column c needs rows l1 <= c only), so those columns --
+// one contiguous slab of the column-major result -- start their D2H copy on a second stream
+// while sub-band k+1 computes.  Only the last slab's copy is exposed.
+int run_single_pipelined(const HostJob& hj)
+{
+    Trace tr;
+    const int N = hj.lmax - hj.lmin + 1;
+    const long ldX = N;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    CUDA_TRY(cudaSetDevice(0));
+    for (int o = 0; o < hj.nout; ++o)
+        if (int rc = scratch_reserve(0, o, (size_t)N * N)) return rc;
+    DeviceScratch& s0 = g_scratch[0];
+    psb::PairArgs A{};
+    if (int rc = run_on_device(hj, 0, hj.lmin, hj.lmax + 1, s0.X[0], hj.nout > 1 ? s0.X[1] : nullptr, ldX, &A)) return rc;
+    int nsub = N >= 2048 ? 8 : (N >= 512 ? 4 : 1);
+    if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(16, atoi(e)));
+    std::vector<int> edges(nsub + 1);
+    psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, nsub, edges.data());
+    for (int k = 1; k < nsub; ++k)               // interior edges onto tile boundaries (relative to lmin)
+        edges[k] = std::min(hj.lmax + 1, hj.lmin + ((edges[k] - hj.lmin + 16) / 32) * 32);
+    const int nt = (N + 31) / 32;
+    for (int k = 0; k < nsub; ++k) {
+        const int lo = edges[k], hi = edges[k + 1];
+        if (hi <= lo) continue;
+        A.row_lo = lo; A.row_hi = hi;
+        if (int rc = launch_any(hj.job, A, s0.stream)) return rc;
+        const int t_lo = (lo - hj.lmin) / 32, t_hi = (hi - hj.lmin + 31) / 32;
+        for (int o = 0; o < hj.nout; ++o) {
+            finish_kernel<<<dim3(nt, t_hi - t_lo), 256, 0, s0.stream>>>(s0.X[o], ldX, hj.lmin, N, hj.scale, t_lo);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(s0.ev[k], s0.stream));
+    }
+    // All kernels are queued; now the copies (a D2H into pageable memory blocks the host thread
+    // until it is done, which is harmless once nothing is left to launch).
+    for (int k = 0; k < nsub; ++k) {
+        const int lo = edges[k], hi = edges[k + 1];
+        if (hi <= lo) continue;
+        CUDA_TRY(cudaStreamWaitEvent(s0.copy_stream, s0.ev[k], 0));
+        const size_t c0 = (size_t)(lo - hj.lmin), nc = (size_t)(hi - lo);
+        for (int o = 0; o < hj.nout; ++o) {
+            if (hj.ldo == ldX)
+                CUDA_TRY(cudaMemcpyAsync(hj.out[o] + c0 * hj.ldo, s0.X[o] + c0 * ldX, nc * N * sizeof(double),
+                                         cudaMemcpyDeviceToHost, s0.copy_stream));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(hj.out[o] + c0 * hj.ldo, hj.ldo * sizeof(double), s0.X[o] + c0 * ldX,
+                                           ldX * sizeof(double), (size_t)N * sizeof(double), nc,
+                                           cudaMemcpyDeviceToHost, s0.copy_stream));
+        }
+    }
+    tr.mark("sub-band kernels + finish", 0, s0.stream);
+    CUDA_TRY(cudaStreamSynchronize(s0.stream));
+    CUDA_TRY(cudaStreamSynchronize(s0.copy_stream));
+    tr.mark("tail of D2H", 0, s0.copy_stream);
+    cudaSetDevice(cur);
+    return OK;
 }
 
 int run_host_job(const HostJob& hj, int ngpus)
 {
+    if (ngpus == 1) return run_single_pipelined(hj);
     Trace tr;
     const int N = hj.lmax - hj.lmin + 1;
     const long ldX = N;
@@ -568,7 +645,7 @@ int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void*
     if (!dX) return fail(ERR_ARG, "null buffer");
     const int N = lmax - lmin + 1;
     const int nt = (N + 31) / 32;
-    finish_kernel<<<dim3(nt, nt), 256, 0, (cudaStream_t)stream>>>(dX, ldX, lmin, N, scale ? 1 : 0);
+    finish_kernel<<<dim3(nt, nt), 256, 0, (cudaStream_t)stream>>>(dX, ldX, lmin, N, scale ? 1 : 0, 0);
     CUDA_TRY(cudaGetLastError());
     return OK;
 }

@@ -16,6 +16,8 @@
 //   and V[m] = sqrt(m(m+L)) (index rises).  f22: f(j+1) = -(4(2j+1) f(j) + a(j) f(j-1)) / a(j+1)
 //   costs 5 FP64 ops per term: no sqrt, no divide.  f00^2 obeys the two-step rational relation
 //   g(j+2) = g(j) a(j+1)^2 / a(j+2)^2 = g(j) RT[t+1] RV[m+1]  (2 ops per two terms).
+//   For the (0,0,0)-only jobs a warp therefore takes pairs of ONE parity of d (d = d_lo + 2o) and
+//   steps l3 by 2: every pair is live on every step and odd-parity terms are never visited.
 //   Tables are staged per chunk of V2_TC steps into shared memory (products of the global
 //   sqrt(n), 1/sqrt(n), 1/n tables) in a layout de-interleaved modulo R so that the one new
 //   value each thread needs per step is a conflict-free 64-bit load; the other R-1 values a
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     constexpr int NQP = v2_nqp(JOB);
     constexpr int R = V2_R;
     constexpr int NTAB = v2_ntab(JOB);       // F00: ratio tables only; F22/F02: value + (negated) inverse
+    constexpr int DS = (FAM == FAM_00) ? 2 : 1;   // stride of d inside a warp == step of l3
 
     // F22/F02 tables hold (value, inverse) pairs so one 128-bit load fetches both; F00 holds ratios.
     extern __shared__ __align__(16) double smem[];
@@ -123,14 +126,16 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     const int e = lane * R;
     const int cV = 2 * woff + e;
     const int dmax = A.lmax - l1;                         // last valid d of this row
-    const int tau_end = min(V2_SPAN - 1 + 2 * l1, A.lenW - 1 - d_lo);   // block-uniform, may be < 0
+    // last step: the last pair (offset SPAN-1) finishes its family, or the window spectrum ends
+    const int tau_end = (A.lenW - 1 - d_lo < 0) ? -1
+                      : min(V2_SPAN - 1 + (2 * l1) / DS, (A.lenW - 1 - d_lo) / DS);   // block-uniform
 
     // ---- start values (closed form), one per pair, parked in shared memory ----
     {
         const double gl1 = T.gam[l1];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int d = d_lo + woff + e + r;
+            const int d = d_lo + DS * (woff + e + r);
             double g00 = 0.0, g22 = 0.0;
             if (d <= dmax) {
                 const int l2 = l1 + d;
@@ -163,22 +168,25 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
 #pragma unroll
     for (int k = 0; k < 2 * R - 1; ++k) { wU0[k] = 0.0; wU1[k] = 0.0; wV0[k] = 0.0; wV1[k] = 0.0; }
 
-    double k4 = 4.0 * (double)(2 * (d_lo + woff) + 1);    // 4 (2j+1) at tau = 0
-    const bool warp_live = (d_lo + woff) <= dmax;
+    double k4 = 4.0 * (double)(2 * (d_lo + woff) + 1);    // 4 (2j+1) at tau = 0   (DS == 1 jobs only)
+    const bool warp_live = (d_lo + DS * woff) <= dmax;
 
     for (int tau0 = 0; tau0 <= tau_end; tau0 += V2_TC) {
         block_sync();
         // ================= stage this chunk's tables =================
         // falling-index tables, entry idx <-> n = tau0 - SPAN + idx  (n = t+1 of the step that uses it)
         for (int idx = tid; idx < V2_SZU; idx += V2_THREADS) {
-            const int n = tau0 - V2_SPAN + idx;
             const int pos = (idx % R) * V2_SUBU + idx / R;
             if constexpr (FAM == FAM_00) {
+                // ratio a(j+1)^2/a(j+2)^2, falling part at n = t+1.  The windows hand a pair the entry
+                // nu = t/2 + 1 (the "next step" slot), hence n = 2 nu - 1.
+                const int n = 2 * (tau0 - V2_SPAN + idx) - 1;
                 double v = 0.0;
                 if (n >= 1 && n <= L - 2)
                     v = ((double)n * (double)(L - n)) * (__ldg(T.INV + n + 1) * __ldg(T.INV + (L - n - 1)));
                 shU[pos] = v;
             } else {
+                const int n = tau0 - V2_SPAN + idx;
                 double u = 0.0, iu = 0.0;
                 if (n >= 1 && n <= L - 1) {
                     u = __ldg(T.S + n) * __ldg(T.S + (L - n));
@@ -189,14 +197,16 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
         }
         // rising-index tables, entry idx <-> m' = tau0 + idx + 2 d_lo  (m' = m+1 of the step that uses it)
         for (int idx = tid; idx < V2_SZV; idx += V2_THREADS) {
-            const int mp = tau0 + idx + 2 * d_lo;
             const int pos = (idx % R) * V2_SUBV + idx / R;
             if constexpr (FAM == FAM_00) {
+                // rising part at mp = m+1 (m = j + d even); slot mu = m/2 + 1, hence mp = 2 mu - 1
+                const int mp = 2 * (tau0 + idx + d_lo) - 1;
                 double v = 0.0;
                 if (mp >= 1)
                     v = ((double)mp * (double)(mp + L)) * (__ldg(T.INV + mp + 1) * __ldg(T.INV + (mp + L + 1)));
                 shV[pos] = v;
             } else {
+                const int mp = tau0 + idx + 2 * d_lo;
                 double v = 0.0, iv = 0.0;
                 if (mp >= 1) {
                     v = __ldg(T.S + mp) * __ldg(T.S + (mp + L));
@@ -205,11 +215,15 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                 reinterpret_cast<double2*>(shV)[pos] = make_double2(v, iv);
             }
         }
-        // W' rows j = tau0 + d_lo + row, row < SZW   (16-byte cp.async; rows past lenW are zero)
+        // W' rows j = d_lo + DS (tau0 + row), row < SZW   (16-byte cp.async; rows past lenW are zero)
         {
-            const double* src = T.Wp + (size_t)(tau0 + d_lo) * NQP;
-            constexpr int NCH = V2_SZW * NQP / 2;
-            for (int c = tid; c < NCH; c += V2_THREADS) cp_async16(shW + 2 * c, src + 2 * c);
+            const double* src = T.Wp + (size_t)(d_lo + DS * tau0) * NQP;
+            constexpr int CPR = NQP / 2;                    // 16-byte pieces per row
+            constexpr int NCH = V2_SZW * CPR;
+            for (int c = tid; c < NCH; c += V2_THREADS) {
+                const int row = c / CPR, piece = c % CPR;
+                cp_async16(shW + 2 * c, src + (size_t)row * DS * NQP + 2 * piece);
+            }
             cp_async_wait_all();
         }
         block_sync();
@@ -247,9 +261,8 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                         wU0[R - 1 + u] = a.x; wU1[R - 1 + u] = a.y;
                         wV0[R - 1 + u] = c.x; wV1[R - 1 + u] = c.y;
                     } else {
-                        // f00^2 only ever touches kU odd / kV even (its pairs are live on (r+s) even)
-                        if (((R - 1 + u) & 1) == 1) wU0[R - 1 + u] = shU[pu];
-                        if (((R - 1 + u) & 1) == 0) wV0[R - 1 + u] = shV[pv];
+                        wU0[R - 1 + u] = shU[pu];
+                        wV0[R - 1 + u] = shV[pv];
                     }
                 }
             }
@@ -282,12 +295,10 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                         }
                     }
                     if constexpr (FAM == FAM_00) {
-                        // f[r] holds g = f00^2 at even parity steps
-                        if (even) {
+                        // f[r] holds g = f00(j)^2; this warp only visits even-parity j
 #pragma unroll
-                            for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(f[r], w[q], acc[r][q]);
-                            f[r] *= wU0[kU] * wV0[kV];
-                        }
+                        for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(f[r], w[q], acc[r][q]);
+                        f[r] *= wU0[kU] * wV0[kV];
                     } else {
                         const double ee = f[r] * f[r];
                         if constexpr (JOB == JOB_MPP) { if (even) acc[r][0] = fma(ee, w[0], acc[r][0]); }
@@ -342,7 +353,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     if (!warp_live) return;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int d = d_lo + woff + e + r;
+        const int d = d_lo + DS * (woff + e + r);
         if (d <= dmax) epilogue<JOB>(A, l1, l1 + d, acc[r]);
     }
 }
