@@ -505,6 +505,20 @@ int run_host_job(const HostJob& hj, int ngpus)
     std::vector<int> edges(ngpus + 1);
     psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, ngpus, edges.data());
 
+    // direct NVLink peer copies into device 0 (falls back to staged copies if P2P is unavailable)
+    static bool peers_on[16] = {};
+    for (int g = 1; g < ngpus; ++g) {
+        if (peers_on[g]) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, g, 0);
+        if (can) {
+            cudaSetDevice(g);
+            if (cudaDeviceEnablePeerAccess(0, 0) != cudaSuccess) cudaGetLastError();
+            cudaSetDevice(0);
+            if (cudaDeviceEnablePeerAccess(g, 0) != cudaSuccess) cudaGetLastError();
+        }
+        peers_on[g] = true;
+    }
     // device 0 owns the full matrix; the others own their band slab only
     for (int o = 0; o < hj.nout; ++o)
         if (int rc = (cudaSetDevice(0), scratch_reserve(0, o, (size_t)N * N))) return rc;

@@ -149,6 +149,83 @@ def test_mcm_sampled_rows_full_size(ps, oracle, kind):
             assert parity_error(np.where(well, G[r:r + 1, c:], 0), np.where(well, R[r:r + 1, c:], 0)) < TOL, r
 
 
+@pytest.mark.parametrize("kind", [0, 1, 4])
+def test_mcm_config2_lmax3071_sampled(ps, oracle, kind):
+    """BASELINE configs[1]: TT, TE and EE/BB MCMs at nside 1024 (lmax 3071), two distinct masks;
+    every 96th row against the long-double oracle."""
+    from powerspectra_jl_b200 import synthetic as syn
+    lmax = 3071
+    V = syn.mask_spectra(lmax, seeds=(1001, 1002))[(0, 1)]
+    rstep, row0 = 96, 7
+    rows = np.arange(row0, lmax + 1, rstep)
+    okinds = (2, 3) if kind == 4 else (kind,)
+    if kind == 4:
+        ee_bb = ps.mcm("EE_BB", ps.SpectralVector(V))
+        got = [ee_bb.getblock(0, 0).parent, ee_bb.getblock(0, 1).parent]
+    else:
+        got = [ps.mcm("TT" if kind == 0 else "TE", ps.SpectralVector(V)).parent]
+    for G, k in zip(got, okinds):
+        R = oracle.mcm(k, 0, lmax, V, row0=row0, rstep=rstep, ld=True)
+        with oracle.abs_mode():
+            S = oracle.mcm(k, 0, lmax, V, row0=row0, rstep=rstep)
+        sel = np.zeros(lmax + 1, bool)
+        sel[rows] = True
+        Gu, Ru, Su = np.triu(G)[sel][:, 2:], np.triu(R)[sel][:, 2:], np.triu(S)[sel][:, 2:]
+        assert parity_worst(Gu, Ru, Su) <= 1.0
+        well = np.abs(Su) <= 1e3 * np.abs(Ru)
+        assert parity_error(np.where(well, Gu, 0), np.where(well, Ru, 0)) < TOL
+
+
+@pytest.mark.parametrize("chans", [("TT", "TT"), ("EE", "EE"), ("TE", "TE")])
+def test_coupledcov_config3_lmax2508_sampled(ps, oracle, chans):
+    """BASELINE configs[2]: Planck-like TTTT / EEEE / TETE at lmax 2508, lenW = 2509, two fields with a
+    T and a P mask each (4 masks, product-mask window spectra); every 64th row against the oracle."""
+    import powerspectra_jl_b200.covariance as cv
+    lmax = 2508
+    ws, sp, rt = _cov_case(ps, lmax)
+    C = ps.coupledcov(chans[0], chans[1], ws, sp, rt).parent
+    assert np.array_equal(C, C.T)
+    cap = {}
+    real = cv._loop
+    cv._loop = lambda block, Cm, spectra, ratios, Ws, ngpus=1: cap.setdefault("a", (
+        block, [s.zero_based(lmax) for s in spectra], [r.zero_based(lmax) for r in ratios], [w.parent for w in Ws])) and Cm
+    try:
+        getattr(cv, "coupledcov" + chans[0] + chans[1])(ps.spectralzeros(range(0, lmax + 1), range(0, lmax + 1)), ws, sp, rt)
+    finally:
+        cv._loop = real
+    block, S_, R_, W_ = cap["a"]
+    assert all(w.size == lmax + 1 for w in W_)
+    rstep, row0 = 64, 3
+    R = oracle.cov(block, 0, lmax, S_, R_, W_, ld=True, row0=row0, rstep=rstep)
+    with oracle.abs_mode():
+        S = oracle.cov(block, 0, lmax, S_, R_, W_, row0=row0, rstep=rstep)
+    sel = np.zeros(lmax + 1, bool)
+    sel[np.arange(row0, lmax + 1, rstep)] = True
+    lo = 0 if chans == ("TT", "TT") else 2
+    Gu, Ru, Su = np.triu(C)[sel][:, lo:], np.triu(R)[sel][:, lo:], np.triu(S)[sel][:, lo:]
+    assert parity_worst(Gu, Ru, Su) <= 1.0
+    well = np.abs(Su) <= 1e3 * np.abs(Ru)
+    assert parity_error(np.where(well, Gu, 0), np.where(well, Ru, 0)) < TOL
+
+
+def test_host_call_across_two_gpus(ps, oracle):
+    """psb200_mcm / psb200_cov with ngpus = 2 (row bands on two devices of one process, slabs
+    copied to device 0 over NVLink) must equal the one-GPU result bit for bit."""
+    if ps.lib().psb200_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from powerspectra_jl_b200 import synthetic as syn
+    lmax = 700
+    V = syn.mask_spectra(lmax, seeds=(1002, 1003))[(0, 1)]
+    for spec in ("TT", "TE", "EE_BB"):
+        a = ps.mcm(spec, ps.SpectralVector(V), lmin=2, ngpus=1)
+        b = ps.mcm(spec, ps.SpectralVector(V), lmin=2, ngpus=2)
+        assert np.array_equal(a.parent, b.parent), spec
+    ws, sp, rt = _cov_case(ps, 300)
+    a = ps.coupledcov("TE", "TE", ws, sp, rt, ngpus=1)
+    b = ps.coupledcov("TE", "TE", ws, sp, rt, ngpus=0)       # 0 = every visible device
+    assert np.array_equal(a.parent, b.parent)
+
+
 COV_ARGS = {
     # block -> (spectra keys, ratio keys, W keys) in the positional order of the reference signatures
     "TTTT": ([("TT", "i", "p"), ("TT", "j", "q"), ("TT", "i", "q"), ("TT", "j", "p")],
