@@ -71,6 +71,16 @@ enum {
 int psb200_mcm(int kind, int lmin, int lmax, const double* V, int nV,
                double* M, long ldM, double* M2, int ngpus);
 
+/* Optional fused call (not a reference method): everything `master` /
+ * `maskedalm2spectra` asks of `mcm` (src/modecoupling.jl:348-362 -- TT, TE(=TB), ET(=BT),
+ * (EE_BB, EB_BE)) from ONE evaluation of the two families per pair:
+ *   M00    = inner_mcm00!(V_TT)      M02_TP = inner_mcm02!(V_TP)     M02_PT = inner_mcm02!(V_PT)
+ *   Mpp    = inner_mcm++!(V_PP)      Mmm    = inner_mcm--!(V_PP)
+ * V_XY = alm2cl(mask X of map 1, mask Y of map 2)[0..nV-1].  All five outputs N x N, leading dim ldM. */
+int psb200_mcm_master(int lmin, int lmax, const double* V_TT, const double* V_TP, const double* V_PT,
+                      const double* V_PP, int nV, double* M00, double* M02_TP, double* M02_PT,
+                      double* Mpp, double* Mmm, long ldM, int ngpus);
+
 /* Coupled covariance block.  spectra[k], ratios[k]: length >= lmax+1; W[k]: length lenW
  * (reference: workspace.lmax+1, src/workspace.jl:197).  nspec/nratio/nW must equal the
  * block's arity: TTTT/EEEE 4/4/8, TTTE 4/2/4, TETE 4/2/5, TEEE* 4/2/4, TTEE 4/0/2. */
@@ -101,6 +111,11 @@ const char* psb200_version(void);
 int psb200_mcm_dev(int kind, int lmin, int lmax, const double* dV, int nV,
                    double* dX, long ldX, double* dX2,
                    int row_lo, int row_hi, void* stream);
+
+/* dX: host array of the five device outputs in the order M00, M02_TP, M02_PT, Mpp, Mmm */
+int psb200_mcm_master_dev(int lmin, int lmax, const double* dV_TT, const double* dV_TP, const double* dV_PT,
+                          const double* dV_PP, int nV, double* const* dX, long ldX,
+                          int row_lo, int row_hi, void* stream);
 
 int psb200_cov_dev(int block, int lmin, int lmax,
                    const double* const* d_spectra, int nspec,   /* host array of device ptrs */

@@ -129,4 +129,29 @@ function mcm_EE_BB_fused(alm₁, alm₂; lmin = 0, lmax = nothing)
     return 𝐌⁺⁺, 𝐌⁻⁻
 end
 
+"""
+    mcm_master(maskT₁, maskP₁, maskT₂, maskP₂; lmin = 0, lmax = nothing)
+
+Optional extra entry point: every mode-coupling matrix `maskedalm2spectra` asks for
+(src/modecoupling.jl:348-362: TT, TE(=TB), ET(=BT) and the (EE_BB, EB_BE) blocks) from ONE fused
+GPU pass over both 3j families (the reference makes 5 `mcm` calls plus the tuple call, i.e. 11
+family evaluations per pair).  Returns (𝐌⁰⁰, 𝐌⁰²_TP, 𝐌⁰²_PT, 𝐌⁺⁺, 𝐌⁻⁻).
+"""
+function mcm_master(maskT₁, maskP₁, maskT₂, maskP₂; lmin = 0, lmax = nothing)
+    lmax = isnothing(lmax) ? minimum(a.lmax for a in (maskT₁, maskP₁, maskT₂, maskP₂)) : lmax
+    V = [collect(PowerSpectra.alm2cl(a, b)[1:(lmax + 1)]) for (a, b) in
+         ((maskT₁, maskT₂), (maskT₁, maskP₂), (maskP₁, maskT₂), (maskP₁, maskP₂))]
+    out = [PowerSpectra.spectralzeros(lmin:lmax, lmin:lmax) for _ in 1:5]
+    P = parent.(out)
+    GC.@preserve V P begin
+        rc = ccall((:psb200_mcm_master, LIB[]), Cint,
+                   (Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint,
+                    Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Clong, Cint),
+                   lmin, lmax, V[1], V[2], V[3], V[4], lmax + 1,
+                   P[1], P[2], P[3], P[4], P[5], stride(P[1], 2), NGPUS[])
+    end
+    check(rc)
+    return Tuple(out)
+end
+
 end # module

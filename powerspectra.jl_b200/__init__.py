@@ -13,12 +13,12 @@ from .covariance import (ConstantDict, CovarianceWorkspace, coupledcov, coupledc
                          loop_covTEEE, loop_covTEEE_planck, loop_covTETE, loop_covTTEE, loop_covTTTE,
                          loop_covTTTT, window_function_W)
 from .modecoupling import (Alm, alm2cl, inner_mcm00, inner_mcm02, inner_mcmmm, inner_mcmpp,
-                           inner_mcmpp_mcmmm, mcm)
+                           inner_mcmpp_mcmmm, maskedalm2spectra, mcm, mcm_master)
 from .spectral import (BlockSpectralMatrix, SpectralArray, SpectralVector, decouple_covmat, spectralones,
                        spectralzeros)
 
 __all__ = [
-    "mcm", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
+    "mcm", "mcm_master", "maskedalm2spectra", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
     "SpectralArray", "SpectralVector", "BlockSpectralMatrix", "spectralzeros", "spectralones",
     "decouple_covmat", "Alm", "alm2cl", "lib", "LIB_PATH", "PSB200Error",
 ]

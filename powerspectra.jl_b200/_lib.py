@@ -20,6 +20,9 @@ PROTOTYPES = {
     "psb200_mcm": (C.c_int, [C.c_int, C.c_int, C.c_int, DP, C.c_int, DP, C.c_long, DP, C.c_int]),
     "psb200_cov": (C.c_int, [C.c_int, C.c_int, C.c_int, DPP, C.c_int, DPP, C.c_int, DPP, C.c_int, C.c_int,
                              DP, C.c_long, C.c_int]),
+    "psb200_mcm_master": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, DP, C.c_int, DP, DP, DP, DP, DP, C.c_long, C.c_int]),
+    "psb200_mcm_master_dev": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.POINTER(C.c_void_p), C.c_long, C.c_int, C.c_int, C.c_void_p]),
     "psb200_last_error": (C.c_char_p, []),
     "psb200_device_count": (C.c_int, []),
     "psb200_version": (C.c_char_p, []),

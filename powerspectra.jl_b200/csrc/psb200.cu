@@ -318,6 +318,7 @@ int launch_any(int job, const psb::PairArgs& A, cudaStream_t st)
         case JOB_TEEEP: return launch_job<JOB_TEEEP>(A, st);
         case JOB_TEEE: return launch_job<JOB_TEEE>(A, st);
         case JOB_TTEE: return launch_job<JOB_TTEE>(A, st);
+        case JOB_MASTER: return launch_job<JOB_MASTER>(A, st);
     }
     return fail(ERR_ARG, "unknown job %d", job);
 }
@@ -343,8 +344,8 @@ int check_common(int lmin, int lmax, long ld, int row_lo, int row_hi)
 // per-device scratch for the host-level calls (grown on demand, kept between calls)
 // ---------------------------------------------------------------------------------------
 struct DeviceScratch {
-    double* X[2] = {nullptr, nullptr};
-    size_t capX[2] = {0, 0};
+    double* X[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t capX[5] = {0, 0, 0, 0, 0};
     double* vec = nullptr;      // packed input vectors
     size_t capVec = 0;
     cudaStream_t stream = nullptr;
@@ -361,7 +362,7 @@ int scratch_reserve(int dev, int which, size_t n)
         CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
         for (auto& e : s.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    if (which < 2) {
+    if (which < 5) {
         if (s.capX[which] < n) {
             if (s.X[which]) cudaFree(s.X[which]);
             s.X[which] = nullptr; s.capX[which] = 0;
@@ -399,13 +400,13 @@ struct HostJob {
     int nW, nsp, nrt;
     const double* vecs[16];
     size_t lens[16];
-    double* out[2];
+    double* out[5];
     long ldo;
     int nout;
     int scale;
 };
 
-int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0, double* X1, long ldX,
+int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* const* X, long ldX,
                   psb::PairArgs* keep = nullptr)
 {
     // Upload the (small) inputs and launch stage 1 for one band on device `dev`.
@@ -414,11 +415,11 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* X0
     size_t tot = 0;
     const int nv = hj.nW + hj.nsp + hj.nrt;
     for (int k = 0; k < nv; ++k) tot += (hj.lens[k] + 3) & ~size_t(3);
-    if (int rc = scratch_reserve(dev, 2, tot)) return rc;
+    if (int rc = scratch_reserve(dev, 5, tot)) return rc;
     psb::PairArgs A{};
     A.lmin = hj.lmin; A.lmax = hj.lmax; A.lenW = hj.lenW;
     A.row_lo = row_lo; A.row_hi = row_hi; A.ld = ldX;
-    A.out0 = X0; A.out1 = X1;
+    A.out0 = X[0]; A.out1 = X[1]; A.out2 = X[2]; A.out3 = X[3]; A.out4 = X[4];
     size_t off = 0;
     for (int k = 0; k < nv; ++k) {
         CUDA_TRY(cudaMemcpyAsync(s.vec + off, hj.vecs[k], hj.lens[k] * sizeof(double), cudaMemcpyHostToDevice, s.stream));
@@ -449,7 +450,11 @@ int run_single_pipelined(const HostJob& hj)
         if (int rc = scratch_reserve(0, o, (size_t)N * N)) return rc;
     DeviceScratch& s0 = g_scratch[0];
     psb::PairArgs A{};
-    if (int rc = run_on_device(hj, 0, hj.lmin, hj.lmax + 1, s0.X[0], hj.nout > 1 ? s0.X[1] : nullptr, ldX, &A)) return rc;
+    {
+        double* Xs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int o = 0; o < hj.nout; ++o) Xs[o] = s0.X[o];
+        if (int rc = run_on_device(hj, 0, hj.lmin, hj.lmax + 1, Xs, ldX, &A)) return rc;
+    }
     int nsub = N >= 2048 ? 8 : (N >= 512 ? 4 : 1);
     if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(16, atoi(e)));
     std::vector<int> edges(nsub + 1);
@@ -532,9 +537,9 @@ int run_host_job(const HostJob& hj, int ngpus)
     for (int g = 0; g < ngpus; ++g) {
         DeviceScratch& s = g_scratch[g];
         const long rowoff = (g == 0) ? 0 : (long)(edges[g] - hj.lmin);   // slab starts at its first row
-        double* X0 = s.X[0] - rowoff * ldX;
-        double* X1 = hj.nout > 1 ? s.X[1] - rowoff * ldX : nullptr;
-        if (int rc = run_on_device(hj, g, edges[g], edges[g + 1], X0, X1, ldX)) return rc;
+        double* Xs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int o = 0; o < hj.nout; ++o) Xs[o] = s.X[o] - rowoff * ldX;
+        if (int rc = run_on_device(hj, g, edges[g], edges[g + 1], Xs, ldX)) return rc;
     }
     tr.mark("alloc + H2D + stage-1 kernels", 0, g_scratch[0].stream);
     // gather the slabs into device 0's matrix over NVLink (peer copies; rows are contiguous)
@@ -633,6 +638,21 @@ int psb200_mcm_dev(int kind, int lmin, int lmax, const double* dV, int nV, doubl
     return launch_any(kMcmJob[kind], A, (cudaStream_t)stream);
 }
 
+int psb200_mcm_master_dev(int lmin, int lmax, const double* dV_TT, const double* dV_TP, const double* dV_PT,
+                          const double* dV_PP, int nV, double* const* dX, long ldX, int row_lo, int row_hi,
+                          void* stream)
+{
+    if (int rc = check_common(lmin, lmax, ldX, row_lo, row_hi)) return rc;
+    if (!dV_TT || !dV_TP || !dV_PT || !dV_PP || nV < 1 || !dX) return fail(ERR_ARG, "null / empty buffer");
+    for (int o = 0; o < 5; ++o) if (!dX[o]) return fail(ERR_ARG, "output %d is null", o);
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::PairArgs A{};
+    A.lmin = lmin; A.lmax = lmax; A.lenW = nV; A.row_lo = row_lo; A.row_hi = row_hi; A.ld = ldX;
+    A.W[0] = dV_TT; A.W[1] = dV_TP; A.W[2] = dV_PT; A.W[3] = dV_PP;
+    A.out0 = dX[0]; A.out1 = dX[1]; A.out2 = dX[2]; A.out3 = dX[3]; A.out4 = dX[4];
+    return launch_any(psb::JOB_MASTER, A, (cudaStream_t)stream);
+}
+
 int psb200_cov_dev(int block, int lmin, int lmax, const double* const* dsp, int nspec,
                    const double* const* drt, int nratio, const double* const* dW, int nW, int lenW,
                    double* dX, long ldX, int row_lo, int row_hi, void* stream)
@@ -681,6 +701,27 @@ int psb200_mcm(int kind, int lmin, int lmax, const double* V, int nV, double* M,
     hj.vecs[0] = V; hj.lens[0] = (size_t)nV;
     hj.out[0] = M; hj.out[1] = M2; hj.ldo = ldM; hj.nout = kind == 4 ? 2 : 1;
     hj.scale = 1;
+    return run_host_job(hj, ng);
+}
+
+int psb200_mcm_master(int lmin, int lmax, const double* V_TT, const double* V_TP, const double* V_PT,
+                      const double* V_PP, int nV, double* M00, double* M02_TP, double* M02_PT, double* Mpp,
+                      double* Mmm, long ldM, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (int rc = check_common(lmin, lmax, ldM, lmin, lmax + 1)) return rc;
+    if (!V_TT || !V_TP || !V_PT || !V_PP || nV < 1 || !M00 || !M02_TP || !M02_PT || !Mpp || !Mmm)
+        return fail(ERR_ARG, "null / empty buffer");
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    HostJob hj{};
+    hj.job = psb::JOB_MASTER;
+    hj.lmin = lmin; hj.lmax = lmax; hj.lenW = nV;
+    hj.nW = 4; hj.nsp = 0; hj.nrt = 0;
+    const double* Vs[4] = {V_TT, V_TP, V_PT, V_PP};
+    for (int k = 0; k < 4; ++k) { hj.vecs[k] = Vs[k]; hj.lens[k] = (size_t)nV; }
+    hj.out[0] = M00; hj.out[1] = M02_TP; hj.out[2] = M02_PT; hj.out[3] = Mpp; hj.out[4] = Mmm;
+    hj.ldo = ldM; hj.nout = 5; hj.scale = 1;
     return run_host_job(hj, ng);
 }
 

@@ -16,6 +16,7 @@ constexpr double INV_4PI = 0.079577471545947667884441881686257181;
 enum Job : int {
     JOB_M00 = 0, JOB_M02, JOB_MPP, JOB_MMM, JOB_MPPMMM,
     JOB_TTTT, JOB_EEEE, JOB_TTTE, JOB_TETE, JOB_TEEEP, JOB_TEEE, JOB_TTEE,
+    JOB_MASTER,      // M00(W0), M02(W1), M02(W2), M++(W3), M--(W3) from ONE evaluation of f00 and f22
     JOB_COUNT
 };
 
@@ -25,23 +26,27 @@ enum Fam : int { FAM_00 = 0, FAM_22 = 1, FAM_02 = 2 };
 __host__ __device__ constexpr int job_family(int job)
 {
     return (job == JOB_M00 || job == JOB_TTTT || job == JOB_TTTE || job == JOB_TTEE) ? FAM_00
-         : (job == JOB_M02 || job == JOB_TETE || job == JOB_TEEE)                    ? FAM_02
+         : (job == JOB_M02 || job == JOB_TETE || job == JOB_TEEE || job == JOB_MASTER) ? FAM_02
                                                                                      : FAM_22;
 }
 // Number of window spectra the job reads.
 __host__ __device__ constexpr int job_nw(int job)
 {
     return (job == JOB_TTTT || job == JOB_EEEE) ? 8
-         : (job == JOB_TTTE || job == JOB_TEEEP || job == JOB_TEEE) ? 4
+         : (job == JOB_TTTE || job == JOB_TEEEP || job == JOB_TEEE || job == JOB_MASTER) ? 4
          : (job == JOB_TETE) ? 5
          : (job == JOB_TTEE) ? 2 : 1;
 }
 // Number of Xi accumulators the job carries (MPPMMM: one W, two parities).
-__host__ __device__ constexpr int job_nacc(int job) { return job == JOB_MPPMMM ? 2 : job_nw(job); }
+__host__ __device__ constexpr int job_nacc(int job)
+{
+    return job == JOB_MPPMMM ? 2 : (job == JOB_MASTER ? 5 : job_nw(job));
+}
 // Reference-counted families per pair (EE_BB counts the (0,-2,2) family twice).
 __host__ __device__ constexpr int job_ref_families(int job)
 {
-    return (job == JOB_M02 || job == JOB_TETE || job == JOB_TEEE || job == JOB_MPPMMM) ? 2 : 1;
+    // MASTER: what `master` needs as distinct reference calls: TT 1 + TE 2 + ET 2 + EE_BB 2
+    return job == JOB_MASTER ? 7 : (job == JOB_M02 || job == JOB_TETE || job == JOB_TEEE || job == JOB_MPPMMM) ? 2 : 1;
 }
 
 struct PairArgs {
@@ -53,7 +58,10 @@ struct PairArgs {
     const double* sp[4];   // signal spectra, 0-based in l
     const double* rt[4];   // noise ratios
     double* out0;          // X[(l1-lmin)*ld + (l2-lmin)]
-    double* out1;          // second output (MPPMMM only)
+    double* out1;          // second output (MPPMMM, MASTER)
+    double* out2;          // MASTER only
+    double* out3;
+    double* out4;
 };
 
 // Epilogue: combine the Xi of one pair into the stored value.  x[] already holds
@@ -72,6 +80,12 @@ __device__ __forceinline__ void epilogue(const PairArgs& A, int l1, int l2, cons
     } else if constexpr (JOB == JOB_MPPMMM) {
         A.out0[o] = x[0];
         A.out1[o] = x[1];
+    } else if constexpr (JOB == JOB_MASTER) {
+        A.out0[o] = x[0];
+        A.out1[o] = x[1];
+        A.out2[o] = x[2];
+        A.out3[o] = x[3];
+        A.out4[o] = x[4];
     } else if constexpr (JOB == JOB_TTTT || JOB == JOB_EEEE) {
         const double s0a = SP(0, l1), s0b = SP(0, l2), s1a = SP(1, l1), s1b = SP(1, l2);
         const double s2a = SP(2, l1), s2b = SP(2, l2), s3a = SP(3, l1), s3b = SP(3, l2);

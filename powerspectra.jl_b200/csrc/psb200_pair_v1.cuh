@@ -75,11 +75,22 @@ __global__ void __launch_bounds__(V1_THREADS) pair_kernel_v1(const PairArgs A)
             }
         } else {  // FAM_02
             n22 = fma(k, f * f, n22);
+            if constexpr (JOB == JOB_MASTER) {
+                if (inW) {
+                    const double kg = k * (f * f);
+                    if (even) acc[3] = fma(kg, __ldg(A.W[3] + j), acc[3]);
+                    else acc[4] = fma(kg, __ldg(A.W[3] + j), acc[4]);
+                }
+            }
             if (even) {
                 n00 = fma(k, h * h, n00);
                 if (inW) {
                     const double kp = k * (h * f);
-                    if constexpr (JOB == JOB_TETE) {
+                    if constexpr (JOB == JOB_MASTER) {
+                        acc[0] = fma(k * (h * h), __ldg(A.W[0] + j), acc[0]);
+                        acc[1] = fma(kp, __ldg(A.W[1] + j), acc[1]);
+                        acc[2] = fma(kp, __ldg(A.W[2] + j), acc[2]);
+                    } else if constexpr (JOB == JOB_TETE) {
                         acc[0] = fma(kp, __ldg(A.W[0] + j), acc[0]);
                         acc[1] = fma(k * (h * h), __ldg(A.W[1] + j), acc[1]);
                         acc[2] = fma(kp, __ldg(A.W[2] + j), acc[2]);
@@ -129,6 +140,11 @@ __global__ void __launch_bounds__(V1_THREADS) pair_kernel_v1(const PairArgs A)
 #pragma unroll
         for (int q = 0; q < NACC; ++q) x[q] = acc[q] * sc;
         if constexpr (JOB == JOB_TETE) x[1] = acc[1] * (INV_4PI / n00);
+        if constexpr (JOB == JOB_MASTER) {
+            x[0] = acc[0] * (INV_4PI / n00);
+            x[3] = acc[3] * (INV_4PI / n22);
+            x[4] = acc[4] * (INV_4PI / n22);
+        }
     }
     epilogue<JOB>(A, l1, l2, x);
 }

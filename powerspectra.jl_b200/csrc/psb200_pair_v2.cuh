@@ -95,7 +95,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 // SMSP for the light jobs, 12 = 3 per SMSP for the 8-accumulator covariance jobs.
 __host__ __device__ constexpr int v2_min_blocks(int job)
 {
-    return (job == JOB_EEEE || job == JOB_TETE) ? 12 : (job == JOB_M00 ? 32 : 16);
+    return (job == JOB_EEEE || job == JOB_TETE || job == JOB_MASTER) ? 12 : (job == JOB_M00 ? 32 : 16);
 }
 
 template <int JOB>
@@ -316,6 +316,16 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                                 const double pr = hv[r] * f[r];
 #pragma unroll
                                 for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(pr, w[q], acc[r][q]);
+                            }
+                        } else if constexpr (JOB == JOB_MASTER) {
+                            if (even) {
+                                const double pr = hv[r] * f[r];
+                                acc[r][0] = fma(hv[r] * hv[r], w[0], acc[r][0]);
+                                acc[r][1] = fma(pr, w[1], acc[r][1]);
+                                acc[r][2] = fma(pr, w[2], acc[r][2]);
+                                acc[r][3] = fma(ee, w[3], acc[r][3]);
+                            } else {
+                                acc[r][4] = fma(ee, w[3], acc[r][4]);
                             }
                         } else if constexpr (JOB == JOB_TETE) {
                             if (even) {

@@ -17,7 +17,7 @@ from . import _lib
 
 MCM_KINDS = {"M00": 0, "M02": 1, "Mpp": 2, "Mmm": 3, "Mpp_Mmm": 4}
 COV_BLOCKS = {"TTTT": 0, "EEEE": 1, "TTTE": 2, "TETE": 3, "TEEE_planck": 4, "TEEE": 5, "TTEE": 6}
-REF_FAMILIES = {"M00": 1, "M02": 2, "Mpp": 1, "Mmm": 1, "Mpp_Mmm": 2,
+REF_FAMILIES = {"master": 7, "M00": 1, "M02": 2, "Mpp": 1, "Mmm": 1, "Mpp_Mmm": 2,
                 "TTTT": 1, "EEEE": 1, "TTTE": 1, "TETE": 2, "TEEE_planck": 1, "TEEE": 2, "TTEE": 1}
 
 
@@ -67,6 +67,19 @@ def mcm_slab(kind, lmin, lmax, V: torch.Tensor, X: torch.Tensor, X2: torch.Tenso
         x2 = C.c_void_p(X2.data_ptr())
     rc = _lib.lib().psb200_mcm_dev(kind, lmin, lmax, C.c_void_p(V.data_ptr()), V.numel(),
                                    C.c_void_p(X.data_ptr()), N, x2, row_lo, row_hi, _stream_ptr())
+    _lib.check(rc)
+
+
+def master_slab(lmin, lmax, V_TT, V_TP, V_PT, V_PP, Xs, row_lo=None, row_hi=None):
+    """Fused stage 1 of psb200_mcm_master_dev: Xs = five (N, N) buffers M00, M02_TP, M02_PT, Mpp, Mmm."""
+    N = lmax - lmin + 1
+    row_lo = lmin if row_lo is None else row_lo
+    row_hi = lmax + 1 if row_hi is None else row_hi
+    for t in (V_TT, V_TP, V_PT, V_PP, *Xs):
+        _require_cuda(t)
+    rc = _lib.lib().psb200_mcm_master_dev(lmin, lmax, C.c_void_p(V_TT.data_ptr()), C.c_void_p(V_TP.data_ptr()),
+                                          C.c_void_p(V_PT.data_ptr()), C.c_void_p(V_PP.data_ptr()), V_TT.numel(),
+                                          _vptrs(Xs), N, row_lo, row_hi, _stream_ptr())
     _lib.check(rc)
 
 

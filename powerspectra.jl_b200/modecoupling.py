@@ -97,6 +97,46 @@ def inner_mcmpp_mcmmm(Mpp, Mmm, V, ngpus=1):
     return Mpp, Mmm
 
 
+def mcm_master(maskT1, maskP1, maskT2, maskP2, *, lmin=0, lmax=None, ngpus=1):
+    """All mode-coupling matrices `master` needs (src/modecoupling.jl:339-377) in one fused GPU pass:
+    returns dict TT, TE (= TB), ET (= BT) -> SpectralArray and EE_BB, EB_BE -> BlockSpectralMatrix.
+    Arguments are the mask Alm's of the two maps (T and P mask each)."""
+    if lmax is None:
+        lmax = min(a.lmax for a in (maskT1, maskP1, maskT2, maskP2))
+    V = [np.ascontiguousarray(alm2cl(a, b)[: lmax + 1]) for a, b in
+         ((maskT1, maskT2), (maskT1, maskP2), (maskP1, maskT2), (maskP1, maskP2))]
+    r = range(lmin, lmax + 1)
+    out = [spectralzeros(r, r) for _ in range(5)]
+    N = lmax - lmin + 1
+    rc = _lib.lib().psb200_mcm_master(lmin, lmax, _dp(V[0]), _dp(V[1]), _dp(V[2]), _dp(V[3]), lmax + 1,
+                                      *[_dp(o.parent) for o in out], N, ngpus)
+    _lib.check(rc)
+    M00, M02tp, M02pt, Mpp, Mmm = out
+    neg = SpectralArray(-Mmm.parent, Mmm.offsets)
+    return {"TT": M00, "TE": M02tp, "TB": M02tp, "ET": M02pt, "BT": M02pt,
+            "EE_BB": BlockSpectralMatrix([[Mpp, Mmm], [Mmm, Mpp]]),
+            "EB_BE": BlockSpectralMatrix([[Mpp, neg], [neg, Mpp]])}
+
+
+def maskedalm2spectra(maskedmap1, maskT1, maskP1, maskedmap2, maskT2, maskP2, *, lmin=0, ngpus=1):
+    """Decoupled TT, TE, ET, TB, BT, EE, BB, EB, BE spectra from the alms of the masked maps
+    (T, E, B triples) and of the masks (src/modecoupling.jl:339-377).  The mode-coupling
+    matrices come from the fused GPU pass; alm2cl and the LU solves stay on the host."""
+    M = mcm_master(maskT1, maskP1, maskT2, maskP2, lmin=lmin, ngpus=ngpus)
+    a1 = dict(zip("TEB", maskedmap1))
+    a2 = dict(zip("TEB", maskedmap2))
+    lmax = M["TT"].lastindex(0)
+
+    def pcl(x, y):
+        return SpectralVector(alm2cl(a1[x], a2[y])[lmin: lmax + 1], lmin)
+    spectra = {}
+    for x, y in (("T", "T"), ("T", "E"), ("E", "T"), ("T", "B"), ("B", "T")):
+        spectra[x + y] = M[x + y].solve(pcl(x, y))
+    spectra["EE"], spectra["BB"] = M["EE_BB"].solve([pcl("E", "E"), pcl("B", "B")])
+    spectra["EB"], spectra["BE"] = M["EB_BE"].solve([pcl("E", "B"), pcl("B", "E")])
+    return spectra
+
+
 def _mask_spectrum(alm1, alm2, lmax):
     if isinstance(alm1, SpectralArray) and alm2 is None:      # already a cross-spectrum V
         if lmax is None:

@@ -407,6 +407,41 @@ def test_simple_kernel_cross_check(ps, oracle, monkeypatch):
         assert parity_worst(A, B, S) <= 1.0, chans
 
 
+def test_fused_master_call(ps, oracle):
+    """psb200_mcm_master: the five matrices `master` needs from one pass over both families must
+    equal the separate calls (and the oracle), and the decoupling built on them must invert it."""
+    from powerspectra_jl_b200 import synthetic as syn
+    lmax, lmin = 500, 2
+    sky = syn.ZonalSky(lmax)
+    al = sky.al0([syn.mask_profile(sky.theta, s) for s in (1001, 1002, 1003, 1004)])
+    mT1, mP1, mT2, mP2 = [ps.Alm.zonal(a) for a in al]
+    M = ps.mcm_master(mT1, mP1, mT2, mP2, lmin=lmin)
+    for key, spec, kind, a, b in (("TT", "TT", 0, mT1, mT2), ("TE", "TE", 1, mT1, mP2), ("ET", "ET", 1, mP1, mT2)):
+        Vk = ps.alm2cl(a, b)
+        with oracle.abs_mode():
+            S = oracle.mcm(kind, lmin, lmax, Vk)
+        assert_parity(M[key].parent, oracle.mcm(kind, lmin, lmax, Vk, ld=True), S)
+        # the fused pass uses the signed f00 chain where `mcm(:TT)` uses the squared recurrence:
+        # same numbers to rounding, not bit for bit
+        assert parity_worst(M[key].parent, ps.mcm(spec, a, b, lmin=lmin).parent, S) <= 1.0, key
+    both = ps.mcm("EE_BB", mP1, mP2, lmin=lmin)
+    # same kernels, different accumulator set: agreement to rounding of the shared recurrence
+    V = ps.alm2cl(mP1, mP2)
+    with oracle.abs_mode():
+        Sp, Sm = oracle.mcm(2, lmin, lmax, V), oracle.mcm(3, lmin, lmax, V)
+    assert_parity(M["EE_BB"].getblock(0, 0).parent, oracle.mcm(2, lmin, lmax, V, ld=True), Sp)
+    assert_parity(M["EE_BB"].getblock(0, 1).parent, oracle.mcm(3, lmin, lmax, V, ld=True), Sm)
+    assert parity_worst(M["EE_BB"].getblock(0, 0).parent, both.getblock(0, 0).parent, Sp) <= 1.0
+    assert np.array_equal(M["EB_BE"].getblock(0, 1).parent, -M["EE_BB"].getblock(0, 1).parent)
+    # round trip: couple known spectra with the matrices, decouple with maskedalm2spectra's solves
+    rng = np.random.default_rng(2)
+    cl = {k: rng.uniform(0.5, 1.5, size=lmax + 1 - lmin) for k in ("TT", "TE", "EE", "BB")}
+    assert np.allclose(M["TT"].solve(ps.SpectralVector(M["TT"].parent @ cl["TT"], lmin)).parent, cl["TT"], rtol=1e-9)
+    pEE = M["EE_BB"].parent @ np.concatenate([cl["EE"], cl["BB"]])
+    ee, bb = M["EE_BB"].solve(pEE)
+    assert np.allclose(ee.parent, cl["EE"], rtol=1e-8) and np.allclose(bb.parent, cl["BB"], rtol=1e-8)
+
+
 def test_error_codes(ps):
     lib = ps.lib()
     V = np.ones(8)
