@@ -95,6 +95,24 @@ def test_mcm_edge_shapes(ps, oracle, lmin, lmax, nV):
             assert_parity(M[:N], R, S, lo=lo)
 
 
+@pytest.mark.parametrize("nV", [1, 2, 5, 129, 130, 257, 700])
+def test_short_and_rough_windows(ps, oracle, nV):
+    """Window vectors much shorter than the families (l3 sum truncated early, chunk boundaries of the
+    staged tables at 128/256 steps) and white-noise rough (no smoothness to hide behind)."""
+    lmax = 340
+    rng = np.random.default_rng(nV)
+    V = rng.normal(size=nV)
+    r = range(0, lmax + 1)
+    for kind, fn in ((0, ps.inner_mcm00), (1, ps.inner_mcm02), (2, ps.inner_mcmpp), (3, ps.inner_mcmmm)):
+        M = fn(ps.spectralzeros(r, r), ps.SpectralVector(V)).parent
+        R = oracle.mcm(kind, 0, lmax, V, ld=True)
+        with oracle.abs_mode():
+            S = oracle.mcm(kind, 0, lmax, V)
+        assert_parity(M, R, S, lo=2 if kind else 0)
+        lo = 2 if kind else 0
+        assert np.all(M[lo:, lo:][R[lo:, lo:] == 0.0] == 0.0)      # |l1-l2| > nV-1: empty sum, exact zero
+
+
 def test_mcm_identities_full_size(ps):
     """lmax = 6143 (BASELINE metric size) through size-independent properties."""
     lmax = 6143
