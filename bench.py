@@ -44,6 +44,15 @@ JOBS = [
 ]
 
 
+# From profiles/r01_ncu_final_summary.txt (ncu --set full, 1 GPU, lmax 6143): per-launch DRAM bytes and
+# FP64 pipe activity of each pair kernel.  Quoted next to the live numbers, never used to compute them.
+NCU_R01 = {
+    "M00": {"dram_bytes": 95.8e6, "fp64_pipe_pct": 68.1}, "Mpp_Mmm": {"dram_bytes": 251.7e6, "fp64_pipe_pct": 76.4},
+    "TTTT": {"dram_bytes": 102.6e6, "fp64_pipe_pct": 68.1}, "EEEE": {"dram_bytes": 97.7e6, "fp64_pipe_pct": 71.8},
+    "TETE": {"dram_bytes": 97.3e6, "fp64_pipe_pct": 74.6},
+}
+
+
 def job_flops_per_tfam(job):
     return sum(f * (20 + 2 * n) for f, n in job[4])
 
@@ -120,14 +129,17 @@ def cpu_sample(inp, lmax, rstep, threads=None):
 
 
 def pick_rstep(inp, lmax, target_s):
-    """Probe with a sparse sample, then choose the row stride so one sample costs ~target_s."""
-    probe = 1024 if lmax >= 4096 else 64
-    cpu_sample(inp, lmax, 4 * probe)              # warm the threads / page in the library
-    terms, dt = cpu_sample(inp, lmax, probe)
-    rate = terms / dt
+    """Choose the row stride so one sample costs ~target_s: a sparse probe first (few rows, so the
+    threads are badly balanced and the rate is pessimistic), then a ~3 s probe, then the answer."""
     full_terms = sum(j[3] for j in JOBS) * t_fam(lmax)
-    want = max(1, int(round(full_terms / (rate * target_s))))
-    return max(4, want), rate
+    rstep = 1024 if lmax >= 4096 else 64
+    cpu_sample(inp, lmax, 4 * rstep)              # warm the threads / page in the library
+    rate = None
+    for goal in (3.0, target_s):
+        terms, dt = cpu_sample(inp, lmax, rstep)
+        rate = terms / dt
+        rstep = max(4, int(round(full_terms / (rate * goal))))
+    return rstep, rate
 
 
 def run_reference(args, lmax):
@@ -387,7 +399,11 @@ def run_gpu(args, lmax):
                                         f"(MEASURED_PEAKS.json has no FP64 entry; nominal {NOMINAL_FP64_TFLOPS})",
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                          "flops_model": "F = 20 + 2 n_acc declared flops per 3j term over full families (SURVEY.md 8d)",
-                         "traffic": None,
+                         "fp64_pipe_active_pct_ncu": NCU_R01.get(dom, {}).get("fp64_pipe_pct"),
+                         "traffic": NCU_R01.get(dom, {}).get("dram_bytes") if world == 1 else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full "
+                                         "capture profiles/r01_ncu_final_summary.txt (1 GPU, lmax 6143); algorithmic HBM bytes = "
+                                         "the 8 N^2/2 output bytes (151 MB), part of which is still in L2 at kernel end",
                          "all_kernels": {"declared_tflops": all_flops / (all_kernel_ms * 1e-3) / 1e12,
                                          "ms": mean_ms}},
             "clocks": clocks,
