@@ -364,6 +364,15 @@ def run_gpu(args, lmax):
     if world == 1:
         ms_e2e = wall_e2e                        # blocking host calls: wall clock brackets the whole call
 
+    # per-rank sum of pair-kernel time (band balance evidence)
+    my_ms = torch.tensor([sum(float(np.mean(v)) for v in per_job.values())], dtype=torch.float64, device="cuda")
+    all_ms = [torch.zeros_like(my_ms) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(all_ms, my_ms)
+    else:
+        all_ms = [my_ms]
+    per_rank_ms = [round(float(x.item()), 3) for x in all_ms]
+
     if rank == 0:
         terms_step = sum(j[3] for j in JOBS) * t_fam(lmax)
         ms_step = ms_total / args.steps
@@ -386,6 +395,7 @@ def run_gpu(args, lmax):
             "config": {"workload": f"lmax={lmax}: MCM TT + EE/BB(M++,M--), coupledcov TTTT+EEEE+TETE "
                                    f"(7 reference families x T_fam={t_fam(lmax):.4e} terms per step)",
                        "parallelism": f"l1 row bands x{world}, NCCL gather to rank 0" if world > 1 else "1 GPU",
+                       "band_edges": edges, "pair_kernel_ms_per_rank": per_rank_ms,
                        "l2": "outputs (6 x N^2 x 8 B = 1.8 GB per step) exceed L2; inputs are O(lmax) vectors",
                        "kernel": os.environ.get("PSB200_KERNEL", "default")},
             "gpu_launches": n_launch,

@@ -585,20 +585,20 @@ const char* psb200_last_error(void) { return g_err.c_str(); }
 const char* psb200_version(void) { return "psb200 0.1 (sm_100a)"; }
 int psb200_device_count(void) { return device_count(); }
 
-// Cost of row l1 as the tuned kernel executes it: every pair d = l2-l1 runs l3 from d to
-// min(d + 2 l1, lenW-1) (the family truncated at the window length) plus the warp's start skew.
+// Cost of row l1 as the tuned kernel executes it: one warp-block per 128 consecutive d, each running
+// l3 from its first d to min(d + 2 l1, lenW-1) plus the 127-step start skew of the warp, plus a
+// fixed per-block overhead (start values, first staging, epilogue) worth about 48 steps.
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
-    const long full = std::min<long>(std::max<long>(lenW - n + 1, 0), D + 1);   // pairs with the whole family inside
-    const long last = std::min<long>(D, lenW - 1);               // last pair with any term
-    long double c = (long double)full * n;
-    if (last >= full) {                                          // truncated pairs: lenW - d terms each
-        const long double a = lenW - full, b = lenW - last;
-        c += (a + b) * (last - full + 1) / 2;
+    long double c = 0;
+    for (long d_lo = 0; d_lo <= D; d_lo += psb::V2_PB) {
+        const long last = (long)lenW - 1 - d_lo;
+        const long steps = last < 0 ? 0 : std::min<long>(psb::V2_SPAN - 1 + 2L * l1, last) + 1;
+        c += (long double)(steps + 48);
     }
-    return c + (long double)(D + 1) * 32;                        // skew / staging overhead per pair
+    return c;
 }
 
 int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges)
