@@ -238,8 +238,10 @@ def run_gpu(args, lmax):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")     # host-side waits that must not occupy the GPUs
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
@@ -328,11 +330,33 @@ def run_gpu(args, lmax):
         per_job.setdefault(name, []).append(e0.elapsed_time(e1))
 
     # ---- end to end: host buffers in, host buffers out, through the public entry points ----
-    if world == 1:
-        # the C-ABI host-level calls (what the Julia shim ccalls): pageable numpy in, pinned host out
-        L = ps.lib()
-        DP = ps._lib.DP
-        host_out = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in v] for name, v in outs.items()}
+    # The reference-facing call is the C ABI (psb200_mcm / psb200_cov with HOST buffers and ngpus = N):
+    # one process drives the N GPUs, each GPU copies its own band of the result to the host.  Under
+    # torchrun rank 0 makes that call while the other ranks wait at a barrier (their GPUs are idle).
+    # The one-process-per-GPU driver (H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0)
+    # is timed as well and reported as e2e.per_rank_driver.
+    L = ps.lib()
+    DP = ps._lib.DP
+    ms_driver = None
+    if world > 1:
+        host_out0 = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory() for _ in v]
+                     for name, v in outs.items()} if rank == 0 else None
+
+        def driver_step():
+            d = {k: to_dev(dd) for k, dd in host.items()}
+            compute(d, False, host_dst=host_out0)
+        driver_step()
+        ms_driver = timed(driver_step, max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
+        del host_out0
+
+    e2e_steps = max(1, min(args.steps, 3))
+    wall_e2e = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+    if rank == 0:
+        host_out = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in v]
+                    for name, v in outs.items()}
 
         def ptrs(arrs):
             return (DP * max(len(arrs), 1))(*[a.ctypes.data_as(DP) for a in arrs])
@@ -343,26 +367,20 @@ def run_gpu(args, lmax):
                 O = host_out[name]
                 if api == "mcm":
                     rc = L.psb200_mcm(code, 0, lmax, a["V"].ctypes.data_as(DP), a["V"].size, O[0].ctypes.data_as(DP), N,
-                                      O[1].ctypes.data_as(DP) if len(O) > 1 else None, 1)
+                                      O[1].ctypes.data_as(DP) if len(O) > 1 else None, world)
                 else:
                     rc = L.psb200_cov(code, 0, lmax, ptrs(a["sp"]), len(a["sp"]), ptrs(a["rt"]), len(a["rt"]),
-                                      ptrs(a["W"]), len(a["W"]), a["W"][0].size, O[0].ctypes.data_as(DP), N, 1)
+                                      ptrs(a["W"]), len(a["W"]), a["W"][0].size, O[0].ctypes.data_as(DP), N, world)
                 ps._lib.check(rc)
-    else:
-        host_out0 = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory() for _ in v] for name, v in outs.items()} if rank == 0 else None
-
-        def e2e_step():
-            d = {k: to_dev(dd) for k, dd in host.items()}
-            compute(d, False, host_dst=host_out0)
-
-    e2e_step()                                   # warm-up (allocations inside the library)
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    ms_e2e_ev = timed(e2e_step, e2e_steps)
-    wall_e2e = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(ms_e2e_ev, 0.0)
-    if world == 1:
-        ms_e2e = wall_e2e                        # blocking host calls: wall clock brackets the whole call
+        torch.cuda.synchronize()
+        e2e_step()                                   # warm-up (allocations inside the library)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()                               # blocking host calls: wall clock brackets them
+        wall_e2e = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        dist.barrier(group=cpu_group)               # gloo: the waiting ranks leave their GPUs idle
+    ms_e2e = wall_e2e
 
     # per-rank sum of pair-kernel time (band balance evidence)
     my_ms = torch.tensor([sum(float(np.mean(v)) for v in per_job.values())], dtype=torch.float64, device="cuda")
@@ -401,8 +419,11 @@ def run_gpu(args, lmax):
             "gpu_launches": n_launch,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / e2e_steps,
-                    "path": "psb200_mcm / psb200_cov C-ABI host calls (pinned host outputs)" if world == 1
-                            else "pinned host -> H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0"},
+                    "path": f"psb200_mcm / psb200_cov C-ABI host calls with ngpus={world} (pageable inputs, pinned "
+                            "host outputs; every GPU copies its own band of the result to the host)",
+                    "per_rank_driver": None if ms_driver is None else {
+                        "ms_per_step": ms_driver, "value": terms_step / (ms_driver * 1e-3),
+                        "path": "pinned host -> H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0"}},
             "roofline": {"bound": "fp64", "kernel": f"pair kernel of job {dom}", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "psb200_dfma_peak DFMA microbenchmark measured in this run "

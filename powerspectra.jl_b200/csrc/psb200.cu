@@ -93,6 +93,36 @@ __global__ void __launch_bounds__(256) finish_kernel(double* __restrict__ X, lon
     }
 }
 
+// Band variant of stage 2 for a device that owns rows [a, a+nb) only (slab X, ld doubles per row,
+// X[(l1-a)*ld + (l2-lmin)]).  For the columns to the right of the band's diagonal block
+// (c0 <= l2-lmin < N) it writes T[(l2-lmin-c0)*nb + (l1-a)] = s2 * x  (the block ROW of the result,
+// column-major, ready for a pitched D2H) and, in place, X = s1 * x (the block COLUMN part);
+// s1 = 2 l1+1, s2 = 2 l2+1 for MCM jobs (scale = 1), both 1 for covariance blocks.
+__global__ void __launch_bounds__(256) band_transpose_kernel(double* __restrict__ X, long ld, double* __restrict__ T,
+                                                             int nb, int a, int lmin, int c0, int N, int scale)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, cc0 = c0 + blockIdx.x * 32;     // band-relative row, matrix-relative column
+    for (int r = ty; r < 32; r += 8) {
+        const int i = r0 + r, j = cc0 + tx;
+        double v = 0.0;
+        if (i < nb && j < N) {
+            v = X[(long)i * ld + j];
+            if (scale) X[(long)i * ld + j] = (double)(2 * (a + i) + 1) * v;
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = cc0 + r, i = r0 + tx;
+        if (i < nb && j < N) {
+            const double v = tile[tx][r];
+            T[(long)(j - c0) * nb + i] = scale ? (double)(2 * (lmin + j) + 1) * v : v;
+        }
+    }
+}
+
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double seed)
 {
@@ -348,6 +378,8 @@ struct DeviceScratch {
     size_t capX[5] = {0, 0, 0, 0, 0};
     double* vec = nullptr;      // packed input vectors
     size_t capVec = 0;
+    double* T = nullptr;        // transposed block row of a band (multi-GPU host path)
+    size_t capT = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // D2H of finished column bands, overlapped with compute
     cudaEvent_t ev[16] = {};
@@ -369,12 +401,19 @@ int scratch_reserve(int dev, int which, size_t n)
             CUDA_TRY(cudaMalloc(&s.X[which], n * sizeof(double)));
             s.capX[which] = n;
         }
-    } else {
+    } else if (which == 5) {
         if (s.capVec < n) {
             if (s.vec) cudaFree(s.vec);
             s.vec = nullptr; s.capVec = 0;
             CUDA_TRY(cudaMalloc(&s.vec, n * sizeof(double)));
             s.capVec = n;
+        }
+    } else {
+        if (s.capT < n) {
+            if (s.T) cudaFree(s.T);
+            s.T = nullptr; s.capT = 0;
+            CUDA_TRY(cudaMalloc(&s.T, n * sizeof(double)));
+            s.capT = n;
         }
     }
     return OK;
@@ -499,92 +538,13 @@ int run_single_pipelined(const HostJob& hj)
     return OK;
 }
 
-int run_host_job(const HostJob& hj, int ngpus)
-{
-    if (ngpus == 1) return run_single_pipelined(hj);
-    Trace tr;
-    const int N = hj.lmax - hj.lmin + 1;
-    const long ldX = N;
-    int cur = 0;
-    cudaGetDevice(&cur);
-    std::vector<int> edges(ngpus + 1);
-    psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, ngpus, edges.data());
-
-    // direct NVLink peer copies into device 0 (falls back to staged copies if P2P is unavailable)
-    static bool peers_on[16] = {};
-    for (int g = 1; g < ngpus; ++g) {
-        if (peers_on[g]) continue;
-        int can = 0;
-        cudaDeviceCanAccessPeer(&can, g, 0);
-        if (can) {
-            cudaSetDevice(g);
-            if (cudaDeviceEnablePeerAccess(0, 0) != cudaSuccess) cudaGetLastError();
-            cudaSetDevice(0);
-            if (cudaDeviceEnablePeerAccess(g, 0) != cudaSuccess) cudaGetLastError();
-        }
-        peers_on[g] = true;
-    }
-    // device 0 owns the full matrix; the others own their band slab only
-    for (int o = 0; o < hj.nout; ++o)
-        if (int rc = (cudaSetDevice(0), scratch_reserve(0, o, (size_t)N * N))) return rc;
-    for (int g = 1; g < ngpus; ++g) {
-        const size_t rows = (size_t)(edges[g + 1] - edges[g]);
-        CUDA_TRY(cudaSetDevice(g));
-        for (int o = 0; o < hj.nout; ++o)
-            if (int rc = scratch_reserve(g, o, std::max<size_t>(rows * N, 1))) return rc;
-    }
-    // stage 1 on every device (asynchronous launches, one stream per device)
-    for (int g = 0; g < ngpus; ++g) {
-        DeviceScratch& s = g_scratch[g];
-        const long rowoff = (g == 0) ? 0 : (long)(edges[g] - hj.lmin);   // slab starts at its first row
-        double* Xs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        for (int o = 0; o < hj.nout; ++o) Xs[o] = s.X[o] - rowoff * ldX;
-        if (int rc = run_on_device(hj, g, edges[g], edges[g + 1], Xs, ldX)) return rc;
-    }
-    tr.mark("alloc + H2D + stage-1 kernels", 0, g_scratch[0].stream);
-    // gather the slabs into device 0's matrix over NVLink (peer copies; rows are contiguous)
-    for (int g = 1; g < ngpus; ++g) {
-        DeviceScratch& s = g_scratch[g];
-        CUDA_TRY(cudaSetDevice(g));
-        const size_t rows = (size_t)(edges[g + 1] - edges[g]);
-        for (int o = 0; o < hj.nout && rows; ++o)
-            CUDA_TRY(cudaMemcpyPeerAsync(g_scratch[0].X[o] + (size_t)(edges[g] - hj.lmin) * ldX, 0,
-                                         s.X[o], g, rows * N * sizeof(double), s.stream));
-    }
-    for (int g = 1; g < ngpus; ++g) {
-        CUDA_TRY(cudaSetDevice(g));
-        CUDA_TRY(cudaStreamSynchronize(g_scratch[g].stream));
-    }
-    // stage 2 + D2H on device 0
-    CUDA_TRY(cudaSetDevice(0));
-    DeviceScratch& s0 = g_scratch[0];
-    tr.mark("gather", 0, s0.stream);
-    for (int o = 0; o < hj.nout; ++o) {
-        if (int rc = psb200_finish_dev(s0.X[o], ldX, hj.lmin, hj.lmax, hj.scale, s0.stream)) return rc;
-        tr.mark("finish kernel", 0, s0.stream);
-        if (hj.ldo == ldX)
-            CUDA_TRY(cudaMemcpyAsync(hj.out[o], s0.X[o], (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
-        else
-            CUDA_TRY(cudaMemcpy2DAsync(hj.out[o], hj.ldo * sizeof(double), s0.X[o], ldX * sizeof(double),
-                                       (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost, s0.stream));
-        tr.mark("D2H", 0, s0.stream);
-    }
-    CUDA_TRY(cudaStreamSynchronize(s0.stream));
-    cudaSetDevice(cur);
-    return OK;
-}
-
-}  // namespace
-
-// =========================================================================================
-// C ABI
-// =========================================================================================
-extern "C" {
-
-const char* psb200_last_error(void) { return g_err.c_str(); }
-const char* psb200_version(void) { return "psb200 0.1 (sm_100a)"; }
-int psb200_device_count(void) { return device_count(); }
-
+// Multi-GPU host path.  Every device owns a cost-balanced band of rows [a, b) and delivers, over its
+// OWN PCIe link and straight into the caller's matrix, the two rectangles only it can complete:
+//   block column: columns [a, b), rows [a, lmax]   (incl. the diagonal block, mirrored locally)
+//   block row   : rows [a, b), columns [b, lmax]   (transposed on the device)
+// These tile the matrix exactly once, so no inter-GPU exchange is needed when the result lives in
+// host memory (the NCCL gather to rank 0 belongs to the device-resident driver, device.py / bench.py).
+// One host thread per device keeps the pageable-memory copies of different GPUs concurrent.
 // Cost of row l1 as the tuned kernel executes it: one warp-block per 128 consecutive d, each running
 // l3 from its first d to min(d + 2 l1, lenW-1) plus the 127-step start skew of the warp, plus a
 // fixed per-block overhead (start values, first staging, epilogue) worth about 48 steps.
@@ -600,6 +560,135 @@ static long double row_cost(int l1, int lmax, int lenW)
     }
     return c;
 }
+
+// cost-balanced split of rows [a, b) into at most nsub consecutive pieces
+static std::vector<int> split_rows(int a, int b, int lmax, int lenW, int nsub)
+{
+    std::vector<int> e{a};
+    if (nsub <= 1 || b - a < 2 * nsub) { e.push_back(b); return e; }
+    long double total = 0;
+    for (int l = a; l < b; ++l) total += row_cost(l, lmax, lenW);
+    long double run = 0;
+    int k = 1;
+    for (int l = a; l < b && k < nsub; ++l) {
+        run += row_cost(l, lmax, lenW);
+        if (run >= total * k / nsub) { if (l + 1 > e.back() && l + 1 < b) e.push_back(l + 1); ++k; }
+    }
+    e.push_back(b);
+    return e;
+}
+
+int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
+{
+    auto body = [&]() -> int {
+        const int N = hj.lmax - hj.lmin + 1;
+        const long ldX = N;
+        const int nb = b - a;
+        if (nb <= 0) return OK;
+        CUDA_TRY(cudaSetDevice(g));
+        for (int o = 0; o < hj.nout; ++o)
+            if (int rc = scratch_reserve(g, o, (size_t)nb * N)) return rc;
+        // sub-bands: each is a complete band of its own (L-shaped region), so its copies can start
+        // while the next sub-band computes
+        int nsub = nb >= 2048 ? 4 : (nb >= 512 ? 2 : 1);
+        if (const char* e = getenv("PSB200_NSUB_MULTI")) nsub = std::max(1, std::min(16, atoi(e)));
+        const std::vector<int> sub = split_rows(a, b, hj.lmax, hj.lenW, nsub);
+        const int ns = (int)sub.size() - 1;
+        std::vector<size_t> toff(ns + 1, 0);             // one transposed block row per (sub-band, output)
+        for (int k = 0; k < ns; ++k)
+            toff[k + 1] = toff[k] + (size_t)(sub[k + 1] - sub[k]) * (size_t)(N - (sub[k + 1] - hj.lmin)) * hj.nout;
+        if (toff[ns]) if (int rc = scratch_reserve(g, 6, toff[ns])) return rc;
+        DeviceScratch& s = g_scratch[g];
+        double* Xs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        const long rowoff = (long)(a - hj.lmin);
+        for (int o = 0; o < hj.nout; ++o) Xs[o] = s.X[o] - rowoff * ldX;   // kernels index rows from lmin
+        psb::PairArgs A{};
+        if (int rc = run_on_device(hj, g, a, b, Xs, ldX, &A)) return rc;
+        Trace tr;
+        for (int k = 0; k < ns; ++k) {
+            const int sa = sub[k], sb = sub[k + 1], nbs = sb - sa;
+            A.row_lo = sa; A.row_hi = sb;
+            if (int rc = launch_any(hj.job, A, s.stream)) return rc;
+            const int nt = (nbs + 31) / 32;
+            const int c0 = sb - hj.lmin;                  // first column right of this diagonal block
+            for (int o = 0; o < hj.nout; ++o) {
+                double* slab = s.X[o] + (size_t)(sa - a) * ldX;         // row sa of the slab
+                finish_kernel<<<dim3(nt, nt), 256, 0, s.stream>>>(slab + (sa - hj.lmin), ldX, sa, nbs, hj.scale, 0);
+                CUDA_TRY(cudaGetLastError());
+                if (c0 < N) {
+                    double* Tk = s.T + toff[k] + (size_t)o * nbs * (N - c0);
+                    band_transpose_kernel<<<dim3((N - c0 + 31) / 32, nt), 256, 0, s.stream>>>(
+                        slab, ldX, Tk, nbs, sa, hj.lmin, c0, N, hj.scale);
+                    CUDA_TRY(cudaGetLastError());
+                }
+            }
+            CUDA_TRY(cudaEventRecord(s.ev[k], s.stream));
+        }
+        // everything is queued; now the copies on the second stream (a copy into pageable memory blocks
+        // this host thread, which is harmless once nothing is left to launch)
+        for (int k = 0; k < ns; ++k) {
+            const int sa = sub[k], sb = sub[k + 1], nbs = sb - sa;
+            const int c0 = sb - hj.lmin;
+            const size_t r0 = (size_t)(sa - hj.lmin);
+            CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev[k], 0));
+            for (int o = 0; o < hj.nout; ++o) {
+                const double* slab = s.X[o] + (size_t)(sa - a) * ldX;
+                // block column: nbs columns of (N - r0) rows each
+                CUDA_TRY(cudaMemcpy2DAsync(hj.out[o] + r0 * hj.ldo + r0, hj.ldo * sizeof(double), slab + r0,
+                                           ldX * sizeof(double), (size_t)(N - r0) * sizeof(double), nbs,
+                                           cudaMemcpyDeviceToHost, s.copy_stream));
+                // block row: (N - c0) columns of nbs rows each
+                if (c0 < N) {
+                    const double* Tk = s.T + toff[k] + (size_t)o * nbs * (N - c0);
+                    CUDA_TRY(cudaMemcpy2DAsync(hj.out[o] + (size_t)c0 * hj.ldo + r0, hj.ldo * sizeof(double), Tk,
+                                               (size_t)nbs * sizeof(double), (size_t)nbs * sizeof(double), N - c0,
+                                               cudaMemcpyDeviceToHost, s.copy_stream));
+                }
+            }
+        }
+        tr.mark("   band: kernels + finish + transpose", g, s.stream);
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.copy_stream));
+        tr.mark("   band: tail of D2H", g, s.copy_stream);
+        return OK;
+    };
+    const int rc = body();
+    if (rc != OK && err) *err = g_err;        // g_err is thread-local: hand the message to the caller
+    return rc;
+}
+
+int run_host_job(const HostJob& hj, int ngpus)
+{
+    if (ngpus == 1) return run_single_pipelined(hj);
+    Trace tr;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::vector<int> edges(ngpus + 1);
+    psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, ngpus, edges.data());
+    std::vector<int> rcs(ngpus, OK);
+    std::vector<std::string> errs(ngpus);
+    std::vector<std::thread> th;
+    for (int g = 1; g < ngpus; ++g)
+        th.emplace_back([&, g] { rcs[g] = run_band_on_device(hj, g, edges[g], edges[g + 1], &errs[g]); });
+    rcs[0] = run_band_on_device(hj, 0, edges[0], edges[1], &errs[0]);
+    for (auto& t : th) t.join();
+    tr.mark("all bands delivered", 0, g_scratch[0].stream);
+    cudaSetDevice(cur);
+    for (int g = 0; g < ngpus; ++g)
+        if (rcs[g] != OK) { g_err = "device " + std::to_string(g) + ": " + errs[g]; return rcs[g]; }
+    return OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* psb200_last_error(void) { return g_err.c_str(); }
+const char* psb200_version(void) { return "psb200 0.1 (sm_100a)"; }
+int psb200_device_count(void) { return device_count(); }
 
 int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges)
 {
