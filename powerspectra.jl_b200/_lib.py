@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsb200.so")
+# PSB200_LIB lets a developer A/B another in-tree build of the same library (tools/); default: the product
+LIB_PATH = os.environ.get("PSB200_LIB") or os.path.join(_HERE, "libpsb200.so")
 
 DP = C.POINTER(C.c_double)
 DPP = C.POINTER(DP)

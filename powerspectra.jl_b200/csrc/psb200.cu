@@ -315,7 +315,7 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     if (int rc = ensure_blocks(dev, A, psb::job_family(JOB) == psb::FAM_00 ? 2 : 1, &bl)) return rc;
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
     constexpr int nqp = psb::v2_nqp(JOB);
-    const int rows_w = A.lenW + 2 * (psb::V2_TC + psb::V2_NW * psb::V2_SPAN);
+    const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_NW * psb::V2_SPAN);
     double* Wp = nullptr;
     tr.mark("  tables + block list", dev, st);
     if (int rc = wp_reserve(dev, st, (size_t)rows_w * nqp, &Wp)) return rc;

@@ -36,21 +36,31 @@ namespace psb {
 
 constexpr int V2_R = 4;                         // pairs per thread
 constexpr int V2_NW = 1;                        // warps per block: staging is warp-private, no block barriers
-constexpr int V2_TC = 128;                      // steps per staged chunk
+constexpr int V2_TC_MAX = 256;
+// steps per staged chunk: longer chunks where the W' tile is small (fewer staging events)
+__host__ __device__ constexpr int v2_tc(int job);
 constexpr int V2_THREADS = V2_NW * 32;
 constexpr int V2_SPAN = 32 * V2_R;              // pairs per warp
 constexpr int V2_PB = V2_THREADS * V2_R;        // pairs per block
-constexpr int V2_SZU = V2_TC + V2_SPAN + V2_R;  // falling-index table entries per chunk
-constexpr int V2_SZV = V2_TC + (2 * V2_NW - 1) * V2_SPAN + V2_R;   // rising-index table entries
-constexpr int V2_SZW = V2_TC + (V2_NW - 1) * V2_SPAN;               // W' rows per chunk
-constexpr int V2_SUBU = V2_SZU / V2_R + 1;      // de-interleaved sub-table strides (+1: skew banks)
-constexpr int V2_SUBV = V2_SZV / V2_R + 1;
+__host__ __device__ constexpr int v2_szu(int tc) { return tc + V2_SPAN + V2_R; }   // falling-index entries per chunk
+__host__ __device__ constexpr int v2_szv(int tc) { return tc + (2 * V2_NW - 1) * V2_SPAN + V2_R; }   // rising-index
+__host__ __device__ constexpr int v2_szw(int tc) { return tc + (V2_NW - 1) * V2_SPAN; }             // W' rows
+__host__ __device__ constexpr int v2_subu(int tc) { return v2_szu(tc) / V2_R + 1; }   // de-interleaved sub-table strides
+__host__ __device__ constexpr int v2_subv(int tc) { return v2_szv(tc) / V2_R + 1; }
 
 __host__ __device__ constexpr int v2_nqp(int job) { return (job_nw(job) + 1) & ~1; }   // W' columns (even)
 __host__ __device__ constexpr int v2_ntab(int job) { return job_family(job) == FAM_00 ? 1 : 2; }
+__host__ __device__ constexpr int v2_tc(int job)
+{
+#ifdef PSB200_TC_ALL
+    return PSB200_TC_ALL;
+#else
+    return v2_nqp(job) <= 2 ? 256 : 128;
+#endif
+}
 __host__ __device__ constexpr int v2_smem_doubles(int job)
 {
-    return v2_ntab(job) * V2_R * (V2_SUBU + V2_SUBV) + V2_SZW * v2_nqp(job)
+    return v2_ntab(job) * V2_R * (v2_subu(v2_tc(job)) + v2_subv(v2_tc(job))) + v2_szw(v2_tc(job)) * v2_nqp(job)
          + V2_PB * (job_family(job) == FAM_02 ? 2 : 1) + 2;
 }
 
@@ -108,6 +118,9 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     constexpr int R = V2_R;
     constexpr int NTAB = v2_ntab(JOB);       // F00: ratio tables only; F22/F02: value + (negated) inverse
     constexpr int DS = (FAM == FAM_00) ? 2 : 1;   // stride of d inside a warp == step of l3
+    constexpr int V2_TC = v2_tc(JOB);
+    constexpr int V2_SZU = v2_szu(V2_TC), V2_SZV = v2_szv(V2_TC), V2_SZW = v2_szw(V2_TC);
+    constexpr int V2_SUBU = v2_subu(V2_TC), V2_SUBV = v2_subv(V2_TC);
 
     // F22/F02 tables hold (value, inverse) pairs so one 128-bit load fetches both; F00 holds ratios.
     extern __shared__ __align__(16) double smem[];
