@@ -472,79 +472,6 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
     return launch_any(hj.job, A, s.stream);
 }
 
-// Single-GPU pipeline: the band is cut into NSUB cost-balanced sub-bands of rows (edges on 32-row
-// tile boundaries), processed in increasing l1.  After sub-band k and its finish pass, every
-// COLUMN below its upper edge is final (column c needs rows l1 <= c only), so those columns --
-// one contiguous slab of the column-major result -- start their D2H copy on a second stream
-// while sub-band k+1 computes.  Only the last slab's copy is exposed.
-int run_single_pipelined(const HostJob& hj)
-{
-    Trace tr;
-    const int N = hj.lmax - hj.lmin + 1;
-    const long ldX = N;
-    int cur = 0;
-    cudaGetDevice(&cur);
-    CUDA_TRY(cudaSetDevice(0));
-    for (int o = 0; o < hj.nout; ++o)
-        if (int rc = scratch_reserve(0, o, (size_t)N * N)) return rc;
-    DeviceScratch& s0 = g_scratch[0];
-    psb::PairArgs A{};
-    {
-        double* Xs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        for (int o = 0; o < hj.nout; ++o) Xs[o] = s0.X[o];
-        if (int rc = run_on_device(hj, 0, hj.lmin, hj.lmax + 1, Xs, ldX, &A)) return rc;
-    }
-    int nsub = N >= 2048 ? 8 : (N >= 512 ? 4 : 1);
-    if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(16, atoi(e)));
-    std::vector<int> edges(nsub + 1);
-    psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, nsub, edges.data());
-    for (int k = 1; k < nsub; ++k)               // interior edges onto tile boundaries (relative to lmin)
-        edges[k] = std::min(hj.lmax + 1, hj.lmin + ((edges[k] - hj.lmin + 16) / 32) * 32);
-    const int nt = (N + 31) / 32;
-    for (int k = 0; k < nsub; ++k) {
-        const int lo = edges[k], hi = edges[k + 1];
-        if (hi <= lo) continue;
-        A.row_lo = lo; A.row_hi = hi;
-        if (int rc = launch_any(hj.job, A, s0.stream)) return rc;
-        const int t_lo = (lo - hj.lmin) / 32, t_hi = (hi - hj.lmin + 31) / 32;
-        for (int o = 0; o < hj.nout; ++o) {
-            finish_kernel<<<dim3(nt, t_hi - t_lo), 256, 0, s0.stream>>>(s0.X[o], ldX, hj.lmin, N, hj.scale, t_lo);
-            CUDA_TRY(cudaGetLastError());
-        }
-        CUDA_TRY(cudaEventRecord(s0.ev[k], s0.stream));
-    }
-    // All kernels are queued; now the copies (a D2H into pageable memory blocks the host thread
-    // until it is done, which is harmless once nothing is left to launch).
-    for (int k = 0; k < nsub; ++k) {
-        const int lo = edges[k], hi = edges[k + 1];
-        if (hi <= lo) continue;
-        CUDA_TRY(cudaStreamWaitEvent(s0.copy_stream, s0.ev[k], 0));
-        const size_t c0 = (size_t)(lo - hj.lmin), nc = (size_t)(hi - lo);
-        for (int o = 0; o < hj.nout; ++o) {
-            if (hj.ldo == ldX)
-                CUDA_TRY(cudaMemcpyAsync(hj.out[o] + c0 * hj.ldo, s0.X[o] + c0 * ldX, nc * N * sizeof(double),
-                                         cudaMemcpyDeviceToHost, s0.copy_stream));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync(hj.out[o] + c0 * hj.ldo, hj.ldo * sizeof(double), s0.X[o] + c0 * ldX,
-                                           ldX * sizeof(double), (size_t)N * sizeof(double), nc,
-                                           cudaMemcpyDeviceToHost, s0.copy_stream));
-        }
-    }
-    tr.mark("sub-band kernels + finish", 0, s0.stream);
-    CUDA_TRY(cudaStreamSynchronize(s0.stream));
-    CUDA_TRY(cudaStreamSynchronize(s0.copy_stream));
-    tr.mark("tail of D2H", 0, s0.copy_stream);
-    cudaSetDevice(cur);
-    return OK;
-}
-
-// Multi-GPU host path.  Every device owns a cost-balanced band of rows [a, b) and delivers, over its
-// OWN PCIe link and straight into the caller's matrix, the two rectangles only it can complete:
-//   block column: columns [a, b), rows [a, lmax]   (incl. the diagonal block, mirrored locally)
-//   block row   : rows [a, b), columns [b, lmax]   (transposed on the device)
-// These tile the matrix exactly once, so no inter-GPU exchange is needed when the result lives in
-// host memory (the NCCL gather to rank 0 belongs to the device-resident driver, device.py / bench.py).
-// One host thread per device keeps the pageable-memory copies of different GPUs concurrent.
 // Cost of row l1 as the tuned kernel executes it: one warp-block per 128 consecutive d, each running
 // l3 from its first d to min(d + 2 l1, lenW-1) plus the 127-step start skew of the warp, plus a
 // fixed per-block overhead (start values, first staging, epilogue) worth about 48 steps.
@@ -590,8 +517,8 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
             if (int rc = scratch_reserve(g, o, (size_t)nb * N)) return rc;
         // sub-bands: each is a complete band of its own (L-shaped region), so its copies can start
         // while the next sub-band computes
-        int nsub = nb >= 2048 ? 4 : (nb >= 512 ? 2 : 1);
-        if (const char* e = getenv("PSB200_NSUB_MULTI")) nsub = std::max(1, std::min(16, atoi(e)));
+        int nsub = nb >= 4096 ? 8 : (nb >= 2048 ? 4 : (nb >= 512 ? 2 : 1));
+        if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(16, atoi(e)));
         const std::vector<int> sub = split_rows(a, b, hj.lmax, hj.lenW, nsub);
         const int ns = (int)sub.size() - 1;
         std::vector<size_t> toff(ns + 1, 0);             // one transposed block row per (sub-band, output)
@@ -659,10 +586,14 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
 
 int run_host_job(const HostJob& hj, int ngpus)
 {
-    if (ngpus == 1) return run_single_pipelined(hj);
-    Trace tr;
     int cur = 0;
     cudaGetDevice(&cur);
+    if (ngpus == 1) {                                   // same scheme, one band, calling thread
+        const int rc = run_band_on_device(hj, 0, hj.lmin, hj.lmax + 1, nullptr);
+        cudaSetDevice(cur);
+        return rc;
+    }
+    Trace tr;
     std::vector<int> edges(ngpus + 1);
     psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, ngpus, edges.data());
     std::vector<int> rcs(ngpus, OK);
