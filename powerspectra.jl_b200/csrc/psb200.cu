@@ -239,7 +239,7 @@ int ensure_blocks(int dev, const psb::PairArgs& A, int ds, BlockList* out)
                 const int d_lo = base + par;
                 if (d_lo >= nd) continue;
                 const long last = A.lenW - 1 - d_lo;
-                const long steps = last < 0 ? 0 : std::min<long>(psb::V2_SPAN - 1 + (2 * l1) / ds, last / ds) + 1;
+                const long steps = last < 0 ? 0 : std::min<long>(psb::V2_GSPAN - 1 + (2 * l1) / ds, last / ds) + 1;
                 v.push_back({steps, make_int2(l1, d_lo)});
             }
         }
@@ -482,7 +482,7 @@ static long double row_cost(int l1, int lmax, int lenW)
     long double c = 0;
     for (long d_lo = 0; d_lo <= D; d_lo += psb::V2_PB) {
         const long last = (long)lenW - 1 - d_lo;
-        const long steps = last < 0 ? 0 : std::min<long>(psb::V2_SPAN - 1 + 2L * l1, last) + 1;
+        const long steps = last < 0 ? 0 : std::min<long>(psb::V2_GSPAN - 1 + 2L * l1, last) + 1;
         c += (long double)(steps + 48);
     }
     return c;

@@ -36,15 +36,27 @@ namespace psb {
 
 constexpr int V2_R = 4;                         // pairs per thread
 constexpr int V2_NW = 1;                        // warps per block: staging is warp-private, no block barriers
+#ifndef PSB200_LG
+#define PSB200_LG 32
+#endif
+// A warp's 128 pairs can be split into G = 32/LG lockstep groups of LG lanes: group q holds the pairs
+// q*GSPAN .. (q+1)*GSPAN-1 and runs GSPAN steps "ahead" in l3 (its j is tau + d_lo + q*GSPAN), so the
+// start skew a warp pays is GSPAN-1 steps instead of 127 while all groups still share the U table
+// and read consecutive windows of the V table.  W' rows are then one address per group instead of
+// a warp-uniform broadcast.  MEASURED (B200, lmax 6143, ms/step): LG=32 153.1, LG=16 156.9, LG=8 163.1 --
+// the extra shared-memory traffic costs more than the skew saves, so the default is one group.
+constexpr int V2_LG = PSB200_LG;                // lanes per lockstep group
+constexpr int V2_G = 32 / V2_LG;                // groups per warp
+constexpr int V2_GSPAN = V2_LG * V2_R;          // pairs per group
 constexpr int V2_TC_MAX = 256;
 // steps per staged chunk: longer chunks where the W' tile is small (fewer staging events)
 __host__ __device__ constexpr int v2_tc(int job);
 constexpr int V2_THREADS = V2_NW * 32;
 constexpr int V2_SPAN = 32 * V2_R;              // pairs per warp
 constexpr int V2_PB = V2_THREADS * V2_R;        // pairs per block
-__host__ __device__ constexpr int v2_szu(int tc) { return tc + V2_SPAN + V2_R; }   // falling-index entries per chunk
-__host__ __device__ constexpr int v2_szv(int tc) { return tc + (2 * V2_NW - 1) * V2_SPAN + V2_R; }   // rising-index
-__host__ __device__ constexpr int v2_szw(int tc) { return tc + (V2_NW - 1) * V2_SPAN; }             // W' rows
+__host__ __device__ constexpr int v2_szu(int tc) { return tc + V2_GSPAN + V2_R; }   // falling-index entries per chunk
+__host__ __device__ constexpr int v2_szv(int tc) { return tc + (2 * V2_G - 1) * V2_GSPAN + V2_R; }   // rising-index
+__host__ __device__ constexpr int v2_szw(int tc) { return tc + (V2_G - 1) * V2_GSPAN; }             // W' rows
 __host__ __device__ constexpr int v2_subu(int tc) { return v2_szu(tc) / V2_R + 1; }   // de-interleaved sub-table strides
 __host__ __device__ constexpr int v2_subv(int tc) { return v2_szv(tc) / V2_R + 1; }
 
@@ -135,13 +147,13 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     const int l1 = blk.x, d_lo = blk.y;
     const int L = 2 * l1 + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int woff = warp * V2_SPAN;                      // d_w - d_lo
-    const int e = lane * R;
+    const int woff = (lane / V2_LG) * V2_GSPAN;           // pair offset of my lockstep group
+    const int e = (lane % V2_LG) * R;                     // pair offset inside the group
     const int cV = 2 * woff + e;
     const int dmax = A.lmax - l1;                         // last valid d of this row
     // last step: the last pair (offset SPAN-1) finishes its family, or the window spectrum ends
     const int tau_end = (A.lenW - 1 - d_lo < 0) ? -1
-                      : min(V2_SPAN - 1 + (2 * l1) / DS, (A.lenW - 1 - d_lo) / DS);   // block-uniform
+                      : min(V2_GSPAN - 1 + (2 * l1) / DS, (A.lenW - 1 - d_lo) / DS);   // block-uniform
 
     // ---- start values (closed form), one per pair, parked in shared memory ----
     {
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     for (int k = 0; k < 2 * R - 1; ++k) { wU0[k] = 0.0; wU1[k] = 0.0; wV0[k] = 0.0; wV1[k] = 0.0; }
 
     double k4 = 4.0 * (double)(2 * (d_lo + woff) + 1);    // 4 (2j+1) at tau = 0   (DS == 1 jobs only)
-    const bool warp_live = (d_lo + DS * woff) <= dmax;
+    const bool warp_live = d_lo <= dmax;
 
     for (int tau0 = 0; tau0 <= tau_end; tau0 += V2_TC) {
         block_sync();
@@ -193,13 +205,13 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
             if constexpr (FAM == FAM_00) {
                 // ratio a(j+1)^2/a(j+2)^2, falling part at n = t+1.  The windows hand a pair the entry
                 // nu = t/2 + 1 (the "next step" slot), hence n = 2 nu - 1.
-                const int n = 2 * (tau0 - V2_SPAN + idx) - 1;
+                const int n = 2 * (tau0 - V2_GSPAN + idx) - 1;
                 double v = 0.0;
                 if (n >= 1 && n <= L - 2)
                     v = ((double)n * (double)(L - n)) * (__ldg(T.INV + n + 1) * __ldg(T.INV + (L - n - 1)));
                 shU[pos] = v;
             } else {
-                const int n = tau0 - V2_SPAN + idx;
+                const int n = tau0 - V2_GSPAN + idx;
                 double u = 0.0, iu = 0.0;
                 if (n >= 1 && n <= L - 1) {
                     u = __ldg(T.S + n) * __ldg(T.S + (L - n));
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
         for (int tg = 0; tg < tg_end; tg += R) {
             // ---- the R new entries of every window ----
             {
-                const int bu = (tg - e + V2_SPAN) / R;     // idx = tg + 1 - e + u + SPAN
+                const int bu = (tg - e + V2_GSPAN) / R;    // idx = tg + 1 - e + u + GSPAN
                 const int bv = (tg + cV) / R + 1;          // idx = tg + cV + R + u
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
