@@ -220,26 +220,27 @@ int ensure_tables(int dev, int lmax, DevTables** out)
 // Block list of one launch: (l1, d_lo) tiles of the band's upper triangle, heaviest first
 // (longest-processing-time order keeps the 148 SMs balanced to the last wave).
 struct BlockList { int2* d = nullptr; int n = 0; unsigned long stamp = 0; };
-typedef std::tuple<int, int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi, d stride
+typedef std::tuple<int, int, int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi, d stride, pairs per thread
 std::map<BlockKey, BlockList> g_blocks;
 unsigned long g_block_stamp = 0;
 
-int ensure_blocks(int dev, const psb::PairArgs& A, int ds, BlockList* out)
+int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, BlockList* out)
 {
-    // ds = 1: a warp takes 128 consecutive d.  ds = 2 ((0,0,0)-only jobs): 128 d of one parity.
+    // A warp takes 32 r pairs: consecutive d (ds = 1) or d of one parity (ds = 2, (0,0,0)-only jobs).
     std::lock_guard<std::mutex> lk(g_tab_mutex);
-    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi, ds);
+    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi, ds, r);
+    const int pb = psb::v2_pb(r), gspan = psb::v2_gspan(r);
     auto it = g_blocks.find(key);
     if (it != g_blocks.end()) { it->second.stamp = ++g_block_stamp; *out = it->second; return OK; }
     std::vector<std::pair<long, int2>> v;
     for (int l1 = A.row_lo; l1 < A.row_hi; ++l1) {
         const int nd = A.lmax - l1 + 1;
-        for (int base = 0; base < nd; base += ds * psb::V2_PB) {
+        for (int base = 0; base < nd; base += ds * pb) {
             for (int par = 0; par < ds; ++par) {
                 const int d_lo = base + par;
                 if (d_lo >= nd) continue;
                 const long last = A.lenW - 1 - d_lo;
-                const long steps = last < 0 ? 0 : std::min<long>(psb::V2_GSPAN - 1 + (2 * l1) / ds, last / ds) + 1;
+                const long steps = last < 0 ? 0 : std::min<long>(gspan - 1 + (2 * l1) / ds, last / ds) + 1;
                 v.push_back({steps, make_int2(l1, d_lo)});
             }
         }
@@ -312,10 +313,10 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, &t)) return rc;
     BlockList bl;
-    if (int rc = ensure_blocks(dev, A, psb::job_family(JOB) == psb::FAM_00 ? 2 : 1, &bl)) return rc;
+    if (int rc = ensure_blocks(dev, A, psb::job_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), &bl)) return rc;
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
     constexpr int nqp = psb::v2_nqp(JOB);
-    const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_NW * psb::V2_SPAN);
+    const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_PB_MAX);
     double* Wp = nullptr;
     tr.mark("  tables + block list", dev, st);
     if (int rc = wp_reserve(dev, st, (size_t)rows_w * nqp, &Wp)) return rc;
@@ -472,17 +473,18 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
     return launch_any(hj.job, A, s.stream);
 }
 
-// Cost of row l1 as the tuned kernel executes it: one warp-block per 128 consecutive d, each running
-// l3 from its first d to min(d + 2 l1, lenW-1) plus the 127-step start skew of the warp, plus a
+// Cost of row l1 as the tuned kernel executes it: one warp-block per 192 consecutive d, each running
+// l3 from its first d to min(d + 2 l1, lenW-1) plus the 191-step start skew of the warp, plus a
 // fixed per-block overhead (start values, first staging, epilogue) worth about 48 steps.
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
     long double c = 0;
-    for (long d_lo = 0; d_lo <= D; d_lo += psb::V2_PB) {
+    constexpr long PBN = 192, SKEW = 191;             // nominal warp tile (6 pairs per thread)
+    for (long d_lo = 0; d_lo <= D; d_lo += PBN) {
         const long last = (long)lenW - 1 - d_lo;
-        const long steps = last < 0 ? 0 : std::min<long>(psb::V2_GSPAN - 1 + 2L * l1, last) + 1;
+        const long steps = last < 0 ? 0 : std::min<long>(SKEW + 2L * l1, last) + 1;
         c += (long double)(steps + 48);
     }
     return c;

@@ -1,7 +1,8 @@
 // psb200_pair_v2.cuh -- tuned pair kernel for sm_100a (FP64-pipe bound by design).
 //
 // Work decomposition
-//   block  = ONE WARP = one l1 row x V2_PB = 128 consecutive d = l2-l1;  thread = R = 4 consecutive d.
+//   block  = ONE WARP = one l1 row x 32 R consecutive d = l2-l1;  thread = R consecutive d (R = 8 for the
+//   one- and two-accumulator jobs, 6 for the covariance jobs).
 //   (Warp-sized blocks: table staging needs only __syncwarp, so the ~12 resident warps of an SM
 //   drift apart and hide each other's staging latency; ncu showed 9-12% barrier stalls with
 //   4-warp blocks.)
@@ -34,7 +35,24 @@
 
 namespace psb {
 
-constexpr int V2_R = 4;                         // pairs per thread
+// Pairs per thread, by job weight.  More pairs per thread = fewer shared-memory bytes per pair-step (each
+// new table entry serves R pairs) but more registers and a longer start skew (32 R - 1 steps).
+// MEASURED (B200, lmax 6143, ms per bench step): R = 4/4/4 154.4, 6/6/4 151.2, 6/6/6 149.5, 8/6/4 150.8,
+// 8/6/6 148.5 -- the shared-memory return path, not occupancy, is the co-limiter next to the FP64 pipe.
+#ifndef PSB200_R_LIGHT
+#define PSB200_R_LIGHT 8        // <= 2 accumulators per pair
+#endif
+#ifndef PSB200_R_MID
+#define PSB200_R_MID 6          // 4-5 accumulators
+#endif
+#ifndef PSB200_R_HEAVY
+#define PSB200_R_HEAVY 6        // 8 accumulators
+#endif
+__host__ __device__ constexpr int v2_r(int job)
+{
+    return job_nacc(job) <= 2 ? PSB200_R_LIGHT : (job_nacc(job) <= 5 ? PSB200_R_MID : PSB200_R_HEAVY);
+}
+constexpr int V2_R_MAX = 8;
 constexpr int V2_NW = 1;                        // warps per block: staging is warp-private, no block barriers
 #ifndef PSB200_LG
 #define PSB200_LG 32
@@ -47,18 +65,18 @@ constexpr int V2_NW = 1;                        // warps per block: staging is w
 // the extra shared-memory traffic costs more than the skew saves, so the default is one group.
 constexpr int V2_LG = PSB200_LG;                // lanes per lockstep group
 constexpr int V2_G = 32 / V2_LG;                // groups per warp
-constexpr int V2_GSPAN = V2_LG * V2_R;          // pairs per group
-constexpr int V2_TC_MAX = 256;
+__host__ __device__ constexpr int v2_gspan(int r) { return V2_LG * r; }   // pairs per group
+constexpr int V2_TC_MAX = 256;                 // upper bound of v2_tc()
 // steps per staged chunk: longer chunks where the W' tile is small (fewer staging events)
 __host__ __device__ constexpr int v2_tc(int job);
 constexpr int V2_THREADS = V2_NW * 32;
-constexpr int V2_SPAN = 32 * V2_R;              // pairs per warp
-constexpr int V2_PB = V2_THREADS * V2_R;        // pairs per block
-__host__ __device__ constexpr int v2_szu(int tc) { return tc + V2_GSPAN + V2_R; }   // falling-index entries per chunk
-__host__ __device__ constexpr int v2_szv(int tc) { return tc + (2 * V2_G - 1) * V2_GSPAN + V2_R; }   // rising-index
-__host__ __device__ constexpr int v2_szw(int tc) { return tc + (V2_G - 1) * V2_GSPAN; }             // W' rows
-__host__ __device__ constexpr int v2_subu(int tc) { return v2_szu(tc) / V2_R + 1; }   // de-interleaved sub-table strides
-__host__ __device__ constexpr int v2_subv(int tc) { return v2_szv(tc) / V2_R + 1; }
+__host__ __device__ constexpr int v2_pb(int r) { return V2_THREADS * r; }            // pairs per block (= per warp)
+constexpr int V2_PB_MAX = V2_THREADS * V2_R_MAX;
+__host__ __device__ constexpr int v2_szu(int tc, int r) { return tc + v2_gspan(r) + r; }   // falling-index entries per chunk
+__host__ __device__ constexpr int v2_szv(int tc, int r) { return tc + (2 * V2_G - 1) * v2_gspan(r) + r; }   // rising-index
+__host__ __device__ constexpr int v2_szw(int tc, int r) { return tc + (V2_G - 1) * v2_gspan(r); }          // W' rows
+__host__ __device__ constexpr int v2_subu(int tc, int r) { return v2_szu(tc, r) / r + 1; }   // de-interleaved sub-table strides
+__host__ __device__ constexpr int v2_subv(int tc, int r) { return v2_szv(tc, r) / r + 1; }
 
 __host__ __device__ constexpr int v2_nqp(int job) { return (job_nw(job) + 1) & ~1; }   // W' columns (even)
 __host__ __device__ constexpr int v2_ntab(int job) { return job_family(job) == FAM_00 ? 1 : 2; }
@@ -67,13 +85,13 @@ __host__ __device__ constexpr int v2_tc(int job)
 #ifdef PSB200_TC_ALL
     return PSB200_TC_ALL;
 #else
-    return v2_nqp(job) <= 2 ? 256 : 128;
+    return (v2_nqp(job) <= 2 ? 256 : 128) / v2_r(job) * v2_r(job);
 #endif
 }
 __host__ __device__ constexpr int v2_smem_doubles(int job)
 {
-    return v2_ntab(job) * V2_R * (v2_subu(v2_tc(job)) + v2_subv(v2_tc(job))) + v2_szw(v2_tc(job)) * v2_nqp(job)
-         + V2_PB * (job_family(job) == FAM_02 ? 2 : 1) + 2;
+    return v2_ntab(job) * v2_r(job) * (v2_subu(v2_tc(job), v2_r(job)) + v2_subv(v2_tc(job), v2_r(job)))
+         + v2_szw(v2_tc(job), v2_r(job)) * v2_nqp(job) + v2_pb(v2_r(job)) * (job_family(job) == FAM_02 ? 2 : 1) + 2;
 }
 
 struct V2Tables {
@@ -117,6 +135,10 @@ __device__ __forceinline__ void cp_async_wait_all()
 // SMSP for the light jobs, 12 = 3 per SMSP for the 8-accumulator covariance jobs.
 __host__ __device__ constexpr int v2_min_blocks(int job)
 {
+    if (v2_r(job) > 4) {
+        if (job_family(job) == FAM_00 && job_nacc(job) <= 2) return 16;
+        return (v2_r(job) >= 8 || v2_r(job) * job_nacc(job) >= 24) ? 8 : 12;
+    }
     return (job == JOB_EEEE || job == JOB_TETE || job == JOB_MASTER) ? 12 : (job == JOB_M00 ? 32 : 16);
 }
 
@@ -127,12 +149,13 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     constexpr int NWQ = job_nw(JOB);
     constexpr int NACC = job_nacc(JOB);
     constexpr int NQP = v2_nqp(JOB);
-    constexpr int R = V2_R;
+    constexpr int R = v2_r(JOB);
+    constexpr int V2_GSPAN = v2_gspan(R), V2_PB = v2_pb(R);
     constexpr int NTAB = v2_ntab(JOB);       // F00: ratio tables only; F22/F02: value + (negated) inverse
     constexpr int DS = (FAM == FAM_00) ? 2 : 1;   // stride of d inside a warp == step of l3
     constexpr int V2_TC = v2_tc(JOB);
-    constexpr int V2_SZU = v2_szu(V2_TC), V2_SZV = v2_szv(V2_TC), V2_SZW = v2_szw(V2_TC);
-    constexpr int V2_SUBU = v2_subu(V2_TC), V2_SUBV = v2_subv(V2_TC);
+    constexpr int V2_SZU = v2_szu(V2_TC, R), V2_SZV = v2_szv(V2_TC, R), V2_SZW = v2_szw(V2_TC, R);
+    constexpr int V2_SUBU = v2_subu(V2_TC, R), V2_SUBV = v2_subv(V2_TC, R);
 
     // F22/F02 tables hold (value, inverse) pairs so one 128-bit load fetches both; F00 holds ratios.
     extern __shared__ __align__(16) double smem[];
@@ -146,7 +169,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     const int2 blk = T.blocks[blockIdx.x];
     const int l1 = blk.x, d_lo = blk.y;
     const int L = 2 * l1 + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int woff = (lane / V2_LG) * V2_GSPAN;           // pair offset of my lockstep group
     const int e = (lane % V2_LG) * R;                     // pair offset inside the group
     const int cV = 2 * woff + e;
