@@ -146,7 +146,7 @@ int kernel_version()
 {
     // read on every call so a test can switch kernels inside one process
     const char* e = getenv("PSB200_KERNEL");
-    return (e && strcmp(e, "v1") == 0) ? 1 : 2;
+    return (e && strcmp(e, "v1") == 0) ? 1 : 2;       // v1: simple kernel (cross-check); default: tuned kernel
 }
 
 // PSB200_TRACE=1: per-phase wall-clock of the host-level calls on stderr (adds stream syncs)
