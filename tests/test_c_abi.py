@@ -1,0 +1,58 @@
+"""The boundary is a plain C ABI: a C program that includes include/psb200.h, links nothing but libdl and
+loads libpsb200.so must be able to use it (this is what a ccall / cgo / JNI binding relies on)."""
+import os
+import subprocess
+import textwrap
+
+from conftest import ROOT
+
+C_SRC = textwrap.dedent(r"""
+    #include <dlfcn.h>
+    #include <stdio.h>
+    #include <string.h>
+    #include "psb200.h"
+
+    typedef int (*mcm_t)(int, int, int, const double*, int, double*, long, double*, int);
+    typedef int (*edges_t)(int, int, int, int, int*);
+    typedef long long (*terms_t)(int, int, int, int);
+    typedef const char* (*str_t)(void);
+    typedef int (*cnt_t)(void);
+
+    int main(int argc, char** argv)
+    {
+        void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+        if (!h) { printf("dlopen failed: %s\n", dlerror()); return 2; }
+        mcm_t mcm = (mcm_t)dlsym(h, "psb200_mcm");
+        edges_t edges = (edges_t)dlsym(h, "psb200_band_edges");
+        terms_t terms = (terms_t)dlsym(h, "psb200_terms");
+        str_t version = (str_t)dlsym(h, "psb200_version");
+        str_t last_error = (str_t)dlsym(h, "psb200_last_error");
+        cnt_t ndev = (cnt_t)dlsym(h, "psb200_device_count");
+        if (!mcm || !edges || !terms || !version || !last_error || !ndev) { printf("missing symbol\n"); return 3; }
+        printf("version=%s devices=%d\n", version(), ndev());
+        int e[5];
+        if (edges(0, 767, 768, 4, e) != 0 || e[0] != 0 || e[4] != 768) { printf("band_edges wrong\n"); return 4; }
+        if (terms(1, 767, 0, 768) != 151289984LL) { printf("terms wrong\n"); return 5; }
+        double V[8] = {1, 1, 1, 1, 1, 1, 1, 1}, M[64];
+        memset(M, 0, sizeof M);
+        int rc = mcm(PSB200_MPP_MMM, 0, 7, V, 8, M, 8, NULL, 1);      /* fused kind without the 2nd output */
+        if (rc != 1) { printf("expected bad-argument code, got %d\n", rc); return 6; }
+        rc = mcm(PSB200_M00, 0, 7, V, 8, M, 8, NULL, 1);
+        if (ndev() == 0) {
+            if (rc != 5 || !strstr(last_error(), "no CPU fallback")) { printf("expected code 5, got %d (%s)\n", rc, last_error()); return 7; }
+        } else if (rc != 0) { printf("compute failed: %d %s\n", rc, last_error()); return 8; }
+        printf("ok rc=%d\n", rc);
+        return 0;
+    }
+""")
+
+
+def test_c_program_uses_the_abi(tmp_path, ps):
+    src = tmp_path / "abi.c"
+    exe = tmp_path / "abi"
+    src.write_text(C_SRC)
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-ldl"], check=True)
+    out = subprocess.run([str(exe), ps.LIB_PATH], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ok rc=" in out.stdout

@@ -460,6 +460,39 @@ def test_fused_master_call(ps, oracle):
     assert np.allclose(ee.parent, cl["EE"], rtol=1e-8) and np.allclose(bb.parent, cl["BB"], rtol=1e-8)
 
 
+def test_gpu_mcm_against_exact_3j_bruteforce(ps):
+    """GPU against matrices built by brute force from exact (sympy) 3j values -- no oracle in between."""
+    from test_oracle import exact_mcm_from_sympy
+    lmax = 24
+    rng = np.random.default_rng(7)
+    for nV in (25, 49, 12):
+        V = rng.normal(size=nV)
+        r = range(0, lmax + 1)
+        for kind, fn in ((0, ps.inner_mcm00), (1, ps.inner_mcm02), (2, ps.inner_mcmpp), (3, ps.inner_mcmmm)):
+            E = exact_mcm_from_sympy(kind, lmax, V)
+            M = fn(ps.spectralzeros(r, r), ps.SpectralVector(V)).parent
+            lo = 2 if kind else 0
+            assert np.max(np.abs(M[lo:, lo:] - E[lo:, lo:])) < 5e-14 * max(1.0, np.abs(E).max()), (kind, nV)
+
+
+@pytest.mark.parametrize("block", ["TTTT", "EEEE", "TTTE", "TETE", "TEEE_planck", "TEEE", "TTEE"])
+def test_gpu_cov_against_exact_3j_bruteforce(ps, block):
+    """Every covariance block on the GPU against an independent numpy transcription of the reference
+    formulas evaluated with exact 3j values (no oracle in between)."""
+    from test_oracle import cov_case_small, exact_cov_from_sympy
+    lmax = 24
+    sp, rt, W = cov_case_small(block, lmax)
+    E = exact_cov_from_sympy(block, lmax, sp, rt, W)
+    fn = {"TTTT": ps.loop_covTTTT, "EEEE": ps.loop_covEEEE, "TTTE": ps.loop_covTTTE, "TETE": ps.loop_covTETE,
+          "TEEE_planck": ps.loop_covTEEE_planck, "TEEE": ps.loop_covTEEE, "TTEE": ps.loop_covTTEE}[block]
+    r = range(0, lmax + 1)
+    V = ps.SpectralVector
+    Cm = fn(ps.spectralzeros(r, r), *[V(x) for x in sp], *[V(x) for x in rt], *[V(x) for x in W]).parent
+    lo = 0 if block in ("TTTT", "TTTE", "TTEE") else 2
+    assert np.max(np.abs(Cm[lo:, lo:] - E[lo:, lo:])) < 1e-13 * max(1.0, np.abs(E[lo:, lo:]).max())
+    assert np.array_equal(Cm, Cm.T)
+
+
 def test_error_codes(ps):
     lib = ps.lib()
     V = np.ones(8)

@@ -156,3 +156,116 @@ def test_covariance_symmetric_and_row_sampling(oracle, ps):
     # long-double instantiation agrees with the Float64 one far inside the parity budget
     Cl = oracle.cov("TETE", 0, lmax, S, R, W, ld=True)
     assert parity_error(C, Cl) < 1e-11
+
+
+def exact_mcm_from_sympy(kind, lmax, V):
+    """Brute-force M[l1,l2] from the exact (sympy) 3j values of tests/golden/w3j_exact.npz, written
+    straight from the definitions in docs/src/spectra.md / src/modecoupling.jl:3-66 -- shares no
+    code with the oracle's loops."""
+    g = np.load(os.path.join(GOLDEN, "w3j_exact.npz"))
+    fam = {}
+    for f, l1, l2, off, n in g["index"]:
+        fam[(int(f), int(l1), int(l2))] = g["values"][off:off + n]
+    M = np.zeros((lmax + 1, lmax + 1))
+    for l1 in range(lmax + 1):
+        for l2 in range(lmax + 1):
+            a, b = min(l1, l2), max(l1, l2)
+            f0 = fam[(0, a, b)]
+            f2 = fam.get((1, a, b))
+            if kind != 0 and f2 is None:
+                continue                           # l < 2 for a spin-2 kind: don't-care region
+            js = np.arange(b - a, a + b + 1)
+            sel = js < V.size
+            par = (l1 + l2 + js) % 2
+            if kind == 0:
+                w = f0 ** 2
+            elif kind == 1:
+                w = f0 * f2
+                sel &= par == 0
+            else:
+                w = f2 ** 2
+                sel &= par == (0 if kind == 2 else 1)
+            M[l1, l2] = (2 * l2 + 1) / (4 * np.pi) * np.sum((2 * js[sel] + 1) * w[sel] * V[js[sel]])
+    return M
+
+
+@pytest.mark.parametrize("nV", [25, 49, 12])
+def test_oracle_mcm_against_exact_3j_bruteforce(oracle, nV):
+    lmax = 24
+    rng = np.random.default_rng(100 + nV)
+    V = rng.normal(size=nV)
+    for kind in range(4):
+        E = exact_mcm_from_sympy(kind, lmax, V)
+        lo = 2 if kind else 0
+        for ld in (False, True):
+            M = oracle.mcm(kind, 0, lmax, V, ld=ld)
+            assert np.max(np.abs(M[lo:, lo:] - E[lo:, lo:])) < 5e-14 * max(1.0, np.abs(E).max()), (kind, ld)
+
+
+def exact_xi_from_sympy(lmax, W, which):
+    """Xi[l1,l2] = (1/4pi) sum (2 l3+1) w(l3) W(l3) from exact 3j; which: "00" f00^2 all parities,
+    "22" f22^2 even parity, "02" f00 f22 even parity (src/modecoupling.jl:3-66)."""
+    kind = {"00": 0, "22": 2, "02": 1}[which]
+    M = exact_mcm_from_sympy(kind, lmax, np.asarray(W))
+    return M / (2 * np.arange(lmax + 1) + 1.0)[None, :]
+
+
+def exact_cov_from_sympy(block, lmax, sp, rt, W):
+    """Second, independent transcription of the seven block formulas of /root/reference/src/covariance.jl
+    (numpy, vectorised over (l1, l2)), on top of the exact-3j Xi."""
+    l = np.arange(lmax + 1)
+    A = lambda k: np.asarray(sp[k])[l][:, None]      # value at l1
+    B = lambda k: np.asarray(sp[k])[l][None, :]      # value at l2
+    Ra = lambda k: np.asarray(rt[k])[l][:, None]
+    Rb = lambda k: np.asarray(rt[k])[l][None, :]
+    X = lambda k, which: exact_xi_from_sympy(lmax, W[k], which)
+    if block in ("TTTT", "EEEE"):
+        w = "00" if block == "TTTT" else "22"
+        return (np.sqrt(A(0) * B(0) * A(1) * B(1)) * X(0, w) + np.sqrt(A(2) * B(2) * A(3) * B(3)) * X(1, w)
+                + np.sqrt(A(0) * B(0)) * X(2, w) * Ra(1) * Rb(1) + np.sqrt(A(1) * B(1)) * X(3, w) * Ra(0) * Rb(0)
+                + np.sqrt(A(2) * B(2)) * X(4, w) * Ra(3) * Rb(3) + np.sqrt(A(3) * B(3)) * X(5, w) * Ra(2) * Rb(2)
+                + X(6, w) * Ra(0) * Ra(1) * Rb(0) * Rb(1) + X(7, w) * Ra(2) * Ra(3) * Rb(2) * Rb(3))
+    if block == "TTTE":
+        return (np.sqrt(A(0) * B(0)) * (A(3) + B(3)) * X(0, "00") + np.sqrt(A(1) * B(1)) * (A(2) + B(2)) * X(1, "00")
+                + (A(3) + B(3)) * X(2, "00") * Ra(0) * Rb(0) + (A(2) + B(2)) * X(3, "00") * Ra(1) * Rb(1)) / 2
+    if block == "TETE":
+        return (np.sqrt(A(0) * B(0) * A(1) * B(1)) * X(0, "02") + 0.5 * (A(2) * B(3) + A(3) * B(2)) * X(1, "00")
+                + np.sqrt(A(0) * B(0)) * X(2, "02") * Ra(1) * Rb(1) + np.sqrt(A(1) * B(1)) * X(3, "02") * Ra(0) * Rb(0)
+                + X(4, "02") * Ra(0) * Rb(0) * Ra(1) * Rb(1))
+    if block in ("TEEE_planck", "TEEE"):
+        w = "22" if block == "TEEE_planck" else "02"
+        return (np.sqrt(A(0) * B(0)) * (A(2) + B(2)) * X(0, w) + np.sqrt(A(1) * B(1)) * (A(3) + B(3)) * X(1, w)
+                + (A(2) + B(2)) * X(2, w) * Ra(0) * Rb(0) + (A(3) + B(3)) * X(3, w) * Ra(1) * Rb(1)) / 2
+    if block == "TTEE":
+        return ((A(0) * B(2) + A(2) * B(0)) * X(0, "00") + (A(1) * B(3) + A(3) * B(1)) * X(1, "00")) / 2
+    raise KeyError(block)
+
+
+COV_SHAPES = {"TTTT": (4, 4, 8), "EEEE": (4, 4, 8), "TTTE": (4, 2, 4), "TETE": (4, 2, 5),
+              "TEEE_planck": (4, 2, 4), "TEEE": (4, 2, 4), "TTEE": (4, 0, 2)}
+
+
+def cov_case_small(block, lmax, seed=0):
+    rng = np.random.default_rng(seed + len(block))
+    nsp, nrt, nw = COV_SHAPES[block]
+    sp = [rng.uniform(0.5, 2.0, size=lmax + 1) for _ in range(nsp)]
+    if block in ("TTTE", "TEEE", "TEEE_planck"):
+        sp[2], sp[3] = sp[2] - 1.2, sp[3] - 1.2          # TE spectra may be negative
+    if block == "TETE":
+        sp[2], sp[3] = sp[2] - 1.2, sp[3] - 1.2
+    if block == "TTEE":
+        sp = [x - 1.2 for x in sp]
+    rt = [rng.uniform(0.5, 1.5, size=lmax + 1) for _ in range(nrt)]
+    W = [rng.normal(size=lmax + 1) for _ in range(nw)]
+    return sp, rt, W
+
+
+@pytest.mark.parametrize("block", list(COV_SHAPES))
+def test_oracle_cov_against_exact_3j_bruteforce(oracle, block):
+    lmax = 24
+    sp, rt, W = cov_case_small(block, lmax)
+    E = exact_cov_from_sympy(block, lmax, sp, rt, W)
+    lo = 0 if block in ("TTTT", "TTTE", "TTEE") else 2
+    for ld in (False, True):
+        Cm = oracle.cov(block, 0, lmax, sp, rt, W, ld=ld)
+        assert np.max(np.abs(Cm[lo:, lo:] - E[lo:, lo:])) < 1e-13 * max(1.0, np.abs(E[lo:, lo:]).max()), (block, ld)
