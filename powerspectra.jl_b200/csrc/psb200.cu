@@ -313,7 +313,7 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, &t)) return rc;
     BlockList bl;
-    if (int rc = ensure_blocks(dev, A, psb::job_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), &bl)) return rc;
+    if (int rc = ensure_blocks(dev, A, psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), &bl)) return rc;
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
     constexpr int nqp = psb::v2_nqp(JOB);
     const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_PB_MAX);

@@ -79,7 +79,22 @@ __host__ __device__ constexpr int v2_subu(int tc, int r) { return v2_szu(tc, r) 
 __host__ __device__ constexpr int v2_subv(int tc, int r) { return v2_szv(tc, r) / r + 1; }
 
 __host__ __device__ constexpr int v2_nqp(int job) { return (job_nw(job) + 1) & ~1; }   // W' columns (even)
-__host__ __device__ constexpr int v2_ntab(int job) { return job_family(job) == FAM_00 ? 1 : 2; }
+// Family as the TUNED kernel evaluates it.  Jobs that only ever use EVEN-parity terms (M02, M++, EEEE,
+// TETE, TEEE, TEEE_planck) never run the three-term spin-2 recurrence: for l1+l2+j even
+//     (j l1 l2; 0 -2 2) = (j l1 l2; 0 0 0) * N(x) / D,      x = j(j+1), a = l1(l1+1), b = l2(l2+1),
+//     N(x) = (x-a-b)(x-a-b+2)/2 - a b,   D = sqrt((l1-1) l1 (l1+1)(l1+2) (l2-1) l2 (l2+1)(l2+2))
+// (two steps of the m-ladder; checked exactly against sympy, tests/test_oracle.py), so they ride the
+// cheap two-step f00^2 recurrence with l3 step 2, exactly like the (0,0,0) jobs.  Only jobs that need
+// odd parity (M--, fused M++/M--, MASTER) keep the spin-2 recurrence.
+__host__ __device__ constexpr bool v2_even_only_spin2(int job)
+{
+    return job == JOB_M02 || job == JOB_MPP || job == JOB_EEEE || job == JOB_TETE || job == JOB_TEEEP || job == JOB_TEEE;
+}
+__host__ __device__ constexpr int v2_family(int job)
+{
+    return v2_even_only_spin2(job) ? FAM_00 : job_family(job);
+}
+__host__ __device__ constexpr int v2_ntab(int job) { return v2_family(job) == FAM_00 ? 1 : 2; }
 __host__ __device__ constexpr int v2_tc(int job)
 {
 #ifdef PSB200_TC_ALL
@@ -91,7 +106,7 @@ __host__ __device__ constexpr int v2_tc(int job)
 __host__ __device__ constexpr int v2_smem_doubles(int job)
 {
     return v2_ntab(job) * v2_r(job) * (v2_subu(v2_tc(job), v2_r(job)) + v2_subv(v2_tc(job), v2_r(job)))
-         + v2_szw(v2_tc(job), v2_r(job)) * v2_nqp(job) + v2_pb(v2_r(job)) * (job_family(job) == FAM_02 ? 2 : 1) + 2;
+         + v2_szw(v2_tc(job), v2_r(job)) * v2_nqp(job) + v2_pb(v2_r(job)) * (v2_family(job) == FAM_02 ? 2 : 1) + 2;
 }
 
 struct V2Tables {
@@ -136,7 +151,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 __host__ __device__ constexpr int v2_min_blocks(int job)
 {
     if (v2_r(job) > 4) {
-        if (job_family(job) == FAM_00 && job_nacc(job) <= 2) return 16;
+        if (v2_family(job) == FAM_00 && job_nacc(job) <= 2) return 16;
         return (v2_r(job) >= 8 || v2_r(job) * job_nacc(job) >= 24) ? 8 : 12;
     }
     return (job == JOB_EEEE || job == JOB_TETE || job == JOB_MASTER) ? 12 : (job == JOB_M00 ? 32 : 16);
@@ -145,7 +160,8 @@ __host__ __device__ constexpr int v2_min_blocks(int job)
 template <int JOB>
 __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2(const PairArgs A, const V2Tables T)
 {
-    constexpr int FAM = job_family(JOB);
+    constexpr int FAM = v2_family(JOB);
+    constexpr bool E2 = v2_even_only_spin2(JOB);      // even-parity spin-2 through f00^2 * (N/D)^k
     constexpr int NWQ = job_nw(JOB);
     constexpr int NACC = job_nacc(JOB);
     constexpr int NQP = v2_nqp(JOB);
@@ -211,12 +227,28 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
 #pragma unroll
         for (int q = 0; q < NACC; ++q) acc[r][q] = 0.0;
     }
+    // even-parity spin-2 through f00^2: per-pair constants of N(x) = t (t/2 + 1) - ab, t = x - (a+b)
+    double e2_s[R], e2_ab[R];
+    if constexpr (E2) {
+        const double a = (double)l1 * (double)(l1 + 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int l2 = l1 + d_lo + DS * (woff + e + r);
+            const double b = (double)l2 * (double)(l2 + 1);
+            e2_s[r] = a + b;
+            e2_ab[r] = a * b;
+        }
+    }
+    // x = j (j+1) of the warp's current l3 (uniform), advanced by 4j+6 per step of 2
+    double xj = (double)(d_lo + DS * woff) * (double)(d_lo + DS * woff + 1);
+    double xinc = 4.0 * (double)(d_lo + DS * woff) + 6.0;
     // rotating windows (2R-1 live entries each)
     double wU0[2 * R - 1], wU1[2 * R - 1], wV0[2 * R - 1], wV1[2 * R - 1];
 #pragma unroll
     for (int k = 0; k < 2 * R - 1; ++k) { wU0[k] = 0.0; wU1[k] = 0.0; wV0[k] = 0.0; wV1[k] = 0.0; }
 
     double k4 = 4.0 * (double)(2 * (d_lo + woff) + 1);    // 4 (2j+1) at tau = 0   (DS == 1 jobs only)
+    (void)k4;
     const bool warp_live = d_lo <= dmax;
 
     for (int tau0 = 0; tau0 <= tau_end; tau0 += V2_TC) {
@@ -344,8 +376,29 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                     }
                     if constexpr (FAM == FAM_00) {
                         // f[r] holds g = f00(j)^2; this warp only visits even-parity j
+                        if constexpr (!E2) {
 #pragma unroll
-                        for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(f[r], w[q], acc[r][q]);
+                            for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(f[r], w[q], acc[r][q]);
+                        } else {
+                            // f22 = f00 N / D on even parity; the 1/D powers are applied in the epilogue
+                            const double t = xj - e2_s[r];
+                            const double nn = fma(t, fma(0.5, t, 1.0), -e2_ab[r]);
+                            const double gn = f[r] * nn;                    // f00 f22 D
+                            if constexpr (JOB == JOB_M02 || JOB == JOB_TEEE) {
+#pragma unroll
+                                for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(gn, w[q], acc[r][q]);
+                            } else if constexpr (JOB == JOB_TETE) {
+                                acc[r][0] = fma(gn, w[0], acc[r][0]);
+                                acc[r][1] = fma(f[r], w[1], acc[r][1]);
+                                acc[r][2] = fma(gn, w[2], acc[r][2]);
+                                acc[r][3] = fma(gn, w[3], acc[r][3]);
+                                acc[r][4] = fma(gn, w[4], acc[r][4]);
+                            } else {                                        // MPP, EEEE, TEEEP: f22^2 D^2
+                                const double gnn = gn * nn;
+#pragma unroll
+                                for (int q = 0; q < NWQ; ++q) acc[r][q] = fma(gnn, w[q], acc[r][q]);
+                            }
+                        }
                         f[r] *= wU0[kU] * wV0[kV];
                     } else {
                         const double ee = f[r] * f[r];
@@ -397,6 +450,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                     }
                 }
                 k4 += 8.0;
+                if constexpr (E2) { xj += xinc; xinc += 8.0; }
             }
             // ---- rotate: next group's carried entries ----
 #pragma unroll
@@ -412,7 +466,27 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int d = d_lo + DS * (woff + e + r);
-        if (d <= dmax) epilogue<JOB>(A, l1, l1 + d, acc[r]);
+        if (d <= dmax) {
+            if constexpr (E2) {
+                // powers of 1/D; l1 < 2 (|m| > l, true symbol 0): exact zeros, as the recurrence path gives
+                const int l2 = l1 + d;
+                double id2 = 0.0;
+                if (l1 >= 2)
+                    id2 = 1.0 / (((double)(l1 - 1) * (double)l1 * ((double)(l1 + 1) * (double)(l1 + 2)))
+                                 * ((double)(l2 - 1) * (double)l2 * ((double)(l2 + 1) * (double)(l2 + 2))));
+                const double id1 = sqrt(id2);
+                if constexpr (JOB == JOB_M02 || JOB == JOB_TEEE) {
+#pragma unroll
+                    for (int q = 0; q < NACC; ++q) acc[r][q] *= id1;
+                } else if constexpr (JOB == JOB_TETE) {
+                    acc[r][0] *= id1; acc[r][2] *= id1; acc[r][3] *= id1; acc[r][4] *= id1;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NACC; ++q) acc[r][q] *= id2;
+                }
+            }
+            epilogue<JOB>(A, l1, l1 + d, acc[r]);
+        }
     }
 }
 

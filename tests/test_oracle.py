@@ -269,3 +269,26 @@ def test_oracle_cov_against_exact_3j_bruteforce(oracle, block):
     for ld in (False, True):
         Cm = oracle.cov(block, 0, lmax, sp, rt, W, ld=ld)
         assert np.max(np.abs(Cm[lo:, lo:] - E[lo:, lo:])) < 1e-13 * max(1.0, np.abs(E[lo:, lo:]).max()), (block, ld)
+
+
+def test_even_parity_spin2_identity_exact():
+    """The identity the tuned kernel uses for every even-parity-only job (psb200_pair_v2.cuh):
+        (j l1 l2; 0 -2 2) = (j l1 l2; 0 0 0) * N(x) / D   for l1+l2+j even,
+        x = j(j+1), a = l1(l1+1), b = l2(l2+1), N = (x-a-b)(x-a-b+2)/2 - a b,
+        D = sqrt((l1-1) l1 (l1+1)(l1+2)(l2-1) l2 (l2+1)(l2+2)),
+    checked on every exact (sympy) family of tests/golden/w3j_exact.npz (l up to 80)."""
+    g = np.load(os.path.join(GOLDEN, "w3j_exact.npz"))
+    fam = {(int(f), int(a), int(b)): g["values"][off:off + n] for f, a, b, off, n in g["index"]}
+    worst, checked = 0.0, 0
+    for (f, l1, l2), f22 in fam.items():
+        if f != 1:
+            continue
+        f00 = fam[(0, l1, l2)]
+        j = np.arange(l2 - l1, l1 + l2 + 1, dtype=np.float64)
+        even = ((l1 + l2 + j.astype(int)) % 2) == 0
+        x, a, b = j * (j + 1), l1 * (l1 + 1.0), l2 * (l2 + 1.0)
+        N = 0.5 * (x - a - b) * (x - a - b + 2) - a * b
+        D = np.sqrt((l1 - 1.0) * l1 * (l1 + 1) * (l1 + 2) * (l2 - 1.0) * l2 * (l2 + 1) * (l2 + 2))
+        worst = max(worst, np.max(np.abs(f22[even] - f00[even] * N[even] / D)))
+        checked += int(even.sum())
+    assert checked > 5000 and worst < 2e-15, (checked, worst)
