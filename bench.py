@@ -47,9 +47,9 @@ JOBS = [
 # From profiles/r01_ncu_final_summary.txt (ncu --set full, 1 GPU, lmax 6143): per-launch DRAM bytes and
 # FP64 pipe activity of each pair kernel.  Quoted next to the live numbers, never used to compute them.
 NCU_R01 = {
-    "M00": {"dram_bytes": 94.8e6, "fp64_pipe_pct": 80.6}, "Mpp_Mmm": {"dram_bytes": 249.5e6, "fp64_pipe_pct": 82.1},
-    "TTTT": {"dram_bytes": 98.1e6, "fp64_pipe_pct": 72.5}, "EEEE": {"dram_bytes": 96.8e6, "fp64_pipe_pct": 75.1},
-    "TETE": {"dram_bytes": 96.5e6, "fp64_pipe_pct": 78.7},
+    "M00": {"dram_bytes": 94.4e6, "fp64_pipe_pct": 80.6}, "Mpp_Mmm": {"dram_bytes": 255.4e6, "fp64_pipe_pct": 82.1},
+    "TTTT": {"dram_bytes": 97.0e6, "fp64_pipe_pct": 72.5}, "EEEE": {"dram_bytes": 98.0e6, "fp64_pipe_pct": 81.6},
+    "TETE": {"dram_bytes": 97.7e6, "fp64_pipe_pct": 79.3},
 }
 
 
