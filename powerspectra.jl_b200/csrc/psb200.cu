@@ -473,19 +473,24 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
     return launch_any(hj.job, A, s.stream);
 }
 
-// Cost of row l1 as the tuned kernel executes it: one warp-block per 192 consecutive d, each running
-// l3 from its first d to min(d + 2 l1, lenW-1) plus the 191-step start skew of the warp, plus a
-// fixed per-block overhead (start values, first staging, epilogue) worth about 48 steps.
+// Cost of row l1 as the tuned kernel executes it.  Most jobs run the two-step f00^2 recurrence: one
+// warp-block per 192 pairs of one parity of d, stepping l3 by 2 from its first d to
+// min(d + 2 l1, lenW-1), plus the 191-step start skew of the warp and a fixed per-block overhead
+// (start values, first table staging, epilogue) worth about 120 steps.
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
+    constexpr long PBN = 192, SKEW = 130, OVH = 120;             // nominal warp tile; skew and overhead weights fitted to per-rank kernel times
     long double c = 0;
-    constexpr long PBN = 192, SKEW = 191;             // nominal warp tile (6 pairs per thread)
-    for (long d_lo = 0; d_lo <= D; d_lo += PBN) {
-        const long last = (long)lenW - 1 - d_lo;
-        const long steps = last < 0 ? 0 : std::min<long>(SKEW + 2L * l1, last) + 1;
-        c += (long double)(steps + 48);
+    for (long base = 0; base <= D; base += 2 * PBN) {
+        for (long par = 0; par < 2; ++par) {
+            const long d_lo = base + par;
+            if (d_lo > D) continue;
+            const long last = (long)lenW - 1 - d_lo;
+            const long steps = last < 0 ? 0 : std::min<long>(SKEW + l1, last / 2) + 1;
+            c += (long double)(steps + OVH);
+        }
     }
     return c;
 }
