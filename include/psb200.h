@@ -132,6 +132,30 @@ int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void*
  * (2 l1+1)(lmax-l1+1) instead. */
 int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges);
 
+/* ---- QuickPol Xi matrix -------------------------------------------------
+ * Replaces the pair loop of quickpolXi! (/root/reference/src/beam.jl:72-101) with Xisum (:16-28)
+ * and the WignerF / wigner3j_f! calls it makes (:86-93):
+ *   Xi[l'', l] = (-1)^(s1+s2+nu1+nu2) sum_{l'} W[l'] (l' l l''; s1+nu1, -s1, -nu1) (l' l l''; s2+nu2, -s2, -nu2)
+ * for l'' = 2..lmax and l = max(2, l''-band_lo) .. min(lmax, l''+band_hi)   (specrowrange, :59-63).
+ * W[0..lenW-1] = quickpolW(omega1, omega2) (:43-56; stays on the host).  Terms with l' > lenW-1 are
+ * dropped (the reference reads W under @inbounds there); entries with |s| > l or |nu| > l'' are 0.
+ * Xb is the storage of the reference's BandedMatrix, parent(parent(Xi)).data: column-major
+ * (band_lo+band_hi+1) x (lmax+1) with leading dimension ldb,
+ *   Xi[l'', l]  at  Xb[(band_hi + l'' - l) + l*ldb].
+ * Only the entries the reference loop visits are written; the caller applies the reference's final
+ * `Xi .*= sgn` (:98-99) to the others if they are non-zero (the visited ones already carry it).
+ * Columns are split over `ngpus` devices in cost-balanced bands; no exchange is needed. */
+int psb200_quickpol_xi(int nu1, int nu2, int s1, int s2, int lmax, const double* W, int lenW,
+                       int band_lo, int band_hi, double* Xb, long ldb, int ngpus);
+
+/* Device-level form: dW, dXb are device pointers, columns l in [col_lo, col_hi) only, asynchronous. */
+int psb200_quickpol_xi_dev(int nu1, int nu2, int s1, int s2, int lmax, const double* dW, int lenW,
+                           int band_lo, int band_hi, double* dXb, long ldb,
+                           int col_lo, int col_hi, void* stream);
+
+/* Cost-balanced contiguous column bands of the Xi matrix: edges[0] = 0 .. edges[nbands] = lmax+1. */
+int psb200_quickpol_edges(int lmax, int band_lo, int band_hi, int nbands, int* edges);
+
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);
 

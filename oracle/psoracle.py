@@ -57,6 +57,9 @@ def lib():
             f = getattr(L, "pso_w3j_family" + suf)
             f.restype = C.c_int
             f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, ip, ip]
+            f = getattr(L, "pso_quickpol_xi" + suf)
+            f.restype = C.c_longlong
+            f.argtypes = [C.c_int] * 5 + [dp, C.c_int, C.c_int, C.c_int, dp, C.c_long]
         L.pso_set_abs_mode.argtypes = [C.c_int]
         L.pso_max_threads.restype = C.c_int
         L.pso_set_threads.argtypes = [C.c_int]
@@ -120,6 +123,33 @@ def cov(block, lmin, lmax, spectra, ratios, W, ld=False, row0=0, rstep=1, thread
     if t < 0:
         raise ValueError("oracle cov: bad arguments")
     return (Cm, t) if return_terms else Cm
+
+
+def band_to_dense(Xb, lmax, band_lo, band_hi):
+    """BandedMatrices storage Xb[band_hi + i - j, j] -> dense A[i, j] (zeros off the band)."""
+    n = lmax + 1
+    A = np.zeros((n, n))
+    for j in range(n):
+        i0, i1 = max(0, j - band_hi), min(n - 1, j + band_lo)
+        A[i0:i1 + 1, j] = Xb[band_hi + i0 - j:band_hi + i1 - j + 1, j]
+    return A
+
+
+def quickpol_xi(nu1, nu2, s1, s2, lmax, W, band_lo, band_hi, ld=False, threads=None, dense=True,
+                return_terms=False):
+    """quickpolXi! (src/beam.jl:72-101).  Returns Xi[l'', l] (dense, zeros off the band and for
+    l'' < 2 or l < 2) or, with dense=False, the (band_lo+band_hi+1) x (lmax+1) band storage."""
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    nb = band_lo + band_hi + 1
+    Xb = np.zeros((nb, lmax + 1), order="F")
+    if threads:
+        lib().pso_set_threads(int(threads))
+    f = lib().pso_quickpol_xi_ld if ld else lib().pso_quickpol_xi
+    t = f(nu1, nu2, s1, s2, lmax, _dp(W), W.size, band_lo, band_hi, _dp(Xb), nb)
+    if t < 0:
+        raise ValueError("oracle quickpol_xi: bad arguments")
+    out = band_to_dense(Xb, lmax, band_lo, band_hi) if dense else Xb
+    return (out, t) if return_terms else out
 
 
 class abs_mode:

@@ -362,3 +362,62 @@ int FN(w3j_family)(int j2, int j3, int m2, int m3, double* out, int nout, int* n
     free(b);
     return n;
 }
+
+/* ---- QuickPol Xi matrix, src/beam.jl:72-101 (quickpolXi!) and :16-28 (Xisum) ----------
+ * For l'' = 2..lmax (one task per row, src/beam.jl:81) and l over the stored band of that
+ * row (specrowrange, src/beam.jl:59-63: l = max(2, l''-band_lo) .. min(lmax, l''+band_hi)):
+ *   wF1 = WignerF(l, l'', -s1, -nu1), wF2 = WignerF(l, l'', -s2, -nu2)      (:86-87)
+ *   Xi[l'', l] = sgn * sum_{l' = max(first1,first2)}^{min(last1,last2)} W[l'] w3j1[l'] w3j2[l']
+ *   sgn = (-1)^(s1+s2+nu1+nu2)                                                (:98-99)
+ * No (2l'+1) and no 1/4pi here: the caller's W (quickpolW, :43-56) carries the weights.
+ * Xb is BandedMatrices' own storage of parent(Xi): Xb[(band_hi + l'' - l) + l*ldb]
+ * (column l of the band, ldb >= band_lo+band_hi+1).  Entries the reference loop does not
+ * visit (rows/columns < 2) are not written.
+ * Two places where the reference leaves behaviour undefined and this restatement decides:
+ *   - l' > lenW-1: the reference indexes W under @inbounds (out of bounds unless the scan
+ *     weights have lmax >= 2*lmax of Xi); here those terms are dropped (W = 0 there);
+ *   - |s| > l or |nu| > l'' (projection larger than the angular momentum): the true symbol
+ *     is 0 and the entry is stored as 0.
+ * abs_mode: sum of |terms| (condition sum for the test tolerance).
+ * Returns the number of 3j terms evaluated (both families, full length). */
+long long FN(quickpol_xi)(int nu1, int nu2, int s1, int s2, int lmax, const double* W, int lenW,
+                          int band_lo, int band_hi, double* Xb, long ldb)
+{
+    if (lmax < 0 || lenW < 1 || band_lo < 0 || band_hi < 0 || ldb < (long)band_lo + band_hi + 1 || !W || !Xb)
+        return -1;
+    long long terms = 0;
+    const int nbuf = 2 * lmax + 1;
+    const REAL sgn = ((s1 + s2 + nu1 + nu2) % 2) ? -1 : 1;
+#pragma omp parallel reduction(+ : terms)
+    {
+        REAL* b1 = (REAL*)malloc(sizeof(REAL) * (nbuf > 0 ? nbuf : 1));
+        REAL* b2 = (REAL*)malloc(sizeof(REAL) * (nbuf > 0 ? nbuf : 1));
+#pragma omp for schedule(dynamic, 1)
+        for (int lpp = 2; lpp <= lmax; ++lpp) {
+            int lo = lpp - band_lo, hi = lpp + band_hi;
+            if (lo < 2) lo = 2;
+            if (hi > lmax) hi = lmax;
+            for (int l = lo; l <= hi; ++l) {
+                REAL acc = 0;
+                if (abs(s1) <= l && abs(s2) <= l && abs(nu1) <= lpp && abs(nu2) <= lpp) {
+                    int min1, max1, min2, max2;
+                    int n1 = FN(family)(l, lpp, -s1, -nu1, b1, &min1, &max1);
+                    int n2 = FN(family)(l, lpp, -s2, -nu2, b2, &min2, &max2);
+                    terms += n1 + n2;
+                    if (n1 > 0 && n2 > 0) {
+                        int a = min1 > min2 ? min1 : min2;
+                        int e = max1 < max2 ? max1 : max2;
+                        if (e > lenW - 1) e = lenW - 1;
+                        for (int lp = a; lp <= e; ++lp) {
+                            REAL t = (REAL)W[lp] * b1[lp - min1] * b2[lp - min2];
+                            acc += pso_abs_mode ? FABS(t) : t;
+                        }
+                    }
+                }
+                Xb[(long)(band_hi + lpp - l) + (long)l * ldb] = (double)(pso_abs_mode ? acc : sgn * acc);
+            }
+        }
+        free(b1); free(b2);
+    }
+    return terms;
+}

@@ -8,6 +8,7 @@ Julia toolchain exists in the build image.  Import name: `powerspectra_jl_b200`
 (the directory name contains a dot; the alias module at the repo root maps it).
 """
 from ._lib import LIB_PATH, PSB200Error, lib
+from .beam import BandedSpectralMatrix, k_u, quickpolW, quickpolXi
 from .covariance import (ConstantDict, CovarianceWorkspace, coupledcov, coupledcovEEEE, coupledcovTEEE,
                          coupledcovTETE, coupledcovTTEE, coupledcovTTTE, coupledcovTTTT, loop_covEEEE,
                          loop_covTEEE, loop_covTEEE_planck, loop_covTETE, loop_covTTEE, loop_covTTTE,
@@ -20,5 +21,5 @@ from .spectral import (BlockSpectralMatrix, SpectralArray, SpectralVector, decou
 __all__ = [
     "mcm", "mcm_master", "maskedalm2spectra", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
     "SpectralArray", "SpectralVector", "BlockSpectralMatrix", "spectralzeros", "spectralones",
-    "decouple_covmat", "Alm", "alm2cl", "lib", "LIB_PATH", "PSB200Error",
+    "decouple_covmat", "BandedSpectralMatrix", "quickpolXi", "quickpolW", "k_u", "Alm", "alm2cl", "lib", "LIB_PATH", "PSB200Error",
 ]

@@ -7,6 +7,7 @@
 #include "psb200_common.cuh"
 #include "psb200_pair_v1.cuh"
 #include "psb200_pair_v2.cuh"
+#include "psb200_quickpol.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -617,6 +618,73 @@ int run_host_job(const HostJob& hj, int ngpus)
     return OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// QuickPol Xi (psb200_quickpol.cuh): columns l of the band storage are independent, so the multi-GPU
+// split is by contiguous column bands of equal cost (a column of nb band rows costs ~ nb * l
+// recurrence steps) and every device moves its own columns to and from the caller's array.
+// ---------------------------------------------------------------------------------------
+int check_quickpol(int lmax, int lenW, int band_lo, int band_hi, long ldb, int col_lo, int col_hi)
+{
+    if (lmax < 0 || lmax > 32767) return fail(ERR_ARG, "need 0 <= lmax <= 32767 (got %d)", lmax);
+    if (lenW < 1) return fail(ERR_ARG, "empty scan spectrum W");
+    if (band_lo < 0 || band_hi < 0 || band_lo > lmax || band_hi > lmax)
+        return fail(ERR_ARG, "band widths (%d, %d) outside [0, lmax]", band_lo, band_hi);
+    if (ldb < (long)band_lo + band_hi + 1) return fail(ERR_ARG, "leading dimension %ld < band_lo+band_hi+1", ldb);
+    if (col_lo < 0 || col_hi > lmax + 1 || col_lo > col_hi)
+        return fail(ERR_ARG, "column band [%d,%d) outside [0,%d]", col_lo, col_hi, lmax);
+    return OK;
+}
+
+int launch_quickpol(const psb::QpArgs& A, cudaStream_t st)
+{
+    const int ncol = A.col_hi - A.col_lo;
+    if (ncol <= 0) return OK;
+    const int nb = A.band_lo + A.band_hi + 1;
+    dim3 grid(ncol, (nb + psb::QP_THREADS - 1) / psb::QP_THREADS);
+    psb::quickpol_kernel<<<grid, psb::QP_THREADS, 0, st>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    return OK;
+}
+
+struct QpHostJob {
+    psb::QpArgs A;              // W / Xb filled per device
+    const double* W;
+    double* Xb;
+};
+
+int run_quickpol_on_device(const QpHostJob& hj, int g, int a, int b, std::string* err)
+{
+    auto body = [&]() -> int {
+        if (b <= a) return OK;
+        CUDA_TRY(cudaSetDevice(g));
+        const int nb = hj.A.band_lo + hj.A.band_hi + 1;
+        const size_t nW = ((size_t)hj.A.lenW + 3) & ~size_t(3);
+        if (int rc = scratch_reserve(g, 5, nW)) return rc;
+        if (int rc = scratch_reserve(g, 0, (size_t)nb * (b - a))) return rc;
+        DeviceScratch& s = g_scratch[g];
+        CUDA_TRY(cudaMemcpyAsync(s.vec, hj.W, (size_t)hj.A.lenW * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        // entries the reference loop does not visit (rows l'' < 2 inside the band) must keep the caller's
+        // values, so the slab starts as a copy of the caller's columns
+        double* host_cols = hj.Xb + (size_t)a * hj.A.ldb;
+        CUDA_TRY(cudaMemcpy2DAsync(s.X[0], (size_t)nb * sizeof(double), host_cols, (size_t)hj.A.ldb * sizeof(double),
+                                   (size_t)nb * sizeof(double), b - a, cudaMemcpyHostToDevice, s.stream));
+        psb::QpArgs A = hj.A;
+        A.W = s.vec;
+        A.ldb = nb;
+        A.Xb = s.X[0] - (long)a * nb;          // the kernel indexes columns from l = 0
+        A.col_lo = a; A.col_hi = b;
+        if (int rc = launch_quickpol(A, s.stream)) return rc;
+        CUDA_TRY(cudaMemcpy2DAsync(host_cols, (size_t)hj.A.ldb * sizeof(double), s.X[0], (size_t)nb * sizeof(double),
+                                   (size_t)nb * sizeof(double), b - a, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        return OK;
+    };
+    const int rc = body();
+    if (rc != OK && err) *err = g_err;
+    return rc;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -776,6 +844,70 @@ int psb200_cov(int block, int lmin, int lmax, const double* const* spectra, int 
     hj.out[0] = C; hj.out[1] = nullptr; hj.ldo = ldC; hj.nout = 1;
     hj.scale = 0;
     return run_host_job(hj, ng);
+}
+
+int psb200_quickpol_edges(int lmax, int band_lo, int band_hi, int nbands, int* edges)
+{
+    if (lmax < 0 || band_lo < 0 || band_hi < 0 || nbands < 1 || !edges) return fail(ERR_ARG, "quickpol_edges: bad arguments");
+    auto cost = [&](int l) -> long double {           // sum over the band rows of column l of min(l, l'')
+        if (l < 2) return 0;
+        const long lo = std::max(2, l - band_hi), hi = std::min(lmax, l + band_lo);
+        const long below = l - lo;                     // rows with l'' < l: min = l''
+        return (long double)below * (lo + l - 1) / 2 + (long double)(hi - l + 1) * l + 64.0L * (hi - lo + 1);
+    };
+    long double total = 0;
+    for (int l = 0; l <= lmax; ++l) total += cost(l);
+    edges[0] = 0;
+    long double run = 0;
+    int b = 1;
+    for (int l = 0; l <= lmax && b < nbands; ++l) {
+        run += cost(l);
+        while (b < nbands && run >= total * b / nbands) edges[b++] = l + 1;
+    }
+    while (b <= nbands) edges[b++] = lmax + 1;
+    return OK;
+}
+
+int psb200_quickpol_xi_dev(int nu1, int nu2, int s1, int s2, int lmax, const double* dW, int lenW,
+                           int band_lo, int band_hi, double* dXb, long ldb, int col_lo, int col_hi, void* stream)
+{
+    if (int rc = check_quickpol(lmax, lenW, band_lo, band_hi, ldb, col_lo, col_hi)) return rc;
+    if (!dW || !dXb) return fail(ERR_ARG, "null buffer");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::QpArgs A{};
+    A.nu1 = nu1; A.nu2 = nu2; A.s1 = s1; A.s2 = s2; A.lmax = lmax; A.lenW = lenW;
+    A.band_lo = band_lo; A.band_hi = band_hi; A.col_lo = col_lo; A.col_hi = col_hi; A.ldb = ldb;
+    A.W = dW; A.Xb = dXb;
+    return launch_quickpol(A, (cudaStream_t)stream);
+}
+
+int psb200_quickpol_xi(int nu1, int nu2, int s1, int s2, int lmax, const double* W, int lenW,
+                       int band_lo, int band_hi, double* Xb, long ldb, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (int rc = check_quickpol(lmax, lenW, band_lo, band_hi, ldb, 0, lmax + 1)) return rc;
+    if (!W || !Xb) return fail(ERR_ARG, "null buffer");
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    QpHostJob hj{};
+    hj.A.nu1 = nu1; hj.A.nu2 = nu2; hj.A.s1 = s1; hj.A.s2 = s2; hj.A.lmax = lmax; hj.A.lenW = lenW;
+    hj.A.band_lo = band_lo; hj.A.band_hi = band_hi; hj.A.ldb = ldb;
+    hj.W = W; hj.Xb = Xb;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::vector<int> edges(ng + 1);
+    psb200_quickpol_edges(lmax, band_lo, band_hi, ng, edges.data());
+    std::vector<int> rcs(ng, OK);
+    std::vector<std::string> errs(ng);
+    std::vector<std::thread> th;
+    for (int g = 1; g < ng; ++g)
+        th.emplace_back([&, g] { rcs[g] = run_quickpol_on_device(hj, g, edges[g], edges[g + 1], &errs[g]); });
+    rcs[0] = run_quickpol_on_device(hj, 0, edges[0], edges[1], &errs[0]);
+    for (auto& t : th) t.join();
+    cudaSetDevice(cur);
+    for (int g = 0; g < ng; ++g)
+        if (rcs[g] != OK) { g_err = "device " + std::to_string(g) + ": " + errs[g]; return rcs[g]; }
+    return OK;
 }
 
 double psb200_dfma_peak(int iters)

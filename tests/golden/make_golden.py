@@ -14,6 +14,11 @@ where /root/reference exists; the fixtures then travel with the repo.
    equations in 384 unknowns; the least-squares solution under the ORACLE's kernels fits all
    of them to ~2e-14 relative, which pins the oracle's f00^2, f22^2 and f00*f22 (even parity,
    diagonal pairs) to NaMaster.  tests/test_oracle.py re-derives the diagonals from V_even.
+4. w3j_general_exact.npz -- exact 3j values (sympy) of the general-spin families the QuickPol
+   path evaluates, f(j) = (j l l''; s+nu, -s, -nu) (/root/reference/src/beam.jl:86-93), for a grid of
+   (s, nu) including the degenerate ones (B(j) = 0 for every j; |s| = l; one-term families), and
+   quickpol_xi_exact: the full Xi matrix of src/beam.jl:72-101 at lmax = 10 from exact 3j symbols
+   for five (nu1, nu2, s1, s2) and one seeded W.
 3. theory_noise_767.npz -- cltt, clte, clee, nltt, nlee (l = 0..767) of test/data/theory.csv and
    noise.csv, the spectra of the reference's covariance test (test/test_covmat.jl:38-45).
 """
@@ -46,6 +51,56 @@ def make_w3j():
     np.savez_compressed(os.path.join(HERE, "w3j_exact.npz"), index=np.array(rows, dtype=np.int64),
                         values=np.array(vals))
     print("w3j_exact:", len(rows), "families,", len(vals), "values")
+
+
+def make_w3j_general():
+    from sympy import N as SN
+    from sympy.physics.wigner import wigner_3j
+    combos = [(s, nu) for s in (-3, -2, -1, 0, 1, 2, 3, 5) for nu in (-2, 0, 2)]
+    pairs = [(2, 2), (2, 3), (3, 2), (4, 4), (5, 7), (7, 5), (6, 6), (9, 12), (12, 12), (16, 11), (20, 20), (5, 30),
+             (30, 28)]
+    rows, vals = [], []
+    for (s, nu) in combos:
+        for (l, lpp) in pairs:
+            if abs(s) > l or abs(nu) > lpp:
+                continue
+            m1 = s + nu
+            lo = max(abs(l - lpp), abs(m1))
+            v = [float(SN(wigner_3j(j, l, lpp, m1, -s, -nu), 30)) for j in range(lo, l + lpp + 1)]
+            rows.append((l, lpp, -s, -nu, lo, len(vals), len(v)))
+            vals.extend(v)
+    # exact Xi matrices at lmax = 10, full band
+    lmax = 10
+    rng = np.random.default_rng(20240611)
+    W = rng.normal(size=2 * lmax + 1)
+    cases = [(0, 0, 0, 0), (2, 2, 2, 2), (-2, 2, 0, 1), (0, 2, 3, -1), (2, -2, -2, 2)]
+    cache = {}
+
+    def fam(l, lpp, s, nu):
+        key = (l, lpp, s, nu)
+        if key not in cache:
+            m1 = s + nu
+            lo = max(abs(l - lpp), abs(m1))
+            cache[key] = (lo, np.array([float(SN(wigner_3j(j, l, lpp, m1, -s, -nu), 30))
+                                        for j in range(lo, l + lpp + 1)]))
+        return cache[key]
+    xis = np.zeros((len(cases), lmax + 1, lmax + 1))
+    for c, (nu1, nu2, s1, s2) in enumerate(cases):
+        sgn = -1.0 if (s1 + s2 + nu1 + nu2) % 2 else 1.0
+        for lpp in range(2, lmax + 1):
+            for l in range(2, lmax + 1):
+                if abs(s1) > l or abs(s2) > l or abs(nu1) > lpp or abs(nu2) > lpp:
+                    continue
+                lo1, f1 = fam(l, lpp, s1, nu1)
+                lo2, f2 = fam(l, lpp, s2, nu2)
+                a = max(lo1, lo2)
+                js = np.arange(a, l + lpp + 1)
+                if js.size:
+                    xis[c, lpp, l] = sgn * np.sum(W[js] * f1[js - lo1] * f2[js - lo2])
+    np.savez_compressed(os.path.join(HERE, "w3j_general_exact.npz"), index=np.array(rows, dtype=np.int64),
+                        values=np.array(vals), xi_lmax=lmax, xi_W=W, xi_cases=np.array(cases, dtype=np.int64),
+                        xi=xis)
+    print("w3j_general_exact:", len(rows), "families,", len(vals), "values;", len(cases), "Xi matrices")
 
 
 def make_namaster():
@@ -89,3 +144,4 @@ if __name__ == "__main__":
     make_theory()
     make_namaster()
     make_w3j()
+    make_w3j_general()
