@@ -636,13 +636,38 @@ int check_quickpol(int lmax, int lenW, int band_lo, int band_hi, long ldb, int c
     return OK;
 }
 
-int launch_quickpol(const psb::QpArgs& A, cudaStream_t st)
+// PSB200_QP=simple selects the table-free variant of the QuickPol kernel (one rsqrt per family and a
+// reciprocal per step); default: the tabulated variant (one rsqrt per step for both families).
+bool quickpol_tabulated()
+{
+    const char* e = getenv("PSB200_QP");
+    return !(e && strcmp(e, "simple") == 0);
+}
+
+int launch_quickpol(psb::QpArgs A, cudaStream_t st)
 {
     const int ncol = A.col_hi - A.col_lo;
     if (ncol <= 0) return OK;
     const int nb = A.band_lo + A.band_hi + 1;
     dim3 grid(ncol, (nb + psb::QP_THREADS - 1) / psb::QP_THREADS);
-    psb::quickpol_kernel<<<grid, psb::QP_THREADS, 0, st>>>(A);
+    if (!quickpol_tabulated()) {
+        psb::quickpol_kernel<false><<<grid, psb::QP_THREADS, 0, st>>>(A);
+        CUDA_TRY(cudaGetLastError());
+        return OK;
+    }
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    const int nT = 2 * A.lmax + 2;                     // j = 0 .. 2 lmax + 1
+    double* buf = nullptr;
+    if (int rc = wp_reserve(dev, st, (size_t)5 * nT, &buf)) return rc;
+    psb::QpD2* bb0 = reinterpret_cast<psb::QpD2*>(buf);
+    psb::QpD2* bb1 = bb0 + nT;
+    double* ij2 = buf + (size_t)4 * nT;
+    psb::quickpol_tables_kernel<<<(nT + 255) / 256, 256, 0, st>>>(ij2, bb0, bb1, nT, A.s1 + A.nu1, A.s2 + A.nu2);
+    CUDA_TRY(cudaGetLastError());
+    A.T.IJ2 = ij2; A.T.BB0 = bb0; A.T.BB1 = bb1;
+    psb::quickpol_kernel<true><<<grid, psb::QP_THREADS, 0, st>>>(A);
     CUDA_TRY(cudaGetLastError());
     return OK;
 }

@@ -24,23 +24,26 @@ def lib():
                             "-o", _OUT, _SRC, "-lm"], check=True, capture_output=True)
         L = C.CDLL(_OUT)
         dp = C.POINTER(C.c_double)
-        L.qp_host_xi.argtypes = [C.c_int] * 5 + [dp, C.c_int, C.c_int, C.c_int, dp, C.c_long]
-        L.qp_host_pair.argtypes = [C.c_int] * 6 + [dp, C.c_int]
+        L.qp_host_xi.argtypes = [C.c_int] * 6 + [dp, C.c_int, C.c_int, C.c_int, dp, C.c_long]
+        L.qp_host_pair.argtypes = [C.c_int] * 7 + [dp, C.c_int]
         L.qp_host_pair.restype = C.c_double
         _lib = L
     return _lib
 
 
-def xi_band(nu1, nu2, s1, s2, lmax, W, band_lo, band_hi):
+VARIANTS = {"simple": 0, "tab": 1}
+
+
+def xi_band(nu1, nu2, s1, s2, lmax, W, band_lo, band_hi, variant="tab"):
     W = np.ascontiguousarray(W, dtype=np.float64)
     nb = band_lo + band_hi + 1
     Xb = np.zeros((nb, lmax + 1), order="F")
     dp = C.POINTER(C.c_double)
-    lib().qp_host_xi(nu1, nu2, s1, s2, lmax, W.ctypes.data_as(dp), W.size, band_lo, band_hi,
+    lib().qp_host_xi(VARIANTS[variant], nu1, nu2, s1, s2, lmax, W.ctypes.data_as(dp), W.size, band_lo, band_hi,
                      Xb.ctypes.data_as(dp), nb)
     return Xb
 
 
-def pair(l, lpp, nu1, nu2, s1, s2, W):
+def pair(l, lpp, nu1, nu2, s1, s2, W, variant="tab"):
     W = np.ascontiguousarray(W, dtype=np.float64)
-    return lib().qp_host_pair(l, lpp, nu1, nu2, s1, s2, W.ctypes.data_as(C.POINTER(C.c_double)), W.size)
+    return lib().qp_host_pair(VARIANTS[variant], l, lpp, nu1, nu2, s1, s2, W.ctypes.data_as(C.POINTER(C.c_double)), W.size)

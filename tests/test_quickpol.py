@@ -94,21 +94,26 @@ def hostcheck():
     return hc
 
 
+VARIANTS = ["tab", "simple"]          # the two instantiations of the CUDA kernel (PSB200_QP)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("case", CASES)
-def test_kernel_arithmetic_on_host_vs_oracle(oracle, hostcheck, case):
+def test_kernel_arithmetic_on_host_vs_oracle(oracle, hostcheck, case, variant):
     lmax, bl, bh = 300, 30, 25
     W = _scan_spectrum(2 * lmax + 1)
     ref, sabs = _oracle_ref(oracle, case, lmax, W, bl, bh)
-    got = hostcheck.xi_band(*case, lmax, W, bl, bh)
+    got = hostcheck.xi_band(*case, lmax, W, bl, bh, variant=variant)
     assert _bound_ratio(got, ref, sabs) < 1.0
     assert np.count_nonzero(ref) > 10000
 
 
-def test_kernel_arithmetic_on_host_exact_and_short_window(oracle, hostcheck):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_kernel_arithmetic_on_host_exact_and_short_window(oracle, hostcheck, variant):
     g = np.load(os.path.join(GOLDEN, "w3j_general_exact.npz"))
     lmax, W = int(g["xi_lmax"]), g["xi_W"]
     for case, exact in zip(g["xi_cases"], g["xi"]):
-        xb = hostcheck.xi_band(*(int(c) for c in case), lmax, W, lmax, lmax)
+        xb = hostcheck.xi_band(*(int(c) for c in case), lmax, W, lmax, lmax, variant=variant)
         assert np.max(np.abs(oracle.band_to_dense(xb, lmax, lmax, lmax) - exact)) < 5e-15
     # window shorter than the families: terms above lenW-1 are dropped, pairs beyond reach are zero
     lmax = 120
@@ -116,11 +121,12 @@ def test_kernel_arithmetic_on_host_exact_and_short_window(oracle, hostcheck):
         W = _scan_spectrum(nW)
         for case in [(0, 0, 0, 0), (2, -2, 2, 1), (0, 2, 3, -1)]:
             ref, sabs = _oracle_ref(oracle, case, lmax, W, 20, 20)
-            got = hostcheck.xi_band(*case, lmax, W, 20, 20)
+            got = hostcheck.xi_band(*case, lmax, W, 20, 20, variant=variant)
             assert _bound_ratio(got, ref, sabs) < 1.0
 
 
-def test_kernel_arithmetic_rescaling_path(oracle, hostcheck):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_kernel_arithmetic_rescaling_path(oracle, hostcheck, variant):
     """Spins close to l: the non-classical regions span > 1e200 in magnitude, so the sweeps rescale."""
     rng = np.random.default_rng(5)
     for (l, lpp, nu1, nu2, s1, s2) in [(2000, 2000, 2, 2, 1990, 1990), (2000, 1990, 2, -2, 1900, -1900),
@@ -133,7 +139,7 @@ def test_kernel_arithmetic_rescaling_path(oracle, hostcheck):
         j = np.arange(a, l + lpp + 1)
         t = W[j] * f1[j - n1] * f2[j - n2]
         ref = (-1.0) ** ((s1 + s2 + nu1 + nu2) % 2) * t.sum()
-        got = hostcheck.pair(l, lpp, nu1, nu2, s1, s2, W)
+        got = hostcheck.pair(l, lpp, nu1, nu2, s1, s2, W, variant=variant)
         assert abs(got - ref) <= 1e-10 * abs(ref) + 1e-13 * np.abs(t).sum(), (l, lpp, s1, s2, got, ref)
 
 
@@ -194,9 +200,16 @@ def test_quickpol_argument_checks(ps):
 # ----------------------------------------------------------------------------------------------------
 # GPU: the CUDA kernel through the C ABI
 # ----------------------------------------------------------------------------------------------------
+@pytest.fixture(params=VARIANTS)
+def qp_variant(request, monkeypatch):
+    """PSB200_QP is read on every call: both instantiations of the kernel are tested in one process."""
+    monkeypatch.setenv("PSB200_QP", request.param)
+    return request.param
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES)
-def test_gpu_quickpol_vs_oracle(ps, oracle, case):
+def test_gpu_quickpol_vs_oracle(ps, oracle, case, qp_variant):
     lmax, bl, bh = 300, 30, 25
     W = _scan_spectrum(2 * lmax + 1)
     ref, sabs = _oracle_ref(oracle, case, lmax, W, bl, bh)
@@ -209,7 +222,7 @@ def test_gpu_quickpol_vs_oracle(ps, oracle, case):
 
 
 @pytest.mark.gpu
-def test_gpu_quickpol_exact_3j_and_untouched_entries(ps, oracle):
+def test_gpu_quickpol_exact_3j_and_untouched_entries(ps, oracle, qp_variant):
     g = np.load(os.path.join(GOLDEN, "w3j_general_exact.npz"))
     lmax, W = int(g["xi_lmax"]), g["xi_W"]
     for case, exact in zip(g["xi_cases"], g["xi"]):
@@ -224,7 +237,7 @@ def test_gpu_quickpol_exact_3j_and_untouched_entries(ps, oracle):
 
 
 @pytest.mark.gpu
-def test_gpu_quickpol_short_window_and_bands(ps, oracle):
+def test_gpu_quickpol_short_window_and_bands(ps, oracle, qp_variant):
     lmax = 200
     for nW, bl, bh in [(1, 10, 10), (2, 0, 0), (7, 5, 40), (60, 40, 5), (401, 200, 200), (1000, 3, 0)]:
         W = _scan_spectrum(nW)
@@ -235,7 +248,7 @@ def test_gpu_quickpol_short_window_and_bands(ps, oracle):
 
 
 @pytest.mark.gpu
-def test_gpu_quickpol_lmax2047_sampled_columns_and_rescaling(ps, oracle):
+def test_gpu_quickpol_lmax2047_sampled_columns_and_rescaling(ps, oracle, qp_variant):
     """Larger problem: every entry of the GPU band against the host build of the same arithmetic is not
     possible on the box (no /root/reference needed, but slow), so the oracle checks a sample of pairs."""
     lmax, bl, bh = 2047, 64, 64
@@ -265,7 +278,7 @@ def test_gpu_quickpol_lmax2047_sampled_columns_and_rescaling(ps, oracle):
 
 
 @pytest.mark.gpu
-def test_gpu_quickpol_two_gpus_and_device_api(ps, oracle):
+def test_gpu_quickpol_two_gpus_and_device_api(ps, oracle, qp_variant):
     import torch
     lmax, bl, bh = 400, 20, 30
     W = _scan_spectrum(2 * lmax + 1)
