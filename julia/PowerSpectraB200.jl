@@ -9,6 +9,7 @@
 #   inner_mcm⁰⁰!  inner_mcm⁰²!  inner_mcm⁺⁺!  inner_mcm⁻⁻!          src/modecoupling.jl:78,99,123,143
 #   loop_covTTTT! loop_covEEEE! loop_covTTTE! loop_covTETE!
 #   loop_covTEEE! loop_covTEEE_planck! loop_covTTEE!                 src/covariance.jl:92,153,208,261,337,376,422
+#   quickpolΞ!(𝚵, ν₁, ν₂, s₁, s₂, ω₁, ω₂, buf1, buf2)                src/beam.jl:72-101
 # Everything else -- mcm, coupledcov, CovarianceWorkspace, window_function_W!, SpectralArray, `\`,
 # decouple_covmat, master -- is the reference's own code and keeps running on the host.
 #
@@ -78,6 +79,28 @@ function cov_call!(block::Int, 𝐂::SpectralArray{Float64,2}, spectra, ratios, 
 end
 
 """
+quickpolΞ! on the GPU.  𝚵 wraps a BandedMatrix over 0:lmax (docs/src/beams.md); its `data` field is the
+(l+u+1) x n band storage the C ABI addresses directly.  quickpolW (src/beam.jl:43-56) stays on the host.
+"""
+function quickpol_call!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂, ω₁, ω₂)
+    size(𝚵, 1) != size(𝚵, 2) && throw(ArgumentError("𝚵 is not square."))
+    lmax = lastindex(𝚵, 1)
+    B = parent(parent(𝚵))                        # OffsetArray -> BandedMatrix
+    W = collect(parent(PowerSpectra.quickpolW(ω₁, ω₂)))
+    bl, bu = PowerSpectra.BandedMatrices.bandwidths(B)
+    data = PowerSpectra.BandedMatrices.bandeddata(B)      # data[u + 1 + i - j, j] = B[i, j]
+    sgn = (-1)^(s₁ + s₂ + ν₁ + ν₂)
+    sgn == -1 && (𝚵[0:1, :] .*= sgn; 𝚵[:, 0:1] .*= sgn)   # entries the loop does not visit only take the sign (:98-99)
+    GC.@preserve W data begin
+        rc = ccall((:psb200_quickpol_xi, LIB[]), Cint,
+                   (Cint, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cdouble}, Clong, Cint),
+                   ν₁, ν₂, s₁, s₂, lmax, W, length(W), bl, bu, data, stride(data, 2), NGPUS[])
+    end
+    check(rc)
+    return 𝚵
+end
+
+"""
     enable!(libpath = "libpsb200.so"; ngpus = 1)
 
 Re-define the inner loops of PowerSpectra to call the B200 library.  `ngpus = 0` uses every
@@ -110,6 +133,10 @@ function enable!(libpath::AbstractString = "libpsb200.so"; ngpus::Integer = 1)
             $(cov_call!)(5, 𝐂, (EEjq, EEjp, TEip, TEiq), (r_EE_jq, r_EE_jp), (W1, W2, W3, W4))
         loop_covTTEE!(𝐂::SpectralArray{Float64,2}, TEip, TEiq, TEjq, TEjp, W1, W2) =
             $(cov_call!)(6, 𝐂, (TEip, TEiq, TEjq, TEjp), (), (W1, W2))
+
+        quickpolΞ!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂, ω₁::Alm, ω₂::Alm,
+                   buf1::Array{Array{Float64,1},1}, buf2::Array{Array{Float64,1},1}) =
+            $(quickpol_call!)(𝚵, ν₁, ν₂, s₁, s₂, ω₁, ω₂)
     end
     return nothing
 end

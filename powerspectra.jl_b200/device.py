@@ -125,6 +125,31 @@ def gather_bands(X: torch.Tensor, edges, lmin, rank, world, group=None):
             w.wait()
 
 
+def quickpol_edges(lmax: int, band_lo: int, band_hi: int, nbands: int):
+    """Cost-balanced column bands of the QuickPol Xi matrix (psb200_quickpol_edges)."""
+    e = (C.c_int * (nbands + 1))()
+    _lib.check(_lib.lib().psb200_quickpol_edges(lmax, band_lo, band_hi, nbands, e))
+    return list(e)
+
+
+def quickpol_slab(nu1, nu2, s1, s2, lmax, W: torch.Tensor, Xb: torch.Tensor, band_lo, band_hi,
+                  col_lo=None, col_hi=None):
+    """Columns [col_lo, col_hi) of the Xi band storage on this rank's GPU (psb200_quickpol_xi_dev).
+    Xb is the FULL (lmax+1, ldb) buffer, row l = column l of the column-major band storage
+    (Xb[l, band_hi + l'' - l]); a band of columns is one contiguous slab, so `gather_bands(Xb, edges, 0, ...)`
+    collects the ranks' slabs on rank 0 exactly as it does for the mode-coupling matrices."""
+    _require_cuda(W)
+    _require_cuda(Xb)
+    if Xb.shape[0] != lmax + 1 or Xb.shape[1] < band_lo + band_hi + 1:
+        raise ValueError("Xb must be (lmax+1, >= band_lo+band_hi+1)")
+    col_lo = 0 if col_lo is None else col_lo
+    col_hi = lmax + 1 if col_hi is None else col_hi
+    rc = _lib.lib().psb200_quickpol_xi_dev(nu1, nu2, s1, s2, lmax, C.c_void_p(W.data_ptr()), W.numel(), band_lo,
+                                           band_hi, C.c_void_p(Xb.data_ptr()), Xb.shape[1], col_lo, col_hi,
+                                           _stream_ptr())
+    _lib.check(rc)
+
+
 def dfma_peak(iters: int = 4096) -> float:
     """Measured FP64 DFMA throughput (FLOP/s) of the current device."""
     v = float(_lib.lib().psb200_dfma_peak(iters))

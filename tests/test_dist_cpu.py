@@ -64,3 +64,36 @@ def test_band_gather_two_ranks(tmp_path, lmin, lmax):
     err, edge = np.load(out)
     assert err < 1e-15          # (x / s) * s rounding only: every band arrived in the right place
     assert lmin < edge <= lmax          # both ranks own rows
+
+
+def _qp_worker(rank, world, port, lmax, bl, bh, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import psoracle as po
+    from powerspectra_jl_b200 import device as dev
+
+    rng = np.random.default_rng(3)
+    W = rng.normal(size=2 * lmax + 1)
+    full = po.quickpol_xi(2, 0, 1, -1, lmax, W, bl, bh, dense=False)       # (nb, lmax+1) band storage
+    edges = dev.quickpol_edges(lmax, bl, bh, world)
+    lo, hi = edges[rank], edges[rank + 1]
+    X = torch.full((lmax + 1, bl + bh + 1), float("nan"), dtype=torch.float64)   # row l = column l of the band storage
+    X[lo:hi] = torch.from_numpy(np.ascontiguousarray(full.T[lo:hi]))          # stand-in for quickpol_slab on my GPU
+    dev.gather_bands(X, edges, 0, rank, world)
+    if rank == 0:
+        Xn = X.numpy()
+        assert not np.isnan(Xn).any(), "a column band did not arrive"
+        np.save(out_path, np.array([float(np.max(np.abs(Xn.T - full))), float(edges[1])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_quickpol_column_gather_two_ranks(tmp_path):
+    out = str(tmp_path / "res.npy")
+    lmax = 90
+    mp.spawn(_qp_worker, args=(2, _free_port(), lmax, 12, 7, out), nprocs=2, join=True)
+    err, edge = np.load(out)
+    assert err == 0.0
+    assert 0.5 * lmax < edge < 0.8 * lmax        # column cost grows with l (plus a fixed per-pair part): split above the middle
