@@ -42,7 +42,8 @@ dW = torch.tensor(W, device="cuda")
 dX = torch.zeros((lmax + 1, nb), device="cuda", dtype=torch.float64)
 res = {"what": "quickpol Xi", "lmax": lmax, "band": band, "case": case, "terms": terms, "pairs": int((lmax - 1) * nb)}
 ref = None
-for variant in ("tab", "simple"):
+fast = bool(os.environ.get("QP_PROBE_FAST"))            # under ncu: device launches only
+for variant in os.environ.get("QP_PROBE_VARIANTS", "tab,simple").split(","):
     os.environ["PSB200_QP"] = variant
 
     def launch():
@@ -63,6 +64,9 @@ for variant in ("tab", "simple"):
     x = dX.cpu().numpy()
     if ref is None:
         ref = x.copy()
+    if fast:
+        res[variant] = {"ms": ms}
+        continue
     Xb = np.zeros((nb, lmax + 1), order="F")
     wp, xp = W.ctypes.data_as(ps._lib.DP), Xb.ctypes.data_as(ps._lib.DP)
     L.psb200_quickpol_xi(nu1, nu2, s1, s2, lmax, wp, W.size, band, band, xp, nb, 1)
@@ -78,6 +82,9 @@ for variant in ("tab", "simple"):
 # CPU oracle on every k-th row (band storage makes a row sample awkward: time a smaller lmax slice of the same
 # band and scale by the exact term ratio is NOT done -- the sample is the low-l part, whose families are shorter,
 # so the oracle's terms/s is reported on its own term count)
+if fast:
+    print(json.dumps(res))
+    sys.exit(0)
 lm_cpu = min(lmax, 1535)
 t0 = time.perf_counter()
 _, t_cpu = po.quickpol_xi(nu1, nu2, s1, s2, lm_cpu, W[: 2 * lm_cpu + 1], band, band, dense=False, return_terms=True)
