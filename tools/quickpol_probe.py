@@ -85,7 +85,7 @@ for variant in os.environ.get("QP_PROBE_VARIANTS", "tab,simple").split(","):
 if fast:
     print(json.dumps(res))
     sys.exit(0)
-lm_cpu = min(lmax, 1535)
+lm_cpu = min(lmax, 3071)
 t0 = time.perf_counter()
 _, t_cpu = po.quickpol_xi(nu1, nu2, s1, s2, lm_cpu, W[: 2 * lm_cpu + 1], band, band, dense=False, return_terms=True)
 dt = time.perf_counter() - t0
