@@ -477,12 +477,14 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
 // Cost of row l1 as the tuned kernel executes it.  Most jobs run the two-step f00^2 recurrence: one
 // warp-block per 192 pairs of one parity of d, stepping l3 by 2 from its first d to
 // min(d + 2 l1, lenW-1), plus the 191-step start skew of the warp and a fixed per-block overhead
-// (start values, first table staging, epilogue) worth about 120 steps.
+// (start values, first table staging, epilogue) worth about 70 steps (least squares over the per-rank pair-kernel
+// times of the 2-, 4- and 8-GPU runs in profiles/bench_r01_n{2,4,8}.json: only SKEW + OVH ~ 200 is constrained,
+// RMS residual 0.12 ms per rank against 0.41 ms for the previous 130 + 120).
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
-    constexpr long PBN = 192, SKEW = 130, OVH = 120;             // nominal warp tile; skew and overhead weights fitted to per-rank kernel times
+    constexpr long PBN = 192, SKEW = 130, OVH = 70;              // nominal warp tile; skew and overhead weights fitted to per-rank kernel times
     long double c = 0;
     for (long base = 0; base <= D; base += 2 * PBN) {
         for (long par = 0; par < 2; ++par) {

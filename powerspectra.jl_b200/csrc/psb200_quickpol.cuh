@@ -92,70 +92,94 @@ PSB_HD void qp_classical(int l, int lpp, int s, int nu, double* jlo, double* jhi
     *jhi = 0.5 * (sqrt(1.0 + 4.0 * xhi) - 1.0);
 }
 
-// Coefficients of both families at index jx >= 1:  an_k = At_k(jx), ian_k = 1/At_k(jx).
-// rjx = 1/jx is returned for the simple variant's 1/(j(j+1)); the table variant does not need it.
-template <bool TAB>
-PSB_HD void qp_coefs(int jx, double d2, double ss, const QpFam& F0, const QpFam& F1, const QpTabs& T,
-                     double* an0, double* ian0, double* an1, double* ian1, double* rjx)
+// State of one sweep (both families): v = L(j) or U(j), p = At * (previous value), vp = previous value,
+// n = sum (2j+1) v^2, s = sum W v_0 v_1.  All in registers after inlining.
+struct QpSweep {
+    double v0, p0, vp0, n0;
+    double v1, p1, vp1, n1;
+    double s;
+};
+
+// One step of a sweep at index j.  The norm and W sums take the values AT j; then both families move to
+// j+1 (forward: jx = j+1) or j-1 (backward: jx = j) with
+//     q = Yt(j) v + p,   p' = At(jx) v,   v' = -q / At(jx).
+// dj = (double)jx, w2 = 2j+1 are carried as doubles (no int->double conversions in the loop).
+// The simple variant also carries rprev = 1/(the other index of the pair {j, j+1}) for 1/(j(j+1)).
+// A family that is not live yet (forward sweep, jx <= |m1_k|) has At = 1/At = 0 and stays at exactly 0.
+template <bool TAB, bool WSUM>
+PSB_HD void qp_step(QpSweep& S, int j, int jx, double dj, double w2, double& rprev, double d2, double ss,
+                    const QpFam& F0, const QpFam& F1, const QpTabs& T, const double* __restrict__ W)
 {
-    const double dj = (double)jx, jj = dj * dj;
+    S.n0 = fma(w2 * S.v0, S.v0, S.n0);
+    S.n1 = fma(w2 * S.v1, S.v1, S.n1);
+    if constexpr (WSUM) S.s = fma(W[j] * S.v0, S.v1, S.s);
+    const double jj = dj * dj;
     const double t12 = (jj - d2) * (ss - jj);
+    double an0, ian0, an1, ian1, y0, y1;
     if constexpr (TAB) {
         const double r = PSB_RSQRT(t12), a = t12 * r;
         const QpD2 b0 = T.BB0[jx], b1 = T.BB1[jx];
-        *an0 = a * b0.x; *ian0 = r * b0.y;
-        *an1 = a * b1.x; *ian1 = r * b1.y;
-        *rjx = 0.0;
-    } else {
-        const double rj = 1.0 / dj, r2 = rj * rj;
-        const double P0 = t12 * ((jj - F0.mm) * r2), P1 = t12 * ((jj - F1.mm) * r2);
-        // a family that is not live yet (jx <= |m1_k|) has P <= 0: keep its state at exactly 0
-        const double r0 = P0 > 0.0 ? PSB_RSQRT(P0) : 0.0, r1 = P1 > 0.0 ? PSB_RSQRT(P1) : 0.0;
-        *an0 = P0 * r0; *ian0 = r0;
-        *an1 = P1 * r1; *ian1 = r1;
-        *rjx = rj;
-    }
-}
-
-// Yt_k(j) for both families; ij = 1/(j(j+1)) (simple variant, 0 at j = 0)
-template <bool TAB>
-PSB_HD void qp_y(int j, double w2, double ij, const QpFam& F0, const QpFam& F1, const QpTabs& T, double* y0, double* y1)
-{
-    if constexpr (TAB) {
         const double t = T.IJ2[j];
-        *y0 = fma(F0.c0, t, F0.dm * w2);
-        *y1 = fma(F1.c0, t, F1.dm * w2);
+        an0 = a * b0.x; ian0 = r * b0.y;
+        an1 = a * b1.x; ian1 = r * b1.y;
+        y0 = fma(F0.c0, t, F0.dm * w2);
+        y1 = fma(F1.c0, t, F1.dm * w2);
     } else {
-        *y0 = -w2 * fma(F0.c0, ij, -F0.dm);
-        *y1 = -w2 * fma(F1.c0, ij, -F1.dm);
+        const double rj = 1.0 / dj, r2 = rj * rj, ij = rj * rprev;
+        const double P0 = t12 * ((jj - F0.mm) * r2), P1 = t12 * ((jj - F1.mm) * r2);
+        const double r0 = P0 > 0.0 ? PSB_RSQRT(P0) : 0.0, r1 = P1 > 0.0 ? PSB_RSQRT(P1) : 0.0;
+        an0 = P0 * r0; ian0 = r0;
+        an1 = P1 * r1; ian1 = r1;
+        y0 = -w2 * fma(F0.c0, ij, -F0.dm);
+        y1 = -w2 * fma(F1.c0, ij, -F1.dm);
+        rprev = rj;
+    }
+    const double q0 = fma(y0, S.v0, S.p0), q1 = fma(y1, S.v1, S.p1);
+    S.vp0 = S.v0; S.p0 = an0 * S.v0; S.v0 = -q0 * ian0;
+    S.vp1 = S.v1; S.p1 = an1 * S.v1; S.v1 = -q1 * ian1;
+}
+
+// Rescaling against overflow.  One step multiplies a value by at most ~1e8 (|Yt| / At), so testing every
+// fourth step against 1e100 keeps everything far below the double range; the branch is almost never taken.
+PSB_HD void qp_rescale(QpSweep& S)
+{
+    const double a0 = fabs(S.v0), a1 = fabs(S.v1);
+    if ((a0 > a1 ? a0 : a1) > QP_BIG) {
+        const double k0 = a0 > QP_BIG ? QP_SMALL : 1.0, k1 = a1 > QP_BIG ? QP_SMALL : 1.0;
+        S.v0 *= k0; S.p0 *= k0; S.vp0 *= k0; S.n0 *= k0 * k0;
+        S.v1 *= k1; S.p1 *= k1; S.vp1 *= k1; S.n1 *= k1 * k1;
+        S.s *= k0 * k1;
     }
 }
 
-// sum_j (2j+1) U(j)^2 of both families swept backward over their whole ranges (U(nmax) = 1).  Only
-// used for the degenerate pairs whose two families overlap in the single term j = nmax.
-template <bool TAB>
-PSB_HD void qp_norm_backward(const QpFam& F0, const QpFam& F1, const QpTabs& T, double d2, double ss, int nmax,
-                             double* n0, double* n1)
+// Steps j = ja, ja+DIR, ..., jb (inclusive; nothing if the range is empty).  DIR = +1 forward, -1 backward.
+template <bool TAB, bool WSUM, int DIR>
+PSB_HD void qp_run(QpSweep& S, int ja, int jb, double& rprev, double d2, double ss,
+                   const QpFam& F0, const QpFam& F1, const QpTabs& T, const double* __restrict__ W)
 {
-    double g0 = 1.0, b0 = 0.0, g1 = 1.0, b1 = 0.0;
-    *n0 = 0.0; *n1 = 0.0;
-    double rj1 = 1.0 / (double)(nmax + 1);
-    const int jend = F0.nmin < F1.nmin ? F0.nmin : F1.nmin;
-    for (int j = nmax; j >= jend; --j) {
-        const double w2 = (double)(2 * j + 1);
-        if (j >= F0.nmin) *n0 = fma(w2 * g0, g0, *n0);
-        if (j >= F1.nmin) *n1 = fma(w2 * g1, g1, *n1);
-        if (j == jend) break;
-        double an0, ian0, an1, ian1, rj, y0, y1;
-        qp_coefs<TAB>(j, d2, ss, F0, F1, T, &an0, &ian0, &an1, &ian1, &rj);
-        qp_y<TAB>(j, w2, rj * rj1, F0, F1, T, &y0, &y1);
-        const double q0 = fma(y0, g0, b0), q1 = fma(y1, g1, b1);
-        b0 = an0 * g0; g0 = -q0 * ian0;          // below its own nmin a family gets ian = 0 and is not summed
-        b1 = an1 * g1; g1 = -q1 * ian1;
-        rj1 = rj;
-        if (fabs(g0) > QP_BIG) { g0 *= QP_SMALL; b0 *= QP_SMALL; *n0 *= QP_SMALL * QP_SMALL; }
-        if (fabs(g1) > QP_BIG) { g1 *= QP_SMALL; b1 *= QP_SMALL; *n1 *= QP_SMALL * QP_SMALL; }
+    int n = DIR > 0 ? jb - ja + 1 : ja - jb + 1;
+    if (n <= 0) return;
+    int j = ja;
+    constexpr int OFF = DIR > 0 ? 1 : 0;                  // jx = j + OFF
+    double dj = (double)(j + OFF), w2 = (double)(2 * j + 1);
+    if constexpr (!TAB) {
+        // 1/(j(j+1)) needs the reciprocal of the index that is NOT jx: j (forward) or j+1 (backward)
+        const int other = DIR > 0 ? j : j + 1;
+        rprev = other > 0 ? 1.0 / (double)other : 0.0;
     }
+    for (; n >= 4; n -= 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            qp_step<TAB, WSUM>(S, j, j + OFF, dj, w2, rprev, d2, ss, F0, F1, T, W);
+            j += DIR; dj += (double)DIR; w2 += 2.0 * DIR;
+        }
+        qp_rescale(S);
+    }
+    for (; n > 0; --n) {
+        qp_step<TAB, WSUM>(S, j, j + OFF, dj, w2, rprev, d2, ss, F0, F1, T, W);
+        j += DIR; dj += (double)DIR; w2 += 2.0 * DIR;
+    }
+    qp_rescale(S);
 }
 
 // One entry of the Xi matrix.  W[0..lenW-1] is 0-based in l'; terms with l' > lenW-1 are dropped.
@@ -171,18 +195,24 @@ PSB_HD double quickpol_pair_t(int l, int lpp, int nu1, int nu2, int s1, int s2, 
     F0.nmin = (m1a < 0 ? -m1a : m1a) > d ? (m1a < 0 ? -m1a : m1a) : d;
     F1.nmin = (m1b < 0 ? -m1b : m1b) > d ? (m1b < 0 ? -m1b : m1b) : d;
     const int nlo = F0.nmin > F1.nmin ? F0.nmin : F1.nmin;
+    const int jA = F0.nmin < F1.nmin ? F0.nmin : F1.nmin;
     const int jW = nmax < lenW - 1 ? nmax : lenW - 1;
     if (nlo > nmax || jW < nlo) return 0.0;                            // no common term inside the window
     const double dl = (double)l * (double)(l + 1) - (double)lpp * (double)(lpp + 1);
     F0.mm = (double)m1a * (double)m1a; F0.c0 = (double)m1a * dl; F0.dm = (double)(s1 - nu1);
     F1.mm = (double)m1b * (double)m1b; F1.c0 = (double)m1b * dl; F1.dm = (double)(s2 - nu2);
     const double d2 = (double)d * (double)d, ss = (double)(nmax + 1) * (double)(nmax + 1);
+    double rprev = 0.0;
 
     if (nlo == nmax) {
-        // the families share only j = nmax, where U_k = 1: Xi = W[nmax] / sqrt(N_1 N_2)
-        double n0, n1;
-        qp_norm_backward<TAB>(F0, F1, T, d2, ss, nmax, &n0, &n1);
-        return (W[nmax] / sqrt(n0)) / sqrt(n1);          // N_k can reach 1e200 each: never multiply them
+        // The families share only j = nmax, where U_k = 1: Xi = W[nmax] / sqrt(N_1 N_2).  The longer family
+        // is swept backward over its whole (short: <= |m1| terms) range for its norm; the other one has the
+        // single term j = nmax, its coefficients below that are 0 and it adds nothing more to its norm.
+        QpSweep B = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0};
+        qp_run<TAB, false, -1>(B, nmax, jA + 1, rprev, d2, ss, F0, F1, T, W);
+        B.n0 = fma((double)(2 * jA + 1) * B.v0, B.v0, B.n0);          // the last value, at j = jA
+        B.n1 = fma((double)(2 * jA + 1) * B.v1, B.v1, B.n1);
+        return (W[nmax] / sqrt(B.n0)) / sqrt(B.n1);      // N_k can reach 1e200 each: never multiply them
     }
 
     // matching point: middle of the intersection of the classical regions, nlo <= c <= nmax-1
@@ -196,64 +226,30 @@ PSB_HD double quickpol_pair_t(int l, int lpp, int nu1, int nu2, int s1, int s2, 
         if (c < nlo) c = nlo;
         if (c > nmax - 1) c = nmax - 1;
     }
+    const int cw = c < jW ? c : jW;                      // last forward step that still sees the window
 
-    // ---------------- forward sweep: j = min(nmin) .. c ----------------
-    // f = L(j), p = At(j) L(j-1), fp = L(j-1).  A family whose nmin = |m1_k| lies above the other's start
-    // stays at exactly 0 until j reaches it (its coefficients are 0 there), then is set to 1.
-    double f0 = 0.0, p0 = 0.0, fp0 = 0.0, nL0 = 0.0;
-    double f1 = 0.0, p1 = 0.0, fp1 = 0.0, nL1 = 0.0;
-    double sLL = 0.0;
-    {
-        int j = F0.nmin < F1.nmin ? F0.nmin : F1.nmin;
-        double rj = (!TAB && j > 0) ? 1.0 / (double)j : 0.0;
-        for (; j <= c; ++j) {
-            if (j == F0.nmin) f0 = 1.0;
-            if (j == F1.nmin) f1 = 1.0;
-            const double w2 = (double)(2 * j + 1);
-            nL0 = fma(w2 * f0, f0, nL0);
-            nL1 = fma(w2 * f1, f1, nL1);
-            if (j >= nlo && j <= jW) sLL = fma(W[j] * f0, f1, sLL);
-            double an0, ian0, an1, ian1, rjp, y0, y1;
-            qp_coefs<TAB>(j + 1, d2, ss, F0, F1, T, &an0, &ian0, &an1, &ian1, &rjp);
-            qp_y<TAB>(j, w2, rj * rjp, F0, F1, T, &y0, &y1);
-            const double q0 = fma(y0, f0, p0), q1 = fma(y1, f1, p1);
-            fp0 = f0; p0 = an0 * f0; f0 = -q0 * ian0;
-            fp1 = f1; p1 = an1 * f1; f1 = -q1 * ian1;
-            rj = rjp;
-            if (fabs(f0) > QP_BIG) { f0 *= QP_SMALL; p0 *= QP_SMALL; fp0 *= QP_SMALL; nL0 *= QP_SMALL * QP_SMALL; sLL *= QP_SMALL; }
-            if (fabs(f1) > QP_BIG) { f1 *= QP_SMALL; p1 *= QP_SMALL; fp1 *= QP_SMALL; nL1 *= QP_SMALL * QP_SMALL; sLL *= QP_SMALL; }
-        }
-    }
-    // now f_k = L_k(c+1), fp_k = L_k(c)
+    // ---------------- forward sweep: L_k(j), j = jA .. c  (values end at c+1) ----------------
+    QpSweep L = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (F0.nmin == jA) L.v0 = 1.0;
+    if (F1.nmin == jA) L.v1 = 1.0;
+    qp_run<TAB, false, +1>(L, jA, nlo - 1, rprev, d2, ss, F0, F1, T, W);    // only the earlier family is live
+    if (F0.nmin > jA) L.v0 = 1.0;                        // the later one starts at j = nlo
+    if (F1.nmin > jA) L.v1 = 1.0;
+    qp_run<TAB, true, +1>(L, nlo, cw, rprev, d2, ss, F0, F1, T, W);
+    qp_run<TAB, false, +1>(L, cw + 1, c, rprev, d2, ss, F0, F1, T, W);
+    // now L.v_k = L_k(c+1), L.vp_k = L_k(c)
 
-    // ---------------- backward sweep: j = nmax .. c+1 ----------------
-    double g0 = 1.0, b0 = 0.0, gp0 = 0.0, nU0 = 0.0;      // g = U(j), b = At(j+1) U(j+1), gp = U(j+1)
-    double g1 = 1.0, b1 = 0.0, gp1 = 0.0, nU1 = 0.0;
-    double sUU = 0.0;
-    {
-        double rj1 = TAB ? 0.0 : 1.0 / (double)(nmax + 1);
-        for (int j = nmax; j > c; --j) {
-            const double w2 = (double)(2 * j + 1);
-            nU0 = fma(w2 * g0, g0, nU0);
-            nU1 = fma(w2 * g1, g1, nU1);
-            if (j <= jW) sUU = fma(W[j] * g0, g1, sUU);
-            double an0, ian0, an1, ian1, rj, y0, y1;
-            qp_coefs<TAB>(j, d2, ss, F0, F1, T, &an0, &ian0, &an1, &ian1, &rj);
-            qp_y<TAB>(j, w2, rj * rj1, F0, F1, T, &y0, &y1);
-            const double q0 = fma(y0, g0, b0), q1 = fma(y1, g1, b1);
-            gp0 = g0; b0 = an0 * g0; g0 = -q0 * ian0;
-            gp1 = g1; b1 = an1 * g1; g1 = -q1 * ian1;
-            rj1 = rj;
-            if (fabs(g0) > QP_BIG) { g0 *= QP_SMALL; b0 *= QP_SMALL; gp0 *= QP_SMALL; nU0 *= QP_SMALL * QP_SMALL; sUU *= QP_SMALL; }
-            if (fabs(g1) > QP_BIG) { g1 *= QP_SMALL; b1 *= QP_SMALL; gp1 *= QP_SMALL; nU1 *= QP_SMALL * QP_SMALL; sUU *= QP_SMALL; }
-        }
-    }
-    // now g_k = U_k(c), gp_k = U_k(c+1)
+    // ---------------- backward sweep: U_k(j), j = nmax .. c+1  (values end at c) ----------------
+    QpSweep U = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0};
+    const int uw = jW > c ? jW : c;                      // first backward step that sees the window
+    qp_run<TAB, false, -1>(U, nmax, uw + 1, rprev, d2, ss, F0, F1, T, W);
+    qp_run<TAB, true, -1>(U, uw, c + 1, rprev, d2, ss, F0, F1, T, W);
+    // now U.v_k = U_k(c), U.vp_k = U_k(c+1)
 
-    const double lam0 = (g0 * fp0 + gp0 * f0) / (fp0 * fp0 + f0 * f0);
-    const double lam1 = (g1 * fp1 + gp1 * f1) / (fp1 * fp1 + f1 * f1);
-    const double N0 = fma(lam0 * lam0, nL0, nU0), N1 = fma(lam1 * lam1, nL1, nU1);
-    return (fma(lam0 * lam1, sLL, sUU) / sqrt(N0)) / sqrt(N1);
+    const double lam0 = (U.v0 * L.vp0 + U.vp0 * L.v0) / (L.vp0 * L.vp0 + L.v0 * L.v0);
+    const double lam1 = (U.v1 * L.vp1 + U.vp1 * L.v1) / (L.vp1 * L.vp1 + L.v1 * L.v1);
+    const double N0 = fma(lam0 * lam0, L.n0, U.n0), N1 = fma(lam1 * lam1, L.n1, U.n1);
+    return (fma(lam0 * lam1, L.s, U.s) / sqrt(N0)) / sqrt(N1);
 }
 
 #ifdef __CUDACC__
