@@ -47,6 +47,12 @@ namespace psb {
 #define PSB_RSQRT(x) (1.0 / sqrt(x))
 #endif
 
+#ifndef PSB200_QP_UNROLL
+#define PSB200_QP_UNROLL 4              // steps between two overflow tests (one step grows a value by < 1e8)
+#endif
+#ifndef PSB200_QP_MINBLOCKS
+#define PSB200_QP_MINBLOCKS 1           // resident 64-thread blocks per SM the register allocation must allow
+#endif
 constexpr double QP_BIG = 1e100;        // rescale threshold
 constexpr double QP_SMALL = 1e-100;
 
@@ -106,20 +112,23 @@ struct QpSweep {
 // dj = (double)jx, w2 = 2j+1 are carried as doubles (no int->double conversions in the loop).
 // The simple variant also carries rprev = 1/(the other index of the pair {j, j+1}) for 1/(j(j+1)).
 // A family that is not live yet (forward sweep, jx <= |m1_k|) has At = 1/At = 0 and stays at exactly 0.
+// pw = &W[j], pij = &IJ2[j], pb0/pb1 = &BB0[jx], &BB1[jx]: the sweeps carry pointers so that the unrolled steps
+// load with immediate offsets (no per-load address arithmetic).
 template <bool TAB, bool WSUM>
-PSB_HD void qp_step(QpSweep& S, int j, int jx, double dj, double w2, double& rprev, double d2, double ss,
-                    const QpFam& F0, const QpFam& F1, const QpTabs& T, const double* __restrict__ W)
+PSB_HD void qp_step(QpSweep& S, const double* __restrict__ pw, const double* __restrict__ pij,
+                    const QpD2* __restrict__ pb0, const QpD2* __restrict__ pb1, double dj, double w2, double& rprev,
+                    double d2, double ss, const QpFam& F0, const QpFam& F1)
 {
     S.n0 = fma(w2 * S.v0, S.v0, S.n0);
     S.n1 = fma(w2 * S.v1, S.v1, S.n1);
-    if constexpr (WSUM) S.s = fma(W[j] * S.v0, S.v1, S.s);
+    if constexpr (WSUM) S.s = fma(*pw * S.v0, S.v1, S.s);
     const double jj = dj * dj;
     const double t12 = (jj - d2) * (ss - jj);
     double an0, ian0, an1, ian1, y0, y1;
     if constexpr (TAB) {
         const double r = PSB_RSQRT(t12), a = t12 * r;
-        const QpD2 b0 = T.BB0[jx], b1 = T.BB1[jx];
-        const double t = T.IJ2[j];
+        const QpD2 b0 = *pb0, b1 = *pb1;
+        const double t = *pij;
         an0 = a * b0.x; ian0 = r * b0.y;
         an1 = a * b1.x; ian1 = r * b1.y;
         y0 = fma(F0.c0, t, F0.dm * w2);
@@ -159,25 +168,33 @@ PSB_HD void qp_run(QpSweep& S, int ja, int jb, double& rprev, double d2, double 
 {
     int n = DIR > 0 ? jb - ja + 1 : ja - jb + 1;
     if (n <= 0) return;
-    int j = ja;
     constexpr int OFF = DIR > 0 ? 1 : 0;                  // jx = j + OFF
-    double dj = (double)(j + OFF), w2 = (double)(2 * j + 1);
+    double dj = (double)(ja + OFF), w2 = (double)(2 * ja + 1);
     if constexpr (!TAB) {
         // 1/(j(j+1)) needs the reciprocal of the index that is NOT jx: j (forward) or j+1 (backward)
-        const int other = DIR > 0 ? j : j + 1;
+        const int other = DIR > 0 ? ja : ja + 1;
         rprev = other > 0 ? 1.0 / (double)other : 0.0;
     }
-    for (; n >= 4; n -= 4) {
+    const double* pw = WSUM ? W + ja : W;
+    const double* pij = TAB ? T.IJ2 + ja : nullptr;
+    const QpD2* pb0 = TAB ? T.BB0 + (ja + OFF) : nullptr;
+    const QpD2* pb1 = TAB ? T.BB1 + (ja + OFF) : nullptr;
+    constexpr int UN = PSB200_QP_UNROLL;
+    for (; n >= UN; n -= UN) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            qp_step<TAB, WSUM>(S, j, j + OFF, dj, w2, rprev, d2, ss, F0, F1, T, W);
-            j += DIR; dj += (double)DIR; w2 += 2.0 * DIR;
+        for (int u = 0; u < UN; ++u) {
+            qp_step<TAB, WSUM>(S, pw + u * DIR, pij + u * DIR, pb0 + u * DIR, pb1 + u * DIR, dj, w2, rprev, d2, ss, F0, F1);
+            dj += (double)DIR; w2 += 2.0 * DIR;
         }
+        if constexpr (WSUM) pw += UN * DIR;
+        if constexpr (TAB) { pij += UN * DIR; pb0 += UN * DIR; pb1 += UN * DIR; }
         qp_rescale(S);
     }
     for (; n > 0; --n) {
-        qp_step<TAB, WSUM>(S, j, j + OFF, dj, w2, rprev, d2, ss, F0, F1, T, W);
-        j += DIR; dj += (double)DIR; w2 += 2.0 * DIR;
+        qp_step<TAB, WSUM>(S, pw, pij, pb0, pb1, dj, w2, rprev, d2, ss, F0, F1);
+        dj += (double)DIR; w2 += 2.0 * DIR;
+        if constexpr (WSUM) pw += DIR;
+        if constexpr (TAB) { pij += DIR; pb0 += DIR; pb1 += DIR; }
     }
     qp_rescale(S);
 }
@@ -279,7 +296,7 @@ __global__ void quickpol_tables_kernel(double* __restrict__ ij2, QpD2* __restric
 }
 
 template <bool TAB>
-__global__ void __launch_bounds__(QP_THREADS) quickpol_kernel(const QpArgs A)
+__global__ void __launch_bounds__(QP_THREADS, PSB200_QP_MINBLOCKS) quickpol_kernel(const QpArgs A)
 {
     const int l = A.col_hi - 1 - (int)blockIdx.x;
     const int nb = A.band_lo + A.band_hi + 1;

@@ -65,7 +65,8 @@ for variant in os.environ.get("QP_PROBE_VARIANTS", "tab,simple").split(","):
     if ref is None:
         ref = x.copy()
     if fast:
-        res[variant] = {"ms": ms}
+        res[variant] = {"ms": ms, "lib": os.environ.get("PSB200_LIB", "default"), "abs_sum": float(np.abs(x).sum()),
+                        "sum": float(x.sum())}
         continue
     Xb = np.zeros((nb, lmax + 1), order="F")
     wp, xp = W.ctypes.data_as(ps._lib.DP), Xb.ctypes.data_as(ps._lib.DP)
