@@ -89,8 +89,9 @@ function quickpol_call!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂
     W = collect(parent(PowerSpectra.quickpolW(ω₁, ω₂)))
     bl, bu = PowerSpectra.BandedMatrices.bandwidths(B)
     data = PowerSpectra.BandedMatrices.bandeddata(B)      # data[u + 1 + i - j, j] = B[i, j]
-    sgn = (-1)^(s₁ + s₂ + ν₁ + ν₂)
-    sgn == -1 && (𝚵[0:1, :] .*= sgn; 𝚵[:, 0:1] .*= sgn)   # entries the loop does not visit only take the sign (:98-99)
+    # `𝚵 .*= sgn` (:98-99): the library overwrites every entry the loop visits (sign included), so scaling the
+    # whole band storage first leaves exactly the unvisited entries (rows / columns below 2) multiplied by sgn
+    isodd(s₁ + s₂ + ν₁ + ν₂) && (data .*= -1)
     GC.@preserve W data begin
         rc = ccall((:psb200_quickpol_xi, LIB[]), Cint,
                    (Cint, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cdouble}, Clong, Cint),

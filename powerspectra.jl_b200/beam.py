@@ -104,18 +104,19 @@ def quickpolXi(Xi: BandedSpectralMatrix, nu1, nu2, s1, s2, omega1, omega2=None, 
     w = np.ascontiguousarray(getattr(W, "parent", W), dtype=np.float64)
     nu1, nu2, s1, s2 = int(nu1), int(nu2), int(s1), int(s2)
     sgn = -1.0 if (s1 + s2 + nu1 + nu2) % 2 else 1.0
-    if sgn < 0 and np.any(Xi.data):
-        # sign of the entries the kernel leaves alone (rows / columns below multipole 2)
-        nb = Xi.band_lo + Xi.band_hi + 1
-        r = np.arange(nb)[:, None]
-        l = np.arange(Xi.lmax + 1)[None, :]
-        lpp = l + r - Xi.band_hi
-        untouched = (l < 2) | (lpp < 2) | (lpp > Xi.lmax)
-        Xi.data[untouched] *= sgn
-    rc = _lib.lib().psb200_quickpol_xi(nu1, nu2, s1, s2, Xi.lmax, w.ctypes.data_as(_lib.DP), w.size,
-                                       Xi.band_lo, Xi.band_hi, Xi.data.ctypes.data_as(_lib.DP),
-                                       Xi.data.shape[0], ngpus)
-    _lib.check(rc)
+    if sgn < 0:
+        # the library overwrites every entry the loop visits (sign included), so scaling the whole band storage
+        # first leaves exactly the unvisited entries (rows / columns below multipole 2) multiplied by sgn
+        Xi.data *= sgn
+    try:
+        rc = _lib.lib().psb200_quickpol_xi(nu1, nu2, s1, s2, Xi.lmax, w.ctypes.data_as(_lib.DP), w.size,
+                                           Xi.band_lo, Xi.band_hi, Xi.data.ctypes.data_as(_lib.DP),
+                                           Xi.data.shape[0], ngpus)
+        _lib.check(rc)
+    except Exception:
+        if sgn < 0:
+            Xi.data *= sgn                      # a failed call leaves 𝚵 as it was
+        raise
     return Xi
 
 

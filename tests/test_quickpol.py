@@ -299,3 +299,12 @@ def test_gpu_quickpol_two_gpus_and_device_api(ps, oracle, qp_variant):
     if torch.cuda.device_count() >= 2:
         two = ps.quickpolXi(ps.BandedSpectralMatrix(lmax, bl, bh), *case, ps.SpectralVector(W), ngpus=2).data
         assert np.array_equal(one, two)
+
+
+def test_failed_call_leaves_matrix_untouched(ps):
+    """Odd s1+s2+nu1+nu2: the mirror pre-scales the storage by the final sign; a failing call must undo that."""
+    Xi = ps.BandedSpectralMatrix(7, 2, 2)
+    Xi.data[:] = 3.0
+    with pytest.raises(ValueError):
+        ps.quickpolXi(Xi, 0, 0, 1, 0, ps.SpectralVector(np.zeros(0)))       # empty W -> bad-argument code 1
+    assert np.all(Xi.data == 3.0)
