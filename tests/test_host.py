@@ -129,3 +129,34 @@ def test_alm2cl_and_workspace(ps):
     w1 = ps.window_function_W(ws, "TT", "TT", "a", "a", "TT", "b", "b", "TT")
     w2 = ps.window_function_W(ws, "TT", "TT", "a", "a", "TT", "b", "b", "TT")
     assert w1 is w2 and len(calls) == 1                      # cached like workspace.W_spectra
+
+
+def test_band_edges_properties_random(ps):
+    """Property test (hypothesis): for any shape the two partitioners return a monotone cover with the right ends,
+    no band is empty while rows remain for the later ones only if the cost demands it, and with the reference
+    term count (lenW = 0) every boundary sits exactly where the prefix sum crosses k/n of the total."""
+    from hypothesis import given, settings, strategies as st
+    from powerspectra_jl_b200 import device as dev
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 40), st.integers(0, 900), st.integers(1, 9), st.integers(0, 1200))
+    def check(lmin, span, nb, lenW):
+        lmax = lmin + span
+        for lw in (0, lenW):
+            e = dev.band_edges(lmin, lmax, nb, lenW=lw)
+            assert len(e) == nb + 1 and e[0] == lmin and e[-1] == lmax + 1
+            assert all(b >= a for a, b in zip(e, e[1:]))
+        e = dev.band_edges(lmin, lmax, nb, lenW=0)
+        l = np.arange(lmin, lmax + 1)
+        cum = np.concatenate([[0], np.cumsum((2 * l + 1) * (lmax - l + 1))]).astype(float)
+        for k in range(1, nb):
+            i = e[k] - lmin                                  # rows [lmin, e[k]) belong to the first k bands
+            assert cum[i] >= cum[-1] * k / nb * (1 - 1e-12)
+            if i > 0 and e[k] > e[k - 1]:
+                assert cum[i - 1] < cum[-1] * k / nb * (1 + 1e-12)
+        # QuickPol column bands
+        bl, bh = min(span, lenW % 50), min(span, lenW % 37)
+        q = dev.quickpol_edges(lmax, bl, bh, nb)
+        assert len(q) == nb + 1 and q[0] == 0 and q[-1] == lmax + 1
+        assert all(b >= a for a, b in zip(q, q[1:]))
+    check()
