@@ -651,7 +651,11 @@ int launch_quickpol(psb::QpArgs A, cudaStream_t st)
     const int ncol = A.col_hi - A.col_lo;
     if (ncol <= 0) return OK;
     const int nb = A.band_lo + A.band_hi + 1;
+#if PSB200_QP_FLAT
+    dim3 grid((unsigned)(((long)ncol * nb + psb::QP_THREADS - 1) / psb::QP_THREADS));
+#else
     dim3 grid(ncol, (nb + psb::QP_THREADS - 1) / psb::QP_THREADS);
+#endif
     if (!quickpol_tabulated()) {
         psb::quickpol_kernel<false><<<grid, psb::QP_THREADS, 0, st>>>(A);
         CUDA_TRY(cudaGetLastError());

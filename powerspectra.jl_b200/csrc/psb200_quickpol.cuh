@@ -50,6 +50,9 @@ namespace psb {
 #ifndef PSB200_QP_UNROLL
 #define PSB200_QP_UNROLL 4              // steps between two overflow tests (one step grows a value by < 1e8)
 #endif
+#ifndef PSB200_QP_FLAT
+#define PSB200_QP_FLAT 0                // 1: flattened (column, row) thread mapping -- next-round experiment
+#endif
 #ifndef PSB200_QP_MINBLOCKS
 #define PSB200_QP_MINBLOCKS 1           // resident 64-thread blocks per SM the register allocation must allow
 #endif
@@ -298,10 +301,21 @@ __global__ void quickpol_tables_kernel(double* __restrict__ ij2, QpD2* __restric
 template <bool TAB>
 __global__ void __launch_bounds__(QP_THREADS, PSB200_QP_MINBLOCKS) quickpol_kernel(const QpArgs A)
 {
-    const int l = A.col_hi - 1 - (int)blockIdx.x;
     const int nb = A.band_lo + A.band_hi + 1;
+#if PSB200_QP_FLAT
+    // experiment for the next round (never run on a GPU yet, default off): (column, band row) flattened into one
+    // index so that no warp is mostly empty -- with 64-thread blocks over 2*128+1 band rows 11 % of the lanes idle
+    const long idx = (long)blockIdx.x * QP_THREADS + (long)threadIdx.x;
+    const long cidx = idx / nb;
+    if (cidx >= (long)(A.col_hi - A.col_lo)) return;
+    const int l = A.col_hi - 1 - (int)cidx;
+    const int r = (int)(idx - cidx * nb);
+    if (l < 2) return;
+#else
+    const int l = A.col_hi - 1 - (int)blockIdx.x;
     const int r = (int)blockIdx.y * QP_THREADS + (int)threadIdx.x;     // band row: l'' = l + r - band_hi
     if (l < A.col_lo || l < 2 || r >= nb) return;
+#endif
     const int lpp = l + r - A.band_hi;
     if (lpp < 2 || lpp > A.lmax) return;
     A.Xb[(long)r + (long)l * A.ldb] = quickpol_pair_t<TAB>(l, lpp, A.nu1, A.nu2, A.s1, A.s2, A.W, A.lenW, A.T);
