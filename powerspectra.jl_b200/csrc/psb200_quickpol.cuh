@@ -48,7 +48,7 @@ namespace psb {
 #endif
 
 #ifndef PSB200_QP_UNROLL
-#define PSB200_QP_UNROLL 4              // steps between two overflow tests (one step grows a value by < 1e8)
+#define PSB200_QP_UNROLL 4              // steps between two overflow tests (see qp_rescale for the bound)
 #endif
 #ifndef PSB200_QP_FLAT
 #define PSB200_QP_FLAT 0                // 1: flattened (column, row) thread mapping -- next-round experiment
@@ -151,8 +151,10 @@ PSB_HD void qp_step(QpSweep& S, const double* __restrict__ pw, const double* __r
     S.vp1 = S.v1; S.p1 = an1 * S.v1; S.v1 = -q1 * ian1;
 }
 
-// Rescaling against overflow.  One step multiplies a value by at most ~1e8 (|Yt| / At), so testing every
-// fourth step against 1e100 keeps everything far below the double range; the branch is almost never taken.
+// Rescaling against overflow.  One step multiplies a value by at most |Yt| / At < (2j+1)(S + |s-nu|) sqrt(j) ~ 1e11
+// for lmax <= 12287 (a crude bound: real growth in the non-classical regions is a small factor per step), so with a
+// test against 1e100 every FOURTH step values stay below 1e145 and the norm terms (2j+1) v^2 below 1e295 -- inside
+// the double range.  Eight steps between tests would not be provably safe.  The branch is almost never taken.
 PSB_HD void qp_rescale(QpSweep& S)
 {
     const double a0 = fabs(S.v0), a1 = fabs(S.v1);
