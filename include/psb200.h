@@ -139,7 +139,7 @@ int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges);
  * for l'' = 2..lmax and l = max(2, l''-band_lo) .. min(lmax, l''+band_hi)   (specrowrange, :59-63).
  * W[0..lenW-1] = quickpolW(omega1, omega2) (:43-56; stays on the host).  Terms with l' > lenW-1 are
  * dropped (the reference reads W under @inbounds there); entries with |s| > l or |nu| > l'' are 0.
- * Xb is the storage of the reference's BandedMatrix, parent(parent(Xi)).data: column-major
+ * Xb is the storage of the reference's BandedMatrix, parent(Xi).data (BandedMatrices.bandeddata): column-major
  * (band_lo+band_hi+1) x (lmax+1) with leading dimension ldb,
  *   Xi[l'', l]  at  Xb[(band_hi + l'' - l) + l*ldb].
  * Only the entries the reference loop visits are written; the caller applies the reference's final

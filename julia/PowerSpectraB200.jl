@@ -85,7 +85,7 @@ quickpolΞ! on the GPU.  𝚵 wraps a BandedMatrix over 0:lmax (docs/src/beams.m
 function quickpol_call!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂, ω₁, ω₂)
     size(𝚵, 1) != size(𝚵, 2) && throw(ArgumentError("𝚵 is not square."))
     lmax = lastindex(𝚵, 1)
-    B = parent(parent(𝚵))                        # OffsetArray -> BandedMatrix
+    B = parent(𝚵)                                # the BandedMatrix (Base.parent(::SpectralArray) unwraps the OffsetArray, src/spectralarray.jl:45)
     W = collect(parent(PowerSpectra.quickpolW(ω₁, ω₂)))
     bl, bu = PowerSpectra.BandedMatrices.bandwidths(B)
     data = PowerSpectra.BandedMatrices.bandeddata(B)      # data[u + 1 + i - j, j] = B[i, j]
