@@ -1,11 +1,11 @@
 """Full-size parity evidence for the QuickPol kernel without a GPU in the loop (run in the build container):
 
-1. the long-double oracle at lmax 6143, band +-128, on the probe's inputs (tools/quickpol_probe.py);
+1. the long-double oracle at lmax 6143, band +-128, on the probe's inputs (tests/tools/quickpol_probe.py);
 2. the host build of the kernel arithmetic (tests/hostcheck, same source as the CUDA kernel) against it;
 3. the checksums the B200 run of the probe printed for the same inputs (profiles/r01_quickpol_ab.jsonl)
    against the checksums of (2) -- ties the device output at full size to (1).
 
-  python tools/quickpol_fullsize_parity.py [lmax] [band] > profiles/r01_quickpol_parity_fullsize.txt
+  python tests/tools/quickpol_fullsize_parity.py [lmax] [band] > profiles/r01_quickpol_parity_fullsize.txt
 """
 import json
 import os
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import hostcheck as hc                                 # noqa: E402
@@ -25,7 +25,7 @@ band = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 case = (2, -2, 2, 2)
 rng = np.random.default_rng(7)
 l = np.arange(2 * lmax + 1)
-W = rng.normal(size=l.size) / (1.0 + l / 40.0) ** 2 + 1.0 / (1.0 + l) ** 1.5      # as tools/quickpol_probe.py
+W = rng.normal(size=l.size) / (1.0 + l / 40.0) ** 2 + 1.0 / (1.0 + l) ** 1.5      # as tests/tools/quickpol_probe.py
 
 t = time.time()
 ref = po.quickpol_xi(*case, lmax, W, band, band, ld=True, dense=False)

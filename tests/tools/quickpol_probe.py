@@ -1,7 +1,7 @@
 """Times the QuickPol Xi kernel (psb200_quickpol_xi[_dev]) on one GPU: both instantiations, device-resident
 and end to end through the host-level C call, next to the CPU oracle on a sample of rows.
 
-  python tools/quickpol_probe.py [lmax] [band] [out.json]
+  python tests/tools/quickpol_probe.py [lmax] [band] [out.json]
 
 A "term" is one 3j family value as the reference evaluates it (src/beam.jl:86-93: two full families per
 stored pair).  Writes one JSON line (stdout and, if given, out.json)."""
@@ -14,7 +14,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import powerspectra_jl_b200 as ps                      # noqa: E402
 from oracle import psoracle as po                      # noqa: E402  (CPU baseline leg only)
 

@@ -6,8 +6,8 @@ cross-spectrum changes sign => cancelling sums).  Columns:
   frac>1e-10  : fraction of entries whose strict relative error exceeds 1e-10
 """
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np
 import powerspectra_jl_b200 as ps
 from oracle import psoracle as po

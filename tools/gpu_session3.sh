@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 : > gpurun_out/qp_ab.jsonl
 for lib in default tools/_build/libpsb200_mb12.so tools/_build/libpsb200_mb14.so tools/_build/libpsb200_mb16.so tools/_build/libpsb200_un8.so tools/_build/libpsb200_un8mb16.so; do
   if [ "$lib" = default ]; then unset PSB200_LIB; else export PSB200_LIB="$PWD/$lib"; fi
-  QP_PROBE_FAST=1 QP_PROBE_VARIANTS=tab,simple timeout 40 python tools/quickpol_probe.py 6143 128 2>&1 | tail -1 >> gpurun_out/qp_ab.jsonl
+  QP_PROBE_FAST=1 QP_PROBE_VARIANTS=tab,simple timeout 40 python tests/tools/quickpol_probe.py 6143 128 2>&1 | tail -1 >> gpurun_out/qp_ab.jsonl
 done
 cat gpurun_out/qp_ab.jsonl | cut -c1-400
 for lib in tools/_build/libpsb200_mb14.so tools/_build/libpsb200_mb16.so; do
