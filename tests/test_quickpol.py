@@ -321,3 +321,32 @@ def test_gpu_quickpol_host_call_across_gpus(ps):
     for ng in sorted({2, n}):
         many = ps.quickpolXi(ps.BandedSpectralMatrix(lmax, bl, bh), *case, ps.SpectralVector(W), ngpus=ng).data
         assert np.array_equal(one, many), ng
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_kernel_arithmetic_random_pairs(oracle, hostcheck, variant):
+    """Property test (hypothesis): any admissible (l, l'', s1, nu1, s2, nu2) and window length -- degenerate
+    families (one or two terms, |s| = l, |nu| = l'', families that overlap in one term, B(j) = 0) included."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=400, deadline=None, derandomize=True)
+    @given(st.integers(2, 70), st.integers(2, 70), st.integers(-70, 70), st.integers(-4, 4), st.integers(-70, 70),
+           st.integers(-4, 4), st.integers(1, 150), st.integers(0, 2 ** 31 - 1))
+    def check(l, lpp, s1, nu1, s2, nu2, nW, seed):
+        s1 = max(-l, min(l, s1))
+        s2 = max(-l, min(l, s2))
+        nu1 = max(-lpp, min(lpp, nu1))
+        nu2 = max(-lpp, min(lpp, nu2))
+        W = np.random.default_rng(seed).normal(size=nW)
+        n1, f1 = oracle.w3j_family(l, lpp, -s1, -nu1, ld=True)
+        n2, f2 = oracle.w3j_family(l, lpp, -s2, -nu2, ld=True)
+        a, e = max(n1, n2), min(l + lpp, nW - 1)
+        ref, sab = 0.0, 0.0
+        if e >= a and f1.size and f2.size:
+            j = np.arange(a, e + 1)
+            t = W[j] * f1[j - n1] * f2[j - n2]
+            ref = (-1.0) ** ((s1 + s2 + nu1 + nu2) % 2) * t.sum()
+            sab = np.abs(t).sum()
+        got = hostcheck.pair(l, lpp, nu1, nu2, s1, s2, W, variant=variant)
+        assert abs(got - ref) <= 1e-10 * abs(ref) + 1e-13 * sab + 1e-300, (l, lpp, s1, nu1, s2, nu2, nW, got, ref)
+    check()
