@@ -630,8 +630,9 @@ int check_quickpol(int lmax, int lenW, int band_lo, int band_hi, long ldb, int c
 {
     if (lmax < 0 || lmax > 32767) return fail(ERR_ARG, "need 0 <= lmax <= 32767 (got %d)", lmax);
     if (lenW < 1) return fail(ERR_ARG, "empty scan spectrum W");
-    if (band_lo < 0 || band_hi < 0 || band_lo > lmax || band_hi > lmax)
-        return fail(ERR_ARG, "band widths (%d, %d) outside [0, lmax]", band_lo, band_hi);
+    // BandedMatrices accepts bandwidths beyond the matrix size (the extra storage rows are padding): so do we
+    if (band_lo < 0 || band_hi < 0 || band_lo > (1 << 20) || band_hi > (1 << 20))
+        return fail(ERR_ARG, "band widths (%d, %d) must be non-negative (and below 2^20)", band_lo, band_hi);
     if (ldb < (long)band_lo + band_hi + 1) return fail(ERR_ARG, "leading dimension %ld < band_lo+band_hi+1", ldb);
     if (col_lo < 0 || col_hi > lmax + 1 || col_lo > col_hi)
         return fail(ERR_ARG, "column band [%d,%d) outside [0,%d]", col_lo, col_hi, lmax);
