@@ -123,6 +123,11 @@ def test_kernel_arithmetic_on_host_exact_and_short_window(oracle, hostcheck, var
             ref, sabs = _oracle_ref(oracle, case, lmax, W, 20, 20)
             got = hostcheck.xi_band(*case, lmax, W, 20, 20, variant=variant)
             assert _bound_ratio(got, ref, sabs) < 1.0
+    # bandwidths beyond the matrix size are legal in BandedMatrices (padding rows of the storage)
+    W = _scan_spectrum(90)
+    ref, sabs = _oracle_ref(oracle, (2, 0, 1, 2), 40, W, 70, 55)
+    got = hostcheck.xi_band(2, 0, 1, 2, 40, W, 70, 55, variant=variant)
+    assert _bound_ratio(got, ref, sabs) < 1.0 and np.count_nonzero(ref) > 1000
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
