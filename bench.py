@@ -431,6 +431,9 @@ def run_gpu(args, lmax):
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                          "flops_model": "F = 20 + 2 n_acc declared flops per 3j term over full families (SURVEY.md 8d)",
                          "fp64_pipe_active_pct_ncu": NCU_R01.get(dom, {}).get("fp64_pipe_pct"),
+                         "frac_note": "frac uses the DECLARED flops of SURVEY.md 8d (full families, sqrt and divide per term); "
+                                      "the kernel executes fewer and cheaper terms, so the kernel-quality figure is "
+                                      "fp64_pipe_active_pct_ncu (share of cycles the FP64 pipe is busy, ncu capture)",
                          "traffic": NCU_R01.get(dom, {}).get("dram_bytes") if world == 1 else None,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full "
                                          "capture profiles/r01_ncu_final_summary.txt (1 GPU, lmax 6143); algorithmic HBM bytes = "
