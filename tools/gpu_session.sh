@@ -9,6 +9,7 @@ step() { echo "=== $1 (t+$(( $(date +%s) - t0 ))s)"; }
 step "quickpol gpu tests"
 timeout 150 python -m pytest tests/test_quickpol.py -m gpu -x -q > gpurun_out/qp_tests.log 2>&1; echo "qp_tests rc=$?"; tail -3 gpurun_out/qp_tests.log
 step "dmma probe"
+[ -x tools/_build/dmma_probe ] || { mkdir -p tools/_build; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/dmma_probe tools/dmma_probe.cu; }
 timeout 30 tools/_build/dmma_probe > gpurun_out/dmma_probe.json 2>&1; echo "dmma rc=$?"; cat gpurun_out/dmma_probe.json
 step "quickpol probe"
 timeout 100 python tests/tools/quickpol_probe.py 6143 128 gpurun_out/quickpol_probe.json > gpurun_out/qp_probe.log 2>&1; echo "probe rc=$?"; tail -2 gpurun_out/qp_probe.log | cut -c1-1500

@@ -1,5 +1,9 @@
 #!/bin/bash
 # A/B of QuickPol kernel builds (register caps / unroll) on one GPU; parity tests on the candidates.
+# The variant libraries are built beforehand in the build container, e.g.
+#   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -DPSB200_QP_MINBLOCKS=14 \
+#        -ccbin /usr/bin/g++ -o tools/_build/libpsb200_mb14.so powerspectra.jl_b200/csrc/psb200.cu -lcudart_static -lpthread -ldl -lrt
+# (mb12/14/16: -DPSB200_QP_MINBLOCKS=..; un8: -DPSB200_QP_UNROLL=8) and selected with PSB200_LIB.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 : > gpurun_out/qp_ab.jsonl
