@@ -13,10 +13,22 @@ over the FULL families exactly as the reference evaluates them:
 Under torchrun (N > 1) the l1 rows are split into N work-balanced bands, every rank computes
 its band, slabs are gathered to rank 0 with NCCL send/recv, rank 0 fills both triangles.
 Total work is fixed => strong scaling.
+
+What the JSON line carries besides the contract keys:
+  roofline.frac      executed FP64 instructions / (time x measured DFMA issue rate) of the dominant kernel:
+                     executed pair-steps (psb200_job_stats: the library's own tiling) x FP64 instructions per
+                     pair-step (counted in the SASS of the loaded libpsb200.so, tools/sass_fp64.py)
+  roofline.useful_frac   same with the LIVE pair-steps only (dead lockstep slots excluded)
+  roofline.declared_frac the SURVEY 8d declared-flop figure (full families, sqrt + divide per term); > 1 is
+                     possible because the kernel executes fewer and cheaper terms than declared
+  multi_gpu_check    the N-GPU host call, the 1-GPU host call and the NCCL-gather driver compared bit for bit
+  parity             strict north-star statistics of sampled rows against the CPU oracle (Float64 and long double)
+  extra              fused master call, TE at lmax 3071, QuickPol, the lmax 12287 sweep point
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -32,6 +44,8 @@ sys.path.insert(0, ROOT)
 METRIC = "3j_terms_per_s (TT+EE/BB MCM and TTTT/EEEE/TETE coupledcov, lmax=6143)"
 UNIT = "terms/s"
 NOMINAL_FP64_TFLOPS = 37.2        # 148 SM x 64 FP64 lanes x 2 x 1.965 GHz
+PARITY_RSTEP = 128                # rows of the in-bench strict-parity statistics (every 128th from row 64)
+CPU_RSTEP = 32                    # the CPU legs time every 32nd l1 row (from row 16) of each call: same rows everywhere
 
 # job name -> (api, code, reference families, [(families fed, n_acc)] for the declared flop model
 #              F = 20 + 2 n_acc per term)
@@ -42,15 +56,22 @@ JOBS = [
     ("EEEE", "cov", 1, 1, [(1, 8)]),
     ("TETE", "cov", 3, 2, [(1, 4), (1, 1)]),
 ]
+SPIN2_JOBS = {"Mpp_Mmm", "EEEE", "TETE"}     # rows l1 < 2 go through low_rows_kernel (one more launch on the band that holds them)
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each pair kernel, from the committed ncu --set full
+# capture named below (1 GPU, lmax 6143).  Quoted as `roofline.traffic`, never used to compute anything.
+NCU_TRAFFIC = {"file": "profiles/r01_ncu_final_summary.txt",
+               "bytes": {"M00": 94.4e6, "Mpp_Mmm": 255.4e6, "TTTT": 97.0e6, "EEEE": 98.0e6, "TETE": 97.7e6}}
+_ncu_json = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+if os.path.exists(_ncu_json):
+    with open(_ncu_json) as _f:
+        NCU_TRAFFIC = json.load(_f)
 
 
-# From profiles/r01_ncu_final_summary.txt (ncu --set full, 1 GPU, lmax 6143): per-launch DRAM bytes and
-# FP64 pipe activity of each pair kernel.  Quoted next to the live numbers, never used to compute them.
-NCU_R01 = {
-    "M00": {"dram_bytes": 94.4e6, "fp64_pipe_pct": 80.6}, "Mpp_Mmm": {"dram_bytes": 255.4e6, "fp64_pipe_pct": 82.1},
-    "TTTT": {"dram_bytes": 97.0e6, "fp64_pipe_pct": 72.5}, "EEEE": {"dram_bytes": 98.0e6, "fp64_pipe_pct": 81.6},
-    "TETE": {"dram_bytes": 97.7e6, "fp64_pipe_pct": 79.3},
-}
+def workload(lmax):
+    """config.workload -- the SAME string in both arms."""
+    return (f"lmax={lmax}: MCM TT + EE/BB(M++,M--), coupledcov TTTT+EEEE+TETE "
+            f"(7 reference families x T_fam={t_fam(lmax):.4e} terms per step)")
 
 
 def job_flops_per_tfam(job):
@@ -76,6 +97,7 @@ def make_inputs(lmax):
     W = lambda *k: ps.window_function_W(ws, *k).parent
     inp = {
         "M00": dict(V=V[(0, 1)]),
+        "M02": dict(V=V[(0, 1)]),
         "Mpp_Mmm": dict(V=V[(1, 1)]),
         "TTTT": dict(
             sp=[sp["TT", i, p].parent, sp["TT", j, q].parent, sp["TT", i, q].parent, sp["TT", j, p].parent],
@@ -104,71 +126,73 @@ def make_inputs(lmax):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the reference-shaped oracle (C/OpenMP restatement; Julia is not installed anywhere)
 # ------------------------------------------------------------------------------------------
-def cpu_sample(inp, lmax, rstep, threads=None):
-    """One bounded sample of the step on the CPU: rows l1 = rstep//2, +rstep, ... of every job.
-    Returns (terms evaluated, seconds)."""
+def cpu_oracle():
+    """The timed CPU build: -O3 -march=native, compiled on THIS machine, all host cores (torchrun exports
+    OMP_NUM_THREADS=1 to its workers: the team size is forced, not inherited)."""
     from oracle import psoracle as po
+    po.use_native_build()
+    cores = po.set_threads(po.host_cores())
+    return po, cores
+
+
+def cpu_sample(po, inp, lmax, rstep=CPU_RSTEP, jobs=JOBS, ld=False):
+    """One bounded sample of the step on the CPU: rows l1 = rstep//2, +rstep, ... of every job.
+    Returns (terms evaluated, seconds, {job: [matrices]})."""
     row0 = rstep // 2
     t0 = time.perf_counter()
     terms = 0
-    for name, api, code, fam, _ in JOBS:
+    out = {}
+    for name, api, code, fam, _ in jobs:
         a = inp[name]
         if api == "mcm":
             if code == 4:      # the reference evaluates the (0,-2,2) family once per block
+                out[name] = []
                 for k in (2, 3):
-                    _, t = po.mcm(k, 0, lmax, a["V"], row0=row0, rstep=rstep, threads=threads, return_terms=True)
+                    M, t = po.mcm(k, 0, lmax, a["V"], row0=row0, rstep=rstep, return_terms=True, ld=ld)
                     terms += t
+                    out[name].append(M)
             else:
-                _, t = po.mcm(code, 0, lmax, a["V"], row0=row0, rstep=rstep, threads=threads, return_terms=True)
+                M, t = po.mcm(code, 0, lmax, a["V"], row0=row0, rstep=rstep, return_terms=True, ld=ld)
                 terms += t
+                out[name] = [M]
         else:
-            _, t = po.cov(code, 0, lmax, a["sp"], a["rt"], a["W"], row0=row0, rstep=rstep, threads=threads,
-                          return_terms=True)
+            M, t = po.cov(code, 0, lmax, a["sp"], a["rt"], a["W"], row0=row0, rstep=rstep, return_terms=True, ld=ld)
             terms += t
-    return terms, time.perf_counter() - t0
+            out[name] = [M]
+    return terms, time.perf_counter() - t0, out
 
 
-def pick_rstep(inp, lmax, target_s):
-    """Choose the row stride so one sample costs ~target_s: a sparse probe first (few rows, so the
-    threads are badly balanced and the rate is pessimistic), then a ~3 s probe, then the answer."""
-    full_terms = sum(j[3] for j in JOBS) * t_fam(lmax)
-    rstep = 1024 if lmax >= 4096 else 64
-    cpu_sample(inp, lmax, 4 * rstep)              # warm the threads / page in the library
-    rate = None
-    for goal in (3.0, target_s):
-        terms, dt = cpu_sample(inp, lmax, rstep)
-        rate = terms / dt
-        rstep = max(4, int(round(full_terms / (rate * goal))))
-    return rstep, rate
+def sample_text(lmax, rstep, terms):
+    nrows = len(range(rstep // 2, lmax + 1, rstep))
+    return (f"every {rstep}th l1 row (rows {rstep // 2}, {rstep // 2 + rstep}, ...: {nrows} rows) of each of the 5 calls, "
+            f"{terms:.3e} terms per sample; C/OpenMP restatement of the reference CPU path built -O3 -march=native "
+            "on this host, not Julia")
 
 
 def run_reference(args, lmax):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import psoracle as po
-    po.build()
+    po, cores = cpu_oracle()
     inp = make_inputs(lmax)
-    cores = po.max_threads()
-    rstep, _ = pick_rstep(inp, lmax, target_s=max(4.0, min(20.0, 150.0 / (args.steps + args.warmup))))
     for _ in range(args.warmup):
-        cpu_sample(inp, lmax, rstep)
+        cpu_sample(po, inp, lmax)
     tt, tn = 0.0, 0
     for _ in range(args.steps):
-        n, dt = cpu_sample(inp, lmax, rstep)
+        n, dt, _ = cpu_sample(po, inp, lmax)
         tt += dt
         tn += n
     value = tn / tt
     full_terms = sum(j[3] for j in JOBS) * t_fam(lmax)
-    sample = f"every {rstep}th l1 row (from row {rstep // 2}) of each of the 5 calls, {tn // args.steps:.3e} terms per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * full_terms / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"lmax={lmax}: MCM TT + EE/BB(M++,M--), coupledcov TTTT+EEEE+TETE",
-                   "note": "C/OpenMP restatement of the reference CPU path (oracle/psoracle.c), not Julia; "
-                           "ms_per_step is the full-step time extrapolated from the row sample by exact term count"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload(lmax),
+                   "note": "CPU arm: each step is the bounded row sample described in cpu_baseline.sample; ms_per_step is "
+                           "the full-step time extrapolated from it by exact term count"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample_text(lmax, CPU_RSTEP, tn / args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -225,6 +249,45 @@ class ClockSampler:
         return out
 
 
+def sass_counts(lib_path):
+    """FP64 instructions per pair-step of every pair kernel, counted live in the loaded library's SASS
+    (tools/sass_fp64.py); the committed count of the same build is the fallback when cuobjdump is absent."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_fp64
+        res, _ = sass_fp64.analyse(lib_path)
+        if res:
+            return res, "cuobjdump -sass of the loaded libpsb200.so (tools/sass_fp64.py), this run"
+    except Exception as e:          # noqa: BLE001 -- any failure falls back to the committed count
+        sys.stderr.write(f"bench: live SASS count failed ({e}); using profiles/r02_sass_fp64.json\n")
+    with open(os.path.join(ROOT, "profiles", "r02_sass_fp64.json")) as f:
+        return json.load(f), "profiles/r02_sass_fp64.json (committed count of the same source)"
+
+
+def job_stats(L, api, code, lmax, lenW, lo, hi):
+    st = (C.c_longlong * 8)()
+    rc = L.psb200_job_stats({"mcm": 0, "cov": 1, "master": 2}[api], code, lmax, lenW, lo, hi, st)
+    assert rc == 0
+    return {"exec_pair_steps": int(st[0]), "live_pair_steps": int(st[1]), "warps": int(st[2])}
+
+
+def strict_stats(G, R, S=None, floor=1e-30):
+    """North-star statistics of one sampled comparison: over every entry with |ref| > floor * max|row|,
+    the largest relative error, the share above 1e-10 (ppm), and the same restricted to entries whose
+    l3 sum cancels by less than 1e3 (S = condition sums, when given)."""
+    rowmax = np.max(np.abs(R), axis=1, keepdims=True)
+    sel = np.abs(R) > floor * rowmax
+    if not sel.any():
+        return {"n": 0}
+    rel = np.abs(G[sel] - R[sel]) / np.abs(R[sel])
+    out = {"n": int(sel.sum()), "strict_max_rel": float(rel.max()), "strict_fail_ppm": float(1e6 * np.mean(rel > 1e-10))}
+    if S is not None:
+        well = np.abs(S[sel]) <= 1e3 * np.abs(R[sel])
+        out["well_conditioned_max_rel"] = float(rel[well].max()) if well.any() else 0.0
+        out["err_over_condition_bound_max"] = float(np.max(np.abs(G[sel] - R[sel]) / (1e-10 * np.abs(R[sel]) + 1e-13 * np.abs(S[sel]))))
+    return out
+
+
 def run_gpu(args, lmax):
     import torch
     import torch.distributed as dist
@@ -249,7 +312,7 @@ def run_gpu(args, lmax):
     inp = make_inputs(lmax)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = {k: {kk: (pin(v) if isinstance(v, np.ndarray) else [pin(x) for x in v]) for kk, v in d.items()}
-            for k, d in inp.items()}
+            for k, d in inp.items() if k in {j[0] for j in JOBS}}
     to_dev = lambda d: {kk: (v.cuda(non_blocking=True) if torch.is_tensor(v) else [x.cuda(non_blocking=True) for x in v])
                         for kk, v in d.items()}
     edges = dev.band_edges(0, lmax, world)
@@ -280,7 +343,7 @@ def run_gpu(args, lmax):
                 dev.mcm_slab(code, 0, lmax, a["V"], X[0], X[1] if len(X) > 1 else None, lo, hi)
             else:
                 dev.cov_slab(code, 0, lmax, a["sp"], a["rt"], a["W"], X[0], lo, hi)
-            launches["n"] += 2          # v2_prep_w + pair_kernel_v2
+            launches["n"] += 2 + (1 if (name in SPIN2_JOBS and lo < 2) else 0)   # v2_prep_w + pair_kernel_v2 (+ low_rows_kernel)
             if record:
                 e1.record()
                 kernel_events.append((name, e0, e1))
@@ -338,6 +401,7 @@ def run_gpu(args, lmax):
     L = ps.lib()
     DP = ps._lib.DP
     ms_driver = None
+    host_out0 = None
     if world > 1:
         host_out0 = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory() for _ in v]
                      for name, v in outs.items()} if rank == 0 else None
@@ -347,37 +411,67 @@ def run_gpu(args, lmax):
             compute(d, False, host_dst=host_out0)
         driver_step()
         ms_driver = timed(driver_step, max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
-        del host_out0
 
     e2e_steps = max(1, min(args.steps, 3))
     wall_e2e = 0.0
+    check = None
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier(group=cpu_group)
+
+    def ptrs(arrs):
+        return (DP * max(len(arrs), 1))(*[a.ctypes.data_as(DP) for a in arrs])
+
+    def host_calls(dst, ngpus, jobs=JOBS):
+        for name, api, code, fam, _ in jobs:
+            a = inp[name]
+            O = dst[name]
+            if api == "mcm":
+                rc = L.psb200_mcm(code, 0, lmax, a["V"].ctypes.data_as(DP), a["V"].size, O[0].ctypes.data_as(DP), N,
+                                  O[1].ctypes.data_as(DP) if len(O) > 1 else None, ngpus)
+            else:
+                rc = L.psb200_cov(code, 0, lmax, ptrs(a["sp"]), len(a["sp"]), ptrs(a["rt"]), len(a["rt"]),
+                                  ptrs(a["W"]), len(a["W"]), a["W"][0].size, O[0].ctypes.data_as(DP), N, ngpus)
+            ps._lib.check(rc)
+
     if rank == 0:
         host_out = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in v]
                     for name, v in outs.items()}
-
-        def ptrs(arrs):
-            return (DP * max(len(arrs), 1))(*[a.ctypes.data_as(DP) for a in arrs])
-
-        def e2e_step():
-            for name, api, code, fam, _ in JOBS:
-                a = inp[name]
-                O = host_out[name]
-                if api == "mcm":
-                    rc = L.psb200_mcm(code, 0, lmax, a["V"].ctypes.data_as(DP), a["V"].size, O[0].ctypes.data_as(DP), N,
-                                      O[1].ctypes.data_as(DP) if len(O) > 1 else None, world)
-                else:
-                    rc = L.psb200_cov(code, 0, lmax, ptrs(a["sp"]), len(a["sp"]), ptrs(a["rt"]), len(a["rt"]),
-                                      ptrs(a["W"]), len(a["W"]), a["W"][0].size, O[0].ctypes.data_as(DP), N, world)
-                ps._lib.check(rc)
         torch.cuda.synchronize()
-        e2e_step()                                   # warm-up (allocations inside the library)
+        host_calls(host_out, world)                  # warm-up (allocations inside the library)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            e2e_step()                               # blocking host calls: wall clock brackets them
+            host_calls(host_out, world)              # blocking host calls: wall clock brackets them
         wall_e2e = (time.perf_counter() - t0) * 1e3
+
+        # ---- the outputs themselves: N-GPU host call == 1-GPU host call == NCCL-gather driver, bit for bit ----
+        # (every (l1,l2) pair is computed independently of the banding, src/modecoupling.jl:84-92, so any difference
+        # is a bug in the band delivery / gather / finish plumbing)
+        check = {"bitwise_equal": True, "max_abs_diff": 0.0, "matrices": 0, "compared": []}
+
+        def cmp(tag, a, b):
+            same = bool(np.array_equal(a, b))
+            check["matrices"] += 1
+            if not same:
+                check["bitwise_equal"] = False
+                check["max_abs_diff"] = max(check["max_abs_diff"], float(np.nanmax(np.abs(a - b))))
+                check.setdefault("mismatch", []).append(tag)
+        one = np.empty((N, N))
+        one2 = np.empty((N, N))
+        for job in JOBS:
+            name = job[0]
+            for k, Xo in enumerate(outs[name]):       # resident path of the timed steps (after gather + finish)
+                cmp(f"{name}[{k}] resident driver vs host call", Xo.cpu().numpy(), host_out[name][k])
+            if world > 1:
+                for k in range(len(outs[name])):      # per-rank driver with its own D2H
+                    cmp(f"{name}[{k}] per-rank driver D2H vs host call", host_out0[name][k].numpy(), host_out[name][k])
+                host_calls({name: [one, one2]}, 1, jobs=[job])
+                for k, ref1 in enumerate([one, one2][:len(outs[name])]):
+                    cmp(f"{name}[{k}] ngpus=1 vs ngpus={world}", ref1, host_out[name][k])
+        check["compared"] = (["device-API driver (bands + NCCL gather + finish) vs C-ABI host call"]
+                             + ([f"C-ABI host call ngpus=1 vs ngpus={world}", "per-rank driver D2H vs C-ABI host call"] if world > 1 else []))
+        del one, one2
+    host_out0 = None
     if world > 1:
         dist.barrier(group=cpu_group)               # gloo: the waiting ranks leave their GPUs idle
     ms_e2e = wall_e2e
@@ -396,22 +490,35 @@ def run_gpu(args, lmax):
         ms_step = ms_total / args.steps
         value = terms_step / (ms_step * 1e-3)
         e2e_value = terms_step / (ms_e2e / e2e_steps * 1e-3)
-        # dominant kernel + roofline (FP64 pipe): declared flops of this rank's band / mean launch time
+        # ---- roofline (FP64 pipe) of the dominant kernel: executed work, measured live ----
         mean_ms = {k: float(np.mean(v)) for k, v in per_job.items()}
         dom = max(mean_ms, key=mean_ms.get)
-        dj = [j for j in JOBS if j[0] == dom][0]
+        peak = dev.dfma_peak(1 << 14) / 1e12                     # TFLOP/s, 2 flops per DFMA lane-instruction
+        issue_peak = peak * 1e12 / 2.0                           # FP64 lane-instructions per second
+        sass, sass_src = sass_counts(ps._lib.LIB_PATH)
         band_tfam = t_fam(lmax, lo, hi)
-        flops = job_flops_per_tfam(dj) * band_tfam
-        achieved = flops / (mean_ms[dom] * 1e-3) / 1e12
-        peak = dev.dfma_peak(1 << 14) / 1e12
-        all_flops = sum(job_flops_per_tfam(j) for j in JOBS) * band_tfam
-        all_kernel_ms = sum(mean_ms.values())
+        kern = {}
+        for job in JOBS:
+            name, api, code = job[0], job[1], job[2]
+            lenW = inp[name]["V"].size if api == "mcm" else inp[name]["W"][0].size
+            st = job_stats(L, api, code, lmax, lenW, lo, hi)
+            sc = sass[name]
+            t = mean_ms[name] * 1e-3
+            kern[name] = {
+                "ms": mean_ms[name], "fp64_instr_per_pair_step": sc["fp64_per_pair_step"],
+                "exec_pair_steps": st["exec_pair_steps"], "live_pair_steps": st["live_pair_steps"],
+                "tiling_efficiency": st["live_pair_steps"] / max(1, st["exec_pair_steps"]),
+                "frac": st["exec_pair_steps"] * sc["fp64_per_pair_step"] / t / issue_peak,
+                "useful_frac": st["live_pair_steps"] * sc["fp64_per_pair_step"] / t / issue_peak,
+                "executed_tflops": st["exec_pair_steps"] * sc["flops_per_pair_step"] / t / 1e12,
+                "declared_frac": job_flops_per_tfam(job) * band_tfam / t / 1e12 / peak,
+            }
+        kd = kern[dom]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"lmax={lmax}: MCM TT + EE/BB(M++,M--), coupledcov TTTT+EEEE+TETE "
-                                   f"(7 reference families x T_fam={t_fam(lmax):.4e} terms per step)",
+            "config": {"workload": workload(lmax),
                        "parallelism": f"l1 row bands x{world}, NCCL gather to rank 0" if world > 1 else "1 GPU",
                        "band_edges": edges, "pair_kernel_ms_per_rank": per_rank_ms,
                        "l2": "outputs (6 x N^2 x 8 B = 1.8 GB per step) exceed L2; inputs are O(lmax) vectors",
@@ -424,35 +531,197 @@ def run_gpu(args, lmax):
                     "per_rank_driver": None if ms_driver is None else {
                         "ms_per_step": ms_driver, "value": terms_step / (ms_driver * 1e-3),
                         "path": "pinned host -> H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0"}},
-            "roofline": {"bound": "fp64", "kernel": f"pair kernel of job {dom}", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": "psb200_dfma_peak DFMA microbenchmark measured in this run "
-                                        f"(MEASURED_PEAKS.json has no FP64 entry; nominal {NOMINAL_FP64_TFLOPS})",
-                         "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
-                         "flops_model": "F = 20 + 2 n_acc declared flops per 3j term over full families (SURVEY.md 8d)",
-                         "fp64_pipe_active_pct_ncu": NCU_R01.get(dom, {}).get("fp64_pipe_pct"),
-                         "frac_note": "frac uses the DECLARED flops of SURVEY.md 8d (full families, sqrt and divide per term); "
-                                      "the kernel executes fewer and cheaper terms, so the kernel-quality figure is "
-                                      "fp64_pipe_active_pct_ncu (share of cycles the FP64 pipe is busy, ncu capture)",
-                         "traffic": NCU_R01.get(dom, {}).get("dram_bytes") if world == 1 else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full "
-                                         "capture profiles/r01_ncu_final_summary.txt (1 GPU, lmax 6143); algorithmic HBM bytes = "
-                                         "the 8 N^2/2 output bytes (151 MB), part of which is still in L2 at kernel end",
-                         "all_kernels": {"declared_tflops": all_flops / (all_kernel_ms * 1e-3) / 1e12,
-                                         "ms": mean_ms}},
+            "roofline": {"bound": "fp64", "kernel": f"pair kernel of job {dom} (rank 0 band)",
+                         "achieved": kd["exec_pair_steps"] * kd["fp64_instr_per_pair_step"] / (kd["ms"] * 1e-3) / 1e12,
+                         "peak": issue_peak / 1e12, "unit": "T FP64 lane-instr/s", "frac": kd["frac"],
+                         "useful_frac": kd["useful_frac"], "declared_frac": kd["declared_frac"],
+                         "how": "achieved = executed pair-steps (psb200_job_stats: lockstep steps x 32 R slots per warp, "
+                                "dead slots included) x FP64 instructions per pair-step (DFMA+DMUL+DADD of the main loop in "
+                                "the SASS) / mean CUDA-event time of the launch; peak = psb200_dfma_peak DFMA microbenchmark "
+                                "of this run / 2 (MEASURED_PEAKS.json has no FP64 entry); useful_frac counts live pair-steps "
+                                "only; declared_frac = SURVEY 8d flops (F = 20 + 2 n_acc per full-family term) / time / peak",
+                         "sass_count_source": sass_src,
+                         "peak_tflops_dfma": peak, "nominal_tflops": NOMINAL_FP64_TFLOPS,
+                         "executed_tflops": kd["executed_tflops"],
+                         "traffic": NCU_TRAFFIC["bytes"].get(dom) if world == 1 else None,
+                         "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full "
+                                         f"capture {NCU_TRAFFIC['file']} (1 GPU, lmax 6143); algorithmic HBM bytes = the 8 N^2/2 "
+                                         "output bytes (151 MB), part of which is still in L2 at kernel end",
+                         "all_kernels": kern},
+            "multi_gpu_check": check,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            from oracle import psoracle as po
-            po.build()
-            rstep, _ = pick_rstep(inp, lmax, target_s=15.0)
-            n, dt = cpu_sample(inp, lmax, rstep)
-            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": po.max_threads(), "kind": "port",
-                                    "sample": f"every {rstep}th l1 row of each of the 5 calls ({n:.3e} terms, {dt:.1f} s); "
-                                              "C/OpenMP restatement of the reference CPU path, not Julia"}
+            po, cores = cpu_oracle()
+            n, dt, ref64 = cpu_sample(po, inp, lmax)
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": sample_text(lmax, CPU_RSTEP, n) + f" ({dt:.1f} s)"}
+            # strict north-star statistics on a sparser row sample: GPU and Float64 oracle against long double
+            _, _, r64 = cpu_sample(po, inp, lmax, rstep=PARITY_RSTEP)
+            _, _, rld = cpu_sample(po, inp, lmax, rstep=PARITY_RSTEP, ld=True)
+            rows = np.arange(PARITY_RSTEP // 2, lmax + 1, PARITY_RSTEP)
+            par = {}
+            for name in r64:
+                for k, (R64, RLD) in enumerate(zip(r64[name], rld[name])):
+                    tag = name if len(r64[name]) == 1 else f"{name}[{k}]"
+                    G = host_out[name][k]          # column-major (l1, l2) = numpy [l2, l1]
+                    gm = np.zeros((len(rows), N)); om = np.zeros_like(gm); rm = np.zeros_like(gm)
+                    for i, r in enumerate(rows):   # sampled row l1 = r, columns l2 >= l1
+                        gm[i, r:] = G[r:, r]
+                        om[i, r:] = R64[r, r:]
+                        rm[i, r:] = RLD[r, r:]
+                    par[tag] = {"gpu_vs_long_double": strict_stats(gm, rm), "f64_oracle_vs_long_double": strict_stats(om, rm),
+                                "gpu_vs_f64_oracle": strict_stats(gm, om)}
+            line["parity"] = {"rows": f"every {PARITY_RSTEP}th l1 row from {PARITY_RSTEP // 2}, columns l2 >= l1",
+                              "criterion": "north star: |err|/|ref| <= 1e-10 on every entry above 1e-30 of its row maximum; "
+                                           "entries whose l3 sum cancels by > 1e3 cannot meet it in ANY Float64 evaluation "
+                                           "(see f64_oracle_vs_long_double); the test suite gates on the condition-aware bound",
+                              "per_matrix": par}
+        if not args.no_extra:
+            line["extra"] = extras(args, ps, dev, L, world, torch, cpu=(world == 1 and not args.no_cpu))
         print(json.dumps(line))
+        if check is not None and not check["bitwise_equal"]:
+            sys.stderr.write("bench: multi_gpu_check FAILED: " + json.dumps(check) + "\n")
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(3)
     if world > 1:
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# extras: measured outside the headline timed region, on rank 0's GPU(s) through the C ABI
+# ------------------------------------------------------------------------------------------
+def extras(args, ps, dev, L, world, torch, cpu):
+    from powerspectra_jl_b200 import synthetic as syn
+    DP = ps._lib.DP
+    out = {}
+
+    def dtime(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def wtime(fn, reps=2):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) * 1e3 / reps
+
+    po = None
+    if cpu:
+        po, cores = cpu_oracle()
+
+    # (1) fused master call vs the separate calls it replaces, lmax 6143, resident, 1 GPU
+    lmax = args.lmax
+    N = lmax + 1
+    sky_V = syn.mask_spectra(lmax, seeds=(1001, 1002))
+    Vd = {k: torch.tensor(v, device="cuda") for k, v in sky_V.items()}
+    X = [torch.empty((N, N), dtype=torch.float64, device="cuda") for _ in range(5)]
+
+    def fused():
+        dev.master_slab(0, lmax, Vd[(0, 0)], Vd[(0, 1)], Vd[(1, 0)], Vd[(1, 1)], X)
+        for k in range(5):
+            dev.finish(X[k], 0, lmax, True)
+
+    def separate():
+        dev.mcm_slab(0, 0, lmax, Vd[(0, 0)], X[0])
+        dev.mcm_slab(1, 0, lmax, Vd[(0, 1)], X[1])
+        dev.mcm_slab(1, 0, lmax, Vd[(1, 0)], X[2])
+        dev.mcm_slab(4, 0, lmax, Vd[(1, 1)], X[3], X[4])
+        for k in range(5):
+            dev.finish(X[k], 0, lmax, True)
+    t_f, t_s = dtime(fused), dtime(separate)
+    out["master_fused"] = {"lmax": lmax, "fused_ms": t_f, "separate_calls_ms": t_s, "speedup": t_s / t_f,
+                           "terms_per_s": 7 * t_fam(lmax) / (t_f * 1e-3),
+                           "what": "psb200_mcm_master_dev (M00, M02 x2, M++, M--) vs psb200_mcm_dev kinds 0, 1, 1, 4; device-resident, 1 GPU"}
+    del X, Vd
+    torch.cuda.empty_cache()
+
+    # (2) TE mode-coupling matrix at lmax 3071 (BASELINE configs[1]) and (4) the lmax 12287 sweep point (configs[4])
+    for tag, lm, kind, fam in (("TE_lmax3071", 3071, 1, 2), ("TT_lmax12287", 12287, 0, 1), ("EE_BB_lmax12287", 12287, 4, 2)):
+        n = lm + 1
+        V = syn.mask_spectra(lm, seeds=(1001, 1002))[(0, 1)]
+        Vt = torch.tensor(V, device="cuda")
+        nout = 2 if kind == 4 else 1
+        Xs = [torch.empty((n, n), dtype=torch.float64, device="cuda") for _ in range(nout)]
+
+        def resident():
+            dev.mcm_slab(kind, 0, lm, Vt, Xs[0], Xs[1] if nout > 1 else None)
+            for x in Xs:
+                dev.finish(x, 0, lm, True)
+        t_r = dtime(resident, reps=2)
+        del Xs
+        torch.cuda.empty_cache()
+        Hs = [torch.empty((n, n), dtype=torch.float64).pin_memory().numpy() for _ in range(nout)]
+
+        def e2e():
+            ps._lib.check(L.psb200_mcm(kind, 0, lm, V.ctypes.data_as(DP), V.size, Hs[0].ctypes.data_as(DP), n,
+                                       Hs[1].ctypes.data_as(DP) if nout > 1 else None, world))
+        t_e = wtime(e2e, reps=2)
+        terms = fam * t_fam(lm)
+        rec = {"lmax": lm, "kind": kind, "ms_resident_1gpu": t_r, "terms_per_s": terms / (t_r * 1e-3),
+               "e2e_ms": t_e, "e2e_terms_per_s": terms / (t_e * 1e-3), "e2e_ngpus": world,
+               "d2h_bytes": nout * n * n * 8}
+        if po is not None:
+            rstep = 32 if lm <= 4096 else 128
+            t0 = time.perf_counter()
+            tn = 0
+            for k in ((2, 3) if kind == 4 else (kind,)):
+                _, t = po.mcm(k, 0, lm, V, row0=rstep // 2, rstep=rstep, return_terms=True)
+                tn += t
+            dt = time.perf_counter() - t0
+            rec["cpu_baseline"] = {"value": tn / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"every {rstep}th l1 row from {rstep // 2} ({tn:.3e} terms, {dt:.1f} s)"}
+            rec["speedup_vs_cpu_e2e"] = rec["e2e_terms_per_s"] / (tn / dt)
+        out[tag] = rec
+        del Hs
+
+    # (3) QuickPol Xi matrix: lmax 6143, band +-128, (nu1, nu2, s1, s2) = (2, -2, 2, 2)
+    lm, band = args.lmax, 128
+    nb = 2 * band + 1
+    rng = np.random.default_rng(7)
+    l = np.arange(2 * lm + 1)
+    W = rng.normal(size=l.size) / (1.0 + l / 40.0) ** 2 + 1.0 / (1.0 + l) ** 1.5
+    nu1, nu2, s1, s2 = 2, -2, 2, 2
+    qterms = 0
+    for lpp in range(2, lm + 1):
+        ls = np.arange(max(2, lpp - band), min(lm, lpp + band) + 1)
+        d = np.abs(ls - lpp)
+        for m1 in (s1 + nu1, s2 + nu2):
+            qterms += int(np.sum(np.maximum(ls + lpp - np.maximum(d, abs(m1)) + 1, 0)))
+    dW = torch.tensor(W, device="cuda")
+    dX = torch.zeros((lm + 1, nb), device="cuda", dtype=torch.float64)
+    t_r = dtime(lambda: dev.quickpol_slab(nu1, nu2, s1, s2, lm, dW, dX, band, band), reps=3)
+    Xb = np.zeros((lm + 1, nb))
+
+    def qe2e():
+        ps._lib.check(L.psb200_quickpol_xi(nu1, nu2, s1, s2, lm, W.ctypes.data_as(DP), W.size, band, band,
+                                           Xb.ctypes.data_as(DP), nb, world))
+    t_e = wtime(qe2e, reps=2)
+    rec = {"lmax": lm, "band": band, "case": [nu1, nu2, s1, s2], "terms": qterms, "ms_resident_1gpu": t_r,
+           "terms_per_s": qterms / (t_r * 1e-3), "e2e_ms": t_e, "e2e_terms_per_s": qterms / (t_e * 1e-3), "e2e_ngpus": world}
+    if po is not None:
+        # CPU sample: the band of the first 1/16 of the rows is cheap and unrepresentative; time a smaller matrix of
+        # the same band instead and quote its own term rate
+        lm_c = 1535
+        Wc = W[:2 * lm_c + 1]
+        t0 = time.perf_counter()
+        _, tn = po.quickpol_xi(nu1, nu2, s1, s2, lm_c, Wc, band, band, dense=False, return_terms=True)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": tn / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"the whole Xi matrix at lmax {lm_c}, same band ({tn:.3e} terms, {dt:.1f} s)"}
+        rec["speedup_vs_cpu_e2e"] = rec["e2e_terms_per_s"] / (tn / dt)
+    out["quickpol"] = rec
+    return out
 
 
 def main():
@@ -462,7 +731,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lmax", type=int, default=6143)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (master, TE, QuickPol, lmax 12287)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, args.lmax)

@@ -159,6 +159,16 @@ int psb200_quickpol_edges(int lmax, int band_lo, int band_hi, int nbands, int* e
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);
 
+/* Work accounting of ONE pair-kernel launch as the tuned kernel tiles it (host arithmetic, no device needed);
+ * what bench.py turns into the executed-work roofline fraction.  api/code: 0/kind = psb200_mcm kinds,
+ * 1/block = psb200_cov blocks, 2/0 = psb200_mcm_master.  lenW = window length of the call.
+ *   out[0] executed pair-steps: lockstep l3 steps of every warp x its 32 R pair slots (dead slots included)
+ *   out[1] live pair-steps: every pair over its own l3 range (truncated at lenW-1, one parity where the job
+ *          steps l3 by 2) -- the part of out[0] that is needed
+ *   out[2] warps launched   out[3] pairs per thread R   out[4] rows per warp   out[5] l3 stride
+ * Rows l1 < 2 of the spin-2 jobs are evaluated by a separate tiny kernel and not counted. */
+int psb200_job_stats(int api, int code, int lmax, int lenW, int row_lo, int row_hi, long long* out);
+
 /* FP64 pipe microbenchmark: dependent-free DFMA streams on every SM for `iters` iterations;
  * returns achieved FLOP/s (2 per DFMA) on the current device, <0 on error. */
 double psb200_dfma_peak(int iters);

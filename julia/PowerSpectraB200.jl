@@ -46,6 +46,7 @@ function mcm_call!(kind::Int, 𝐌::SpectralArray{Float64,2}, V::SpectralVector{
                    𝐌2::Union{Nothing,SpectralArray{Float64,2}} = nothing)
     @assert axes(𝐌, 1) == axes(𝐌, 2)
     lmin, lmax = first(axes(𝐌, 1)), last(axes(𝐌, 1))
+    firstindex(V) == 0 || throw(ArgumentError("window spectrum must start at l = 0 (got $(firstindex(V)))"))
     v = collect(parent(V))                       # V is 0-indexed: SpectralVector(alm2cl(...)[1:lmax+1])
     P = parent(𝐌)                                # dense column-major N x N
     p2 = 𝐌2 === nothing ? Ptr{Cdouble}(C_NULL) : pointer(parent(𝐌2))
@@ -63,6 +64,7 @@ function cov_call!(block::Int, 𝐂::SpectralArray{Float64,2}, spectra, ratios, 
     lmin, lmax = first(axes(𝐂, 1)), last(axes(𝐂, 1))
     sp = [zero_based(s, lmax) for s in spectra]
     rt = [zero_based(r, lmax) for r in ratios]
+    all(w -> firstindex(w) == 0, Ws) || throw(ArgumentError("window spectra must start at l = 0"))
     ws = [collect(parent(w)) for w in Ws]        # 0-indexed, length workspace.lmax + 1
     lenW = minimum(length, ws)
     psp, prt, pws = pointer.(sp), pointer.(rt), pointer.(ws)
@@ -91,12 +93,14 @@ function quickpol_call!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂
     data = PowerSpectra.BandedMatrices.bandeddata(B)      # data[u + 1 + i - j, j] = B[i, j]
     # `𝚵 .*= sgn` (:98-99): the library overwrites every entry the loop visits (sign included), so scaling the
     # whole band storage first leaves exactly the unvisited entries (rows / columns below 2) multiplied by sgn
-    isodd(s₁ + s₂ + ν₁ + ν₂) && (data .*= -1)
-    GC.@preserve W data begin
-        rc = ccall((:psb200_quickpol_xi, LIB[]), Cint,
-                   (Cint, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cdouble}, Clong, Cint),
-                   ν₁, ν₂, s₁, s₂, lmax, W, length(W), bl, bu, data, stride(data, 2), NGPUS[])
+    flip = isodd(s₁ + s₂ + ν₁ + ν₂)
+    flip && (data .*= -1)
+    rc = GC.@preserve W data begin
+        ccall((:psb200_quickpol_xi, LIB[]), Cint,
+              (Cint, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cdouble}, Clong, Cint),
+              ν₁, ν₂, s₁, s₂, lmax, W, length(W), bl, bu, data, stride(data, 2), NGPUS[])
     end
+    rc != 0 && flip && (data .*= -1)             # a failed call leaves the matrix as it was handed in
     check(rc)
     return 𝚵
 end
@@ -118,21 +122,30 @@ function enable!(libpath::AbstractString = "libpsb200.so"; ngpus::Integer = 1)
         inner_mcm⁺⁺!(𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64}) = $(mcm_call!)(2, 𝐌, V)
         inner_mcm⁻⁻!(𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64}) = $(mcm_call!)(3, 𝐌, V)
 
-        loop_covTTTT!(𝐂::SpectralArray{Float64,2}, TTip, TTjq, TTiq, TTjp, r_ip, r_jq, r_iq, r_jp,
+        # The spectra / ratio arguments carry the reference's own types (src/covariance.jl:92-97 etc.) with T = Float64,
+        # so every override is strictly more specific than the method it shadows (typing only 𝐂 would make the
+        # two methods ambiguous: ours wins on argument 1, the reference's on arguments 2 onward).
+        loop_covTTTT!(𝐂::SpectralArray{Float64,2}, TTip::SpectralVector{Float64}, TTjq::SpectralVector{Float64}, TTiq::SpectralVector{Float64}, TTjp::SpectralVector{Float64},
+                      r_ip::SpectralVector{Float64}, r_jq::SpectralVector{Float64}, r_iq::SpectralVector{Float64}, r_jp::SpectralVector{Float64},
                       W1, W2, W3, W4, W5, W6, W7, W8) =
             $(cov_call!)(0, 𝐂, (TTip, TTjq, TTiq, TTjp), (r_ip, r_jq, r_iq, r_jp), (W1, W2, W3, W4, W5, W6, W7, W8))
-        loop_covEEEE!(𝐂::SpectralArray{Float64,2}, EEip, EEjq, EEiq, EEjp, r_ip, r_jq, r_iq, r_jp,
+        loop_covEEEE!(𝐂::SpectralArray{Float64,2}, EEip::SpectralVector{Float64}, EEjq::SpectralVector{Float64}, EEiq::SpectralVector{Float64}, EEjp::SpectralVector{Float64},
+                      r_ip::SpectralVector{Float64}, r_jq::SpectralVector{Float64}, r_iq::SpectralVector{Float64}, r_jp::SpectralVector{Float64},
                       W1, W2, W3, W4, W5, W6, W7, W8) =
             $(cov_call!)(1, 𝐂, (EEip, EEjq, EEiq, EEjp), (r_ip, r_jq, r_iq, r_jp), (W1, W2, W3, W4, W5, W6, W7, W8))
-        loop_covTTTE!(𝐂::SpectralArray{Float64,2}, TTip, TTjp, TEiq, TEjq, r_ip, r_jp, W1, W2, W3, W4) =
+        loop_covTTTE!(𝐂::SpectralArray{Float64,2}, TTip::SpectralVector{Float64}, TTjp::SpectralVector{Float64}, TEiq::SpectralVector{Float64}, TEjq::SpectralVector{Float64},
+                      r_ip::SpectralVector{Float64}, r_jp::SpectralVector{Float64}, W1, W2, W3, W4) =
             $(cov_call!)(2, 𝐂, (TTip, TTjp, TEiq, TEjq), (r_ip, r_jp), (W1, W2, W3, W4))
-        loop_covTETE!(𝐂::SpectralArray{Float64,2}, TTip, EEjq, TEiq, TEjp, r_TT_ip, r_PP_jq, W1, W2, W3, W4, W5) =
+        loop_covTETE!(𝐂::SpectralArray{Float64,2}, TTip::SpectralVector{Float64}, EEjq::SpectralVector{Float64}, TEiq::SpectralVector{Float64}, TEjp::SpectralVector{Float64},
+                      r_TT_ip::SpectralVector{Float64}, r_PP_jq::SpectralVector{Float64}, W1, W2, W3, W4, W5) =
             $(cov_call!)(3, 𝐂, (TTip, EEjq, TEiq, TEjp), (r_TT_ip, r_PP_jq), (W1, W2, W3, W4, W5))
-        loop_covTEEE_planck!(𝐂::SpectralArray{Float64,2}, EEjq, EEjp, TEip, TEiq, r_EE_jq, r_EE_jp, W1, W2, W3, W4) =
+        loop_covTEEE_planck!(𝐂::SpectralArray{Float64,2}, EEjq::SpectralVector{Float64}, EEjp::SpectralVector{Float64}, TEip::SpectralVector{Float64}, TEiq::SpectralVector{Float64},
+                             r_EE_jq::SpectralVector{Float64}, r_EE_jp::SpectralVector{Float64}, W1, W2, W3, W4) =
             $(cov_call!)(4, 𝐂, (EEjq, EEjp, TEip, TEiq), (r_EE_jq, r_EE_jp), (W1, W2, W3, W4))
-        loop_covTEEE!(𝐂::SpectralArray{Float64,2}, EEjq, EEjp, TEip, TEiq, r_EE_jq, r_EE_jp, W1, W2, W3, W4) =
+        loop_covTEEE!(𝐂::SpectralArray{Float64,2}, EEjq::SpectralVector{Float64}, EEjp::SpectralVector{Float64}, TEip::SpectralVector{Float64}, TEiq::SpectralVector{Float64},
+                      r_EE_jq::SpectralVector{Float64}, r_EE_jp::SpectralVector{Float64}, W1, W2, W3, W4) =
             $(cov_call!)(5, 𝐂, (EEjq, EEjp, TEip, TEiq), (r_EE_jq, r_EE_jp), (W1, W2, W3, W4))
-        loop_covTTEE!(𝐂::SpectralArray{Float64,2}, TEip, TEiq, TEjq, TEjp, W1, W2) =
+        loop_covTTEE!(𝐂::SpectralArray{Float64,2}, TEip::SpectralVector{Float64}, TEiq::SpectralVector{Float64}, TEjq::SpectralVector{Float64}, TEjp::SpectralVector{Float64}, W1, W2) =
             $(cov_call!)(6, 𝐂, (TEip, TEiq, TEjq, TEjp), (), (W1, W2))
 
         quickpolΞ!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂, ω₁::Alm, ω₂::Alm,

@@ -35,14 +35,28 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_native = False
+
+
+def use_native_build() -> str:
+    """Timed CPU arm of bench.py only: (re)build the oracle with -O3 -march=native ON THIS MACHINE
+    (`make native`) and load that build instead of the portable one.  Must be called
+    before the first use of the library in the process."""
+    global _native
+    if _lib is not None and not _native:
+        raise RuntimeError("use_native_build() must come before the first oracle call")
+    subprocess.run(["make", "-C", _HERE, "native"], check=True, capture_output=True)
+    _native = True
+    return os.path.join(_HERE, "_build", "libpsoracle_native.so")
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        path = os.path.join(_HERE, "_build", "libpsoracle_native.so") if _native else _LIB_PATH
+        if not os.path.exists(path):
             build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(path)
         dp = C.POINTER(C.c_double)
         dpp = C.POINTER(dp)
         ip = C.POINTER(C.c_int)
@@ -54,6 +68,13 @@ def lib():
             f.restype = C.c_longlong
             f.argtypes = [C.c_int, C.c_int, C.c_int, dpp, C.c_int, dpp, C.c_int, dpp, C.c_int, C.c_int,
                           dp, C.c_long, C.c_int, C.c_int]
+            f = getattr(L, "pso_mcm_rows" + suf)
+            f.restype = C.c_longlong
+            f.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, C.c_long, ip, C.c_int]
+            f = getattr(L, "pso_cov_rows" + suf)
+            f.restype = C.c_longlong
+            f.argtypes = [C.c_int, C.c_int, C.c_int, dpp, C.c_int, dpp, C.c_int, dpp, C.c_int, C.c_int,
+                          dp, C.c_long, ip, C.c_int]
             f = getattr(L, "pso_w3j_family" + suf)
             f.restype = C.c_int
             f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, ip, ip]
@@ -89,22 +110,33 @@ def w3j_family(l1, l2, m2, m3, ld=False):
     return nmin.value, out[:k].copy()
 
 
-def mcm(kind, lmin, lmax, V, ld=False, row0=0, rstep=1, threads=None, return_terms=False):
-    """inner_mcm00!/02!/++!/--! (src/modecoupling.jl:78-159).  kind: 0..3 or a name."""
+def _rows(rows):
+    a = np.ascontiguousarray(rows, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def mcm(kind, lmin, lmax, V, ld=False, row0=0, rstep=1, threads=None, return_terms=False, rows=None):
+    """inner_mcm00!/02!/++!/--! (src/modecoupling.jl:78-159).  kind: 0..3 or a name.
+    rows: explicit list of l1 rows to evaluate (default: lmin+row0, +rstep, ...)."""
     kind = MCM_KINDS.get(kind, kind)
     V = np.ascontiguousarray(V, dtype=np.float64)
     N = lmax - lmin + 1
     M = np.zeros((N, N), order="F")
     if threads:
         lib().pso_set_threads(int(threads))
-    f = lib().pso_mcm_ld if ld else lib().pso_mcm
-    t = f(kind, lmin, lmax, _dp(V), V.size, _dp(M), N, row0, rstep)
+    if rows is not None:
+        ra, rp = _rows(rows)
+        f = lib().pso_mcm_rows_ld if ld else lib().pso_mcm_rows
+        t = f(kind, lmin, lmax, _dp(V), V.size, _dp(M), N, rp, ra.size)
+    else:
+        f = lib().pso_mcm_ld if ld else lib().pso_mcm
+        t = f(kind, lmin, lmax, _dp(V), V.size, _dp(M), N, row0, rstep)
     if t < 0:
         raise ValueError("oracle mcm: bad arguments")
     return (M, t) if return_terms else M
 
 
-def cov(block, lmin, lmax, spectra, ratios, W, ld=False, row0=0, rstep=1, threads=None, return_terms=False):
+def cov(block, lmin, lmax, spectra, ratios, W, ld=False, row0=0, rstep=1, threads=None, return_terms=False, rows=None):
     """loop_cov*! (src/covariance.jl:92-446); positional order of the reference."""
     block = COV_BLOCKS.get(block, block)
     sa, sp = _vecs(spectra)
@@ -118,8 +150,13 @@ def cov(block, lmin, lmax, spectra, ratios, W, ld=False, row0=0, rstep=1, thread
     Cm = np.zeros((N, N), order="F")
     if threads:
         lib().pso_set_threads(int(threads))
-    f = lib().pso_cov_ld if ld else lib().pso_cov
-    t = f(block, lmin, lmax, sp, len(sa), rp, len(ra), wp, len(wa), lenW, _dp(Cm), N, row0, rstep)
+    if rows is not None:
+        rowa, rowp = _rows(rows)
+        f = lib().pso_cov_rows_ld if ld else lib().pso_cov_rows
+        t = f(block, lmin, lmax, sp, len(sa), rp, len(ra), wp, len(wa), lenW, _dp(Cm), N, rowp, rowa.size)
+    else:
+        f = lib().pso_cov_ld if ld else lib().pso_cov
+        t = f(block, lmin, lmax, sp, len(sa), rp, len(ra), wp, len(wa), lenW, _dp(Cm), N, row0, rstep)
     if t < 0:
         raise ValueError("oracle cov: bad arguments")
     return (Cm, t) if return_terms else Cm
@@ -164,3 +201,17 @@ class abs_mode:
 
 def max_threads() -> int:
     return lib().pso_max_threads()
+
+
+def set_threads(n: int) -> int:
+    """Force the OpenMP team size (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    lib().pso_set_threads(int(n))
+    return max_threads()
+
+
+def host_cores() -> int:
+    """CPUs this process may run on (what the reference's Julia threads would be started with)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1

@@ -42,24 +42,31 @@
 typedef struct {
     int j2, j3, m2, m3, m1;
     int nmin, nmax;
+    const REAL* root;   /* root[j - nmin] = sqrt[(j^2-(j2-j3)^2)((j2+j3+1)^2-j^2)(j^2-m1^2 if m1 != 0)], j = nmin..nmax+1 */
 } FN(fam_t);
 
+/* The square root every coefficient needs is evaluated ONCE per j (X(j) and Z(j+1) share it), into a
+ * per-thread scratch, before the recurrences run. */
+static void FN(fill_roots)(const FN(fam_t)* w, REAL* root)
+{
+    const REAL d = (REAL)(w->j2 - w->j3), s = (REAL)(w->j2 + w->j3 + 1), m = (REAL)w->m1;
+    for (int j = w->nmin; j <= w->nmax + 1; ++j) {
+        const REAL jj = (REAL)j;
+        REAL a2 = (jj * jj - d * d) * (s * s - jj * jj);
+        if (w->m1 != 0) a2 *= (jj * jj - m * m);
+        if (a2 < 0) a2 = 0;
+        root[j - w->nmin] = SQRT(a2);
+    }
+}
 static inline REAL FN(Xc)(const FN(fam_t)* w, int j)   /* coefficient of f(j+1) */
 {
-    REAL jp = (REAL)(j + 1);
-    REAL d = (REAL)(w->j2 - w->j3), s = (REAL)(w->j2 + w->j3 + 1);
-    REAL a2 = (jp * jp - d * d) * (s * s - jp * jp);
-    if (w->m1 == 0) return SQRT(a2);
-    return (REAL)j * SQRT(a2 * (jp * jp - (REAL)(w->m1 * w->m1)));
+    const REAL r = w->root[j + 1 - w->nmin];
+    return w->m1 == 0 ? r : (REAL)j * r;
 }
 static inline REAL FN(Zc)(const FN(fam_t)* w, int j)   /* coefficient of f(j-1) */
 {
-    REAL jj = (REAL)j;
-    REAL d = (REAL)(w->j2 - w->j3), s = (REAL)(w->j2 + w->j3 + 1);
-    REAL a2 = (jj * jj - d * d) * (s * s - jj * jj);
-    if (a2 < 0) a2 = 0;
-    if (w->m1 == 0) return SQRT(a2);
-    return (REAL)(j + 1) * SQRT(a2 * (jj * jj - (REAL)(w->m1 * w->m1)));
+    const REAL r = w->root[j - w->nmin];
+    return w->m1 == 0 ? r : (REAL)(j + 1) * r;
 }
 static inline REAL FN(Yc)(const FN(fam_t)* w, int j)   /* coefficient of f(j) */
 {
@@ -71,7 +78,7 @@ static inline REAL FN(Yc)(const FN(fam_t)* w, int j)   /* coefficient of f(j) */
 
 /* Whole family f(j) = (j j2 j3; -m2-m3 m2 m3), j = nmin..nmax, into out[0..n-1].
  * Returns n (0 if the family is empty). */
-static int FN(family)(int j2, int j3, int m2, int m3, REAL* out, int* pnmin, int* pnmax)
+static int FN(family)(int j2, int j3, int m2, int m3, REAL* out, int* pnmin, int* pnmax, REAL* scratch)
 {
     FN(fam_t) w;
     w.j2 = j2; w.j3 = j3; w.m2 = m2; w.m3 = m3; w.m1 = -m2 - m3;
@@ -83,6 +90,8 @@ static int FN(family)(int j2, int j3, int m2, int m3, REAL* out, int* pnmin, int
     int n = w.nmax - w.nmin + 1;
     if (n <= 0) return 0;
     const int nmin = w.nmin, nmax = w.nmax;
+    FN(fill_roots)(&w, scratch);
+    w.root = scratch;
 #define PSI(j) out[(j) - nmin]
 
     if (n == 1) {
@@ -196,34 +205,53 @@ static inline REAL FN(xi)(const double* W, int lenW, const REAL* w, int nmin, in
  * Only rows l1 = lmin + row0 + k*rstep are computed (rstep = 1: all rows), so a
  * deterministic sample of rows can be timed.  M is column-major, M[(l1-lmin)+(l2-lmin)*ld].
  * Returns the number of 3j terms evaluated (full families, as the reference does). */
+long long FN(mcm_rows)(int kind, int lmin, int lmax, const double* V, int nV, double* M, long ld,
+                       const int* rows, int nrows);
 long long FN(mcm)(int kind, int lmin, int lmax, const double* V, int nV, double* M, long ld,
                   int row0, int rstep)
 {
     if (kind < 0 || kind > 3 || lmin < 0 || lmax < lmin || nV < 1 || rstep < 1 || row0 < 0) return -1;
+    int n = 0;
+    for (int l1 = lmin + row0; l1 <= lmax; l1 += rstep) ++n;
+    int* rows = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+    n = 0;
+    for (int l1 = lmin + row0; l1 <= lmax; l1 += rstep) rows[n++] = l1;
+    long long t = FN(mcm_rows)(kind, lmin, lmax, V, nV, M, ld, rows, n);
+    free(rows);
+    return t;
+}
+/* Same for an explicit list of rows l1 (absolute multipoles, lmin <= l1 <= lmax, any order). */
+long long FN(mcm_rows)(int kind, int lmin, int lmax, const double* V, int nV, double* M, long ld,
+                       const int* rows, int nrows)
+{
+    if (kind < 0 || kind > 3 || lmin < 0 || lmax < lmin || nV < 1 || nrows < 0 || (nrows && !rows)) return -1;
+    for (int i = 0; i < nrows; ++i) if (rows[i] < lmin || rows[i] > lmax) return -1;
     long long terms = 0;
     int nbuf = 2 * lmax + 1;
 #pragma omp parallel reduction(+ : terms)
     {
         REAL* b0 = (REAL*)malloc(sizeof(REAL) * nbuf);
         REAL* b2 = (REAL*)malloc(sizeof(REAL) * nbuf);
+        REAL* rootbuf = (REAL*)malloc(sizeof(REAL) * (nbuf + 2));
 #pragma omp for schedule(dynamic, 1)
-        for (int l1 = lmin + row0; l1 <= lmax; l1 += rstep) {
+        for (int ir = 0; ir < nrows; ++ir) {
+            const int l1 = rows[ir];
             for (int l2 = l1; l2 <= lmax; ++l2) {
                 int nmin, nmax, n;
                 REAL xi;
                 if (kind == 0) {
-                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
+                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) b0[i] = b0[i] * b0[i];
                     xi = FN(xi)(V, nV, b0, nmin, nmax, l1, l2, 0);
                     terms += n;
                 } else if (kind == 1) {
-                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
-                    FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax);
+                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf);
+                    FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) b0[i] *= b2[i];
                     xi = FN(xi)(V, nV, b0, nmin, nmax, l1, l2, 1);
                     terms += 2 * n;
                 } else {
-                    n = FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax);
+                    n = FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) b2[i] = b2[i] * b2[i];
                     xi = FN(xi)(V, nV, b2, nmin, nmax, l1, l2, kind == 2 ? 1 : 2);
                     terms += n;
@@ -232,7 +260,7 @@ long long FN(mcm)(int kind, int lmin, int lmax, const double* V, int nV, double*
                 M[(long)(l2 - lmin) + (long)(l1 - lmin) * ld] = (double)((REAL)(2 * l1 + 1) * xi);
             }
         }
-        free(b0); free(b2);
+        free(b0); free(b2); free(rootbuf);
     }
     return terms;
 }
@@ -241,23 +269,43 @@ long long FN(mcm)(int kind, int lmin, int lmax, const double* V, int nV, double*
  * (src/covariance.jl:92-122,153-183,208-235,261-302,376-402,337-372,422-446).
  * sp / rt / W follow the positional order of the reference signatures; every vector
  * is 0-based in l.  Returns the number of 3j terms evaluated, -1 on bad arguments. */
+long long FN(cov_rows)(int block, int lmin, int lmax, const double* const* sp, int nsp,
+                       const double* const* rt, int nrt, const double* const* W, int nW, int lenW,
+                       double* C, long ld, const int* rows, int nrows);
 long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int nsp,
                   const double* const* rt, int nrt, const double* const* W, int nW, int lenW,
                   double* C, long ld, int row0, int rstep)
 {
+    if (lmin < 0 || lmax < lmin || rstep < 1 || row0 < 0) return -1;
+    int n = 0;
+    for (int l1 = lmin + row0; l1 <= lmax; l1 += rstep) ++n;
+    int* rows = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+    n = 0;
+    for (int l1 = lmin + row0; l1 <= lmax; l1 += rstep) rows[n++] = l1;
+    long long t = FN(cov_rows)(block, lmin, lmax, sp, nsp, rt, nrt, W, nW, lenW, C, ld, rows, n);
+    free(rows);
+    return t;
+}
+long long FN(cov_rows)(int block, int lmin, int lmax, const double* const* sp, int nsp,
+                       const double* const* rt, int nrt, const double* const* W, int nW, int lenW,
+                       double* C, long ld, const int* rows, int nrows)
+{
     static const int need_sp[7] = {4, 4, 4, 4, 4, 4, 4};
     static const int need_rt[7] = {4, 4, 2, 2, 2, 2, 0};
     static const int need_W[7] = {8, 8, 4, 5, 4, 4, 2};
-    if (block < 0 || block > 6 || lmin < 0 || lmax < lmin || lenW < 1 || rstep < 1 || row0 < 0) return -1;
+    if (block < 0 || block > 6 || lmin < 0 || lmax < lmin || lenW < 1 || nrows < 0 || (nrows && !rows)) return -1;
     if (nsp != need_sp[block] || nrt != need_rt[block] || nW != need_W[block]) return -1;
+    for (int i = 0; i < nrows; ++i) if (rows[i] < lmin || rows[i] > lmax) return -1;
     long long terms = 0;
     int nbuf = 2 * lmax + 1;
 #pragma omp parallel reduction(+ : terms)
     {
         REAL* b0 = (REAL*)malloc(sizeof(REAL) * nbuf);
         REAL* b2 = (REAL*)malloc(sizeof(REAL) * nbuf);
+        REAL* rootbuf = (REAL*)malloc(sizeof(REAL) * (nbuf + 2));
 #pragma omp for schedule(dynamic, 1)
-        for (int l1 = lmin + row0; l1 <= lmax; l1 += rstep) {
+        for (int ir = 0; ir < nrows; ++ir) {
+            const int l1 = rows[ir];
             for (int l2 = l1; l2 <= lmax; ++l2) {
                 int nmin, nmax, n;
                 REAL c = 0;
@@ -267,8 +315,8 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                 if (block == 0 || block == 1) {
                     /* spectra: ip, jq, iq, jp ; ratios: ip, jq, iq, jp */
                     int par = block == 0 ? 0 : 1;
-                    n = block == 0 ? FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax)
-                                   : FN(family)(l1, l2, -2, 2, b0, &nmin, &nmax);
+                    n = block == 0 ? FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf)
+                                   : FN(family)(l1, l2, -2, 2, b0, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) b0[i] = b0[i] * b0[i];
                     terms += n;
                     REAL x[8];
@@ -283,7 +331,7 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                         AT(x[7] * R(2, l1) * R(3, l1) * R(2, l2) * R(3, l2));
                 } else if (block == 2) {
                     /* TTTE: spectra TTip, TTjp, TEiq, TEjq ; ratios ip, jp */
-                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
+                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) b0[i] = b0[i] * b0[i];
                     terms += n;
                     REAL x[4];
@@ -294,8 +342,8 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                          AT((S(2, l1) + S(2, l2)) * x[3] * R(1, l1) * R(1, l2))) / 2;
                 } else if (block == 3) {
                     /* TETE: spectra TTip, EEjq, TEiq, TEjp ; ratios TT_ip, PP_jq */
-                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
-                    FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax);
+                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf);
+                    FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) { b2[i] *= b0[i]; b0[i] *= b0[i]; }
                     terms += 2 * n;
                     REAL x1 = FN(xi)(W[0], lenW, b2, nmin, nmax, l1, l2, 1);
@@ -311,12 +359,12 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                 } else if (block == 4 || block == 5) {
                     /* TEEE: spectra EEjq, EEjp, TEip, TEiq ; ratios EE_jq, EE_jp */
                     if (block == 4) {
-                        n = FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax);
+                        n = FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax, rootbuf);
                         for (int i = 0; i < n; ++i) b2[i] = b2[i] * b2[i];
                         terms += n;
                     } else {
-                        n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
-                        FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax);
+                        n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf);
+                        FN(family)(l1, l2, -2, 2, b2, &nmin, &nmax, rootbuf);
                         for (int i = 0; i < n; ++i) b2[i] *= b0[i];
                         terms += 2 * n;
                     }
@@ -328,7 +376,7 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                          AT((S(3, l1) + S(3, l2)) * x[3] * R(1, l1) * R(1, l2))) / 2;
                 } else {
                     /* TTEE: spectra TEip, TEiq, TEjq, TEjp */
-                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax);
+                    n = FN(family)(l1, l2, 0, 0, b0, &nmin, &nmax, rootbuf);
                     for (int i = 0; i < n; ++i) b0[i] = b0[i] * b0[i];
                     terms += n;
                     REAL x1 = FN(xi)(W[0], lenW, b0, nmin, nmax, l1, l2, 0);
@@ -343,7 +391,7 @@ long long FN(cov)(int block, int lmin, int lmax, const double* const* sp, int ns
                 C[(long)(l2 - lmin) + (long)(l1 - lmin) * ld] = (double)c;
             }
         }
-        free(b0); free(b2);
+        free(b0); free(b2); free(rootbuf);
     }
     return terms;
 }
@@ -357,7 +405,9 @@ int FN(w3j_family)(int j2, int j3, int m2, int m3, double* out, int nout, int* n
     if (n <= 0) { if (nmin) *nmin = lo; if (nmax) *nmax = j2 + j3; return 0; }
     if (nout < n) return -1;
     REAL* b = (REAL*)malloc(sizeof(REAL) * n);
-    FN(family)(j2, j3, m2, m3, b, nmin, nmax);
+    REAL* rootbuf = (REAL*)malloc(sizeof(REAL) * (n + 2));
+    FN(family)(j2, j3, m2, m3, b, nmin, nmax, rootbuf);
+    free(rootbuf);
     for (int i = 0; i < n; ++i) out[i] = (double)b[i];
     free(b);
     return n;
@@ -392,6 +442,7 @@ long long FN(quickpol_xi)(int nu1, int nu2, int s1, int s2, int lmax, const doub
     {
         REAL* b1 = (REAL*)malloc(sizeof(REAL) * (nbuf > 0 ? nbuf : 1));
         REAL* b2 = (REAL*)malloc(sizeof(REAL) * (nbuf > 0 ? nbuf : 1));
+        REAL* rootbuf = (REAL*)malloc(sizeof(REAL) * (nbuf + 2));
 #pragma omp for schedule(dynamic, 1)
         for (int lpp = 2; lpp <= lmax; ++lpp) {
             int lo = lpp - band_lo, hi = lpp + band_hi;
@@ -401,8 +452,8 @@ long long FN(quickpol_xi)(int nu1, int nu2, int s1, int s2, int lmax, const doub
                 REAL acc = 0;
                 if (abs(s1) <= l && abs(s2) <= l && abs(nu1) <= lpp && abs(nu2) <= lpp) {
                     int min1, max1, min2, max2;
-                    int n1 = FN(family)(l, lpp, -s1, -nu1, b1, &min1, &max1);
-                    int n2 = FN(family)(l, lpp, -s2, -nu2, b2, &min2, &max2);
+                    int n1 = FN(family)(l, lpp, -s1, -nu1, b1, &min1, &max1, rootbuf);
+                    int n2 = FN(family)(l, lpp, -s2, -nu2, b2, &min2, &max2, rootbuf);
                     terms += n1 + n2;
                     if (n1 > 0 && n2 > 0) {
                         int a = min1 > min2 ? min1 : min2;
@@ -417,7 +468,7 @@ long long FN(quickpol_xi)(int nu1, int nu2, int s1, int s2, int lmax, const doub
                 Xb[(long)(band_hi + lpp - l) + (long)l * ldb] = (double)(pso_abs_mode ? acc : sgn * acc);
             }
         }
-        free(b1); free(b2);
+        free(b1); free(b2); free(rootbuf);
     }
     return terms;
 }

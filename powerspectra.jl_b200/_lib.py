@@ -36,6 +36,7 @@ PROTOTYPES = {
     "psb200_band_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "psb200_terms": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "psb200_dfma_peak": (C.c_double, [C.c_int]),
+    "psb200_job_stats": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_longlong)]),
     "psb200_quickpol_xi": (C.c_int, [C.c_int] * 5 + [DP, C.c_int, C.c_int, C.c_int, DP, C.c_long, C.c_int]),
     "psb200_quickpol_xi_dev": (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long,
                                                          C.c_int, C.c_int, C.c_void_p]),

@@ -7,6 +7,7 @@
 #include "psb200_common.cuh"
 #include "psb200_pair_v1.cuh"
 #include "psb200_pair_v2.cuh"
+#include "psb200_lowrows.cuh"
 #include "psb200_quickpol.cuh"
 
 #include <algorithm>
@@ -182,7 +183,7 @@ struct DevTables {
 DevTables g_tables[16];
 std::mutex g_tab_mutex;
 
-int ensure_tables(int dev, int lmax, DevTables** out)
+int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
 {
     std::lock_guard<std::mutex> lk(g_tab_mutex);
     DevTables& t = g_tables[dev];
@@ -209,50 +210,68 @@ int ensure_tables(int dev, int lmax, DevTables** out)
     CUDA_TRY(cudaMalloc(&t.IS, nS * sizeof(double)));
     CUDA_TRY(cudaMalloc(&t.INV, nS * sizeof(double)));
     CUDA_TRY(cudaMalloc(&t.gam, ng * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(t.S, S.data(), nS * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(t.IS, IS.data(), nS * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(t.INV, INV.data(), nS * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(t.gam, G.data(), ng * sizeof(double), cudaMemcpyHostToDevice));
+    // Uploads go on the LAUNCHING stream (the kernels that read the tables run on non-blocking streams, which
+    // do not order against the legacy default stream a plain cudaMemcpy uses), and the stream is drained
+    // before the pageable host vectors die.
+    CUDA_TRY(cudaMemcpyAsync(t.S, S.data(), nS * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t.IS, IS.data(), nS * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t.INV, INV.data(), nS * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t.gam, G.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     t.lmax = want; t.nS = nS;
     *out = &t;
     return OK;
 }
 
-// Block list of one launch: (l1, d_lo) tiles of the band's upper triangle, heaviest first
-// (longest-processing-time order keeps the 148 SMs balanced to the last wave).
+// Block list of one launch: (first l1, d_lo) tiles of the band's upper triangle, heaviest first
+// (longest-processing-time order keeps the 148 SMs balanced to the last wave).  A tile is nr consecutive rows
+// x (32/nr) r pairs of each: consecutive d (ds = 1) or d of one parity (ds = 2, (0,0,0)-recurrence jobs).
 struct BlockList { int2* d = nullptr; int n = 0; unsigned long stamp = 0; };
-typedef std::tuple<int, int, int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi, d stride, pairs per thread
+typedef std::tuple<int, int, int, int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi, d stride, pairs per thread, rows per warp
 std::map<BlockKey, BlockList> g_blocks;
 unsigned long g_block_stamp = 0;
 
-int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, BlockList* out)
+// Tiling of rows [row_lo, row_hi) as the tuned kernel runs it.  fn(l1_first, d_lo, steps) per warp.
+template <class F>
+void for_each_tile(int lmax, int lenW, int row_lo, int row_hi, int ds, int r, int nr, F fn)
 {
-    // A warp takes 32 r pairs: consecutive d (ds = 1) or d of one parity (ds = 2, (0,0,0)-only jobs).
-    std::lock_guard<std::mutex> lk(g_tab_mutex);
-    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi, ds, r);
-    const int pb = psb::v2_pb(r), gspan = psb::v2_gspan(r);
-    auto it = g_blocks.find(key);
-    if (it != g_blocks.end()) { it->second.stamp = ++g_block_stamp; *out = it->second; return OK; }
-    std::vector<std::pair<long, int2>> v;
-    for (int l1 = A.row_lo; l1 < A.row_hi; ++l1) {
-        const int nd = A.lmax - l1 + 1;
-        for (int base = 0; base < nd; base += ds * pb) {
+    const int span = (32 / nr) * r;
+    for (int l1 = row_lo; l1 < row_hi; l1 += nr) {
+        const int l1_last = std::min(l1 + nr, row_hi) - 1;
+        const int nd = lmax - l1 + 1;
+        for (int base = 0; base < nd; base += ds * span) {
             for (int par = 0; par < ds; ++par) {
                 const int d_lo = base + par;
                 if (d_lo >= nd) continue;
-                const long last = A.lenW - 1 - d_lo;
-                const long steps = last < 0 ? 0 : std::min<long>(gspan - 1 + (2 * l1) / ds, last / ds) + 1;
-                v.push_back({steps, make_int2(l1, d_lo)});
+                const long last = (long)lenW - 1 - d_lo;
+                const long steps = last < 0 ? 0 : std::min<long>(span - 1 + (2 * l1_last) / ds, last / ds) + 1;
+                fn(l1, d_lo, steps);
             }
         }
     }
+}
+
+int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, int nr, cudaStream_t st, BlockList* out)
+{
+    std::lock_guard<std::mutex> lk(g_tab_mutex);
+    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi, ds, r, nr);
+    auto it = g_blocks.find(key);
+    if (it != g_blocks.end()) { it->second.stamp = ++g_block_stamp; *out = it->second; return OK; }
+    std::vector<std::pair<long, int2>> v;
+    for_each_tile(A.lmax, A.lenW, A.row_lo, A.row_hi, ds, r, nr,
+                  [&](int l1, int d_lo, long steps) { v.push_back({steps, make_int2(l1, d_lo)}); });
     std::stable_sort(v.begin(), v.end(), [](const std::pair<long, int2>& a, const std::pair<long, int2>& b) { return a.first > b.first; });
     std::vector<int2> h(v.size());
     for (size_t i = 0; i < v.size(); ++i) h[i] = v[i].second;
-    if (g_blocks.size() >= 64) {                 // drop the least recently used list
-        auto old = g_blocks.begin();
-        for (auto jt = g_blocks.begin(); jt != g_blocks.end(); ++jt) if (jt->second.stamp < old->second.stamp) old = jt;
-        CUDA_TRY(cudaDeviceSynchronize());
+    // LRU per device (a list is only ever evicted by a call on the device that owns it, after that device has
+    // drained: lists of other devices may be in use by their own worker threads)
+    size_t mine = 0;
+    for (auto& kv : g_blocks) if (std::get<0>(kv.first) == dev) ++mine;
+    if (mine >= 96) {
+        auto old = g_blocks.end();
+        for (auto jt = g_blocks.begin(); jt != g_blocks.end(); ++jt)
+            if (std::get<0>(jt->first) == dev && (old == g_blocks.end() || jt->second.stamp < old->second.stamp)) old = jt;
+        CUDA_TRY(cudaDeviceSynchronize());       // current device == dev (launch_job asked cudaGetDevice)
         cudaFree(old->second.d);
         g_blocks.erase(old);
     }
@@ -261,7 +280,9 @@ int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, BlockList* out
     bl.stamp = ++g_block_stamp;
     if (bl.n) {
         CUDA_TRY(cudaMalloc(&bl.d, h.size() * sizeof(int2)));
-        CUDA_TRY(cudaMemcpy(bl.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        // on the launching stream, drained before the pageable host vector dies (see ensure_tables)
+        CUDA_TRY(cudaMemcpyAsync(bl.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
     }
     g_blocks[key] = bl;
     *out = bl;
@@ -295,8 +316,20 @@ int wp_reserve(int dev, cudaStream_t st, size_t n, double** out)
 }
 
 template <int JOB>
-int launch_job(const psb::PairArgs& A, cudaStream_t st)
+int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
 {
+    if (A_in.row_hi - A_in.row_lo <= 0) return OK;
+    psb::PairArgs A = A_in;
+    if constexpr (psb::job_has_spin2(JOB)) {
+        // rows l1 < 2 of the spin-2 jobs (true symbol 0; what the reference's family routine yields): psb200_lowrows.cuh
+        if (A.row_lo < 2) {
+            const int nlow = std::min(A.row_hi, 2) - A.row_lo;
+            dim3 grid((A.lmax - A.row_lo + 1 + 127) / 128, nlow);
+            psb::low_rows_kernel<JOB><<<grid, 128, 0, st>>>(A);
+            CUDA_TRY(cudaGetLastError());
+            A.row_lo = std::min(A.row_hi, 2);
+        }
+    }
     const int rows = A.row_hi - A.row_lo;
     if (rows <= 0) return OK;
     if (kernel_version() == 1) {
@@ -312,9 +345,9 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     Trace tr;
     tr.mark("  (inputs uploaded)", dev, st);
     DevTables* t = nullptr;
-    if (int rc = ensure_tables(dev, A.lmax, &t)) return rc;
+    if (int rc = ensure_tables(dev, A.lmax, st, &t)) return rc;
     BlockList bl;
-    if (int rc = ensure_blocks(dev, A, psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), &bl)) return rc;
+    if (int rc = ensure_blocks(dev, A, psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), psb::v2_nr(JOB), st, &bl)) return rc;
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
     constexpr int nqp = psb::v2_nqp(JOB);
     const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_PB_MAX);
@@ -332,6 +365,33 @@ int launch_job(const psb::PairArgs& A, cudaStream_t st)
     if (e != 0) return fail(ERR_CUDA, "pair kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     tr.mark("  pair kernel", dev, st);
     return OK;
+}
+
+// tiling parameters of a job as the tuned kernel runs it: l3 stride, pairs per thread, rows per warp
+template <int JOB>
+void job_tiling(int* ds, int* r, int* nr)
+{
+    *ds = psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1; *r = psb::v2_r(JOB); *nr = psb::v2_nr(JOB);
+}
+int job_tiling_any(int job, int* ds, int* r, int* nr)
+{
+    using namespace psb;
+    switch (job) {
+        case JOB_M00: job_tiling<JOB_M00>(ds, r, nr); return OK;
+        case JOB_M02: job_tiling<JOB_M02>(ds, r, nr); return OK;
+        case JOB_MPP: job_tiling<JOB_MPP>(ds, r, nr); return OK;
+        case JOB_MMM: job_tiling<JOB_MMM>(ds, r, nr); return OK;
+        case JOB_MPPMMM: job_tiling<JOB_MPPMMM>(ds, r, nr); return OK;
+        case JOB_TTTT: job_tiling<JOB_TTTT>(ds, r, nr); return OK;
+        case JOB_EEEE: job_tiling<JOB_EEEE>(ds, r, nr); return OK;
+        case JOB_TTTE: job_tiling<JOB_TTTE>(ds, r, nr); return OK;
+        case JOB_TETE: job_tiling<JOB_TETE>(ds, r, nr); return OK;
+        case JOB_TEEEP: job_tiling<JOB_TEEEP>(ds, r, nr); return OK;
+        case JOB_TEEE: job_tiling<JOB_TEEE>(ds, r, nr); return OK;
+        case JOB_TTEE: job_tiling<JOB_TTEE>(ds, r, nr); return OK;
+        case JOB_MASTER: job_tiling<JOB_MASTER>(ds, r, nr); return OK;
+    }
+    return fail(ERR_ARG, "unknown job %d", job);
 }
 
 int launch_any(int job, const psb::PairArgs& A, cudaStream_t st)
@@ -474,25 +534,27 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
     return launch_any(hj.job, A, s.stream);
 }
 
-// Cost of row l1 as the tuned kernel executes it.  Most jobs run the two-step f00^2 recurrence: one
-// warp-block per 192 pairs of one parity of d, stepping l3 by 2 from its first d to
-// min(d + 2 l1, lenW-1), plus the 191-step start skew of the warp and a fixed per-block overhead
-// (start values, first table staging, epilogue) worth about 70 steps (least squares over the per-rank pair-kernel
-// times of the 2-, 4- and 8-GPU runs in profiles/bench_r01_n{2,4,8}.json: only SKEW + OVH ~ 200 is constrained,
-// RMS residual 0.12 ms per rank against 0.41 ms for the previous 130 + 120).
+// Cost of row l1 as the tuned kernel executes it.  Most jobs run the two-step f00^2 recurrence: one warp per
+// NR rows x SPAN pairs of one parity of d (SPAN = (32/NR) R), stepping l3 by 2 from its first d to
+// min(d + 2 l1, lenW-1), plus the start skew of the warp and a fixed per-block overhead (start values, first
+// table staging, epilogue).  Skew and overhead weights come from a least-squares fit over the per-rank
+// pair-kernel times of the round-1 2-, 4- and 8-GPU runs (NR = 1, SPAN = 192: only SKEW + OVH ~ 200 steps was
+// constrained, RMS residual 0.12 ms per rank); the skew term scales with SPAN, the overhead does not.
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
-    constexpr long PBN = 192, SKEW = 130, OVH = 70;              // nominal warp tile; skew and overhead weights fitted to per-rank kernel times
+    constexpr long NRH = psb::v2_nr(psb::JOB_TTTT);
+    constexpr long SPAN = psb::v2_span(psb::JOB_TTTT);           // the covariance jobs dominate a step
+    constexpr long SKEW = (130 * SPAN) / 192, OVH = 70;
     long double c = 0;
-    for (long base = 0; base <= D; base += 2 * PBN) {
+    for (long base = 0; base <= D; base += 2 * SPAN) {
         for (long par = 0; par < 2; ++par) {
             const long d_lo = base + par;
             if (d_lo > D) continue;
             const long last = (long)lenW - 1 - d_lo;
             const long steps = last < 0 ? 0 : std::min<long>(SKEW + l1, last / 2) + 1;
-            c += (long double)(steps + OVH);
+            c += (long double)(steps + OVH) / NRH;               // a warp is shared by NR rows
         }
     }
     return c;
@@ -598,8 +660,8 @@ int run_host_job(const HostJob& hj, int ngpus)
 {
     int cur = 0;
     cudaGetDevice(&cur);
-    if (ngpus == 1) {                                   // same scheme, one band, calling thread
-        const int rc = run_band_on_device(hj, 0, hj.lmin, hj.lmax + 1, nullptr);
+    if (ngpus == 1) {                                   // same scheme, one band, calling thread, the CALLER's current device
+        const int rc = run_band_on_device(hj, cur, hj.lmin, hj.lmax + 1, nullptr);
         cudaSetDevice(cur);
         return rc;
     }
@@ -628,7 +690,8 @@ int run_host_job(const HostJob& hj, int ngpus)
 // ---------------------------------------------------------------------------------------
 int check_quickpol(int lmax, int lenW, int band_lo, int band_hi, long ldb, int col_lo, int col_hi)
 {
-    if (lmax < 0 || lmax > 32767) return fail(ERR_ARG, "need 0 <= lmax <= 32767 (got %d)", lmax);
+    // 12287: the bound up to which the rescaling cadence of the sweep was analysed (psb200_quickpol.cuh)
+    if (lmax < 0 || lmax > 12287) return fail(ERR_ARG, "need 0 <= lmax <= 12287 (got %d)", lmax);
     if (lenW < 1) return fail(ERR_ARG, "empty scan spectrum W");
     // BandedMatrices accepts bandwidths beyond the matrix size (the extra storage rows are padding): so do we
     if (band_lo < 0 || band_hi < 0 || band_lo > (1 << 20) || band_hi > (1 << 20))
@@ -749,6 +812,35 @@ long long psb200_terms(int families, int lmax, int row_lo, int row_hi)
     long long t = 0;
     for (int l = row_lo; l < row_hi; ++l) t += (long long)(2 * l + 1) * (lmax - l + 1);
     return t * families;
+}
+
+int psb200_job_stats(int api, int code, int lmax, int lenW, int row_lo, int row_hi, long long* out)
+{
+    if (!out || lmax < 0 || lenW < 1 || row_lo < 0 || row_hi > lmax + 1 || row_lo > row_hi)
+        return fail(ERR_ARG, "job_stats: bad arguments");
+    int job = -1;
+    if (api == 0 && code >= 0 && code <= 4) job = kMcmJob[code];
+    else if (api == 1 && code >= 0 && code <= 6) job = kCovJob[code];
+    else if (api == 2) job = psb::JOB_MASTER;
+    else return fail(ERR_ARG, "job_stats: unknown api/code %d/%d", api, code);
+    int ds = 1, r = 1, nr = 1;
+    if (int rc = job_tiling_any(job, &ds, &r, &nr)) return rc;
+    int lo = row_lo;
+    switch (job) {           // spin-2 jobs: rows l1 < 2 belong to low_rows_kernel
+        case psb::JOB_M00: case psb::JOB_TTTT: case psb::JOB_TTTE: case psb::JOB_TTEE: break;
+        default: lo = std::min(row_hi, std::max(row_lo, 2));
+    }
+    long long exec = 0, warps = 0;
+    for_each_tile(lmax, lenW, lo, row_hi, ds, r, nr, [&](int, int, long steps) { exec += steps * 32LL * r; ++warps; });
+    long long live = 0;
+    for (int l1 = lo; l1 < row_hi; ++l1) {
+        for (int d = 0; d <= lmax - l1; ++d) {
+            const long jend = std::min<long>((long)d + 2L * l1, (long)lenW - 1);
+            if (jend >= d) live += (jend - d) / ds + 1;
+        }
+    }
+    out[0] = exec; out[1] = live; out[2] = warps; out[3] = r; out[4] = nr; out[5] = ds;
+    return OK;
 }
 
 int psb200_mcm_dev(int kind, int lmin, int lmax, const double* dV, int nV, double* dX, long ldX,

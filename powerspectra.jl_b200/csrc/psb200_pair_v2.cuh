@@ -1,15 +1,23 @@
 // psb200_pair_v2.cuh -- tuned pair kernel for sm_100a (FP64-pipe bound by design).
 //
 // Work decomposition
-//   block  = ONE WARP = one l1 row x 32 R consecutive d = l2-l1;  thread = R consecutive d (R = 8 for the
-//   one- and two-accumulator jobs, 6 for the covariance jobs).
-//   (Warp-sized blocks: table staging needs only __syncwarp, so the ~12 resident warps of an SM
+//   block  = ONE WARP = NR consecutive l1 rows x (32/NR) R consecutive d = l2-l1 of each row;
+//   thread = R consecutive d of ONE row (R = 8 for the one- and two-accumulator jobs, 6 for the covariance
+//   jobs); lanes [g LPR, (g+1) LPR) of the warp, LPR = 32/NR, hold row l1 + g over the SAME d window.
+//   (Warp-sized blocks: table staging needs only __syncwarp, so the ~8-12 resident warps of an SM
 //   drift apart and hide each other's staging latency; ncu showed 9-12% barrier stalls with
 //   4-warp blocks.)
 //   All pairs of a warp advance l3 = j in LOCKSTEP (j = tau + d_w, d_w = first d of the warp), so
 //   every window spectrum read W'_q[j] is a warp-uniform shared-memory broadcast and feeds all
 //   pairs with no per-pair loads.  A pair becomes live when j reaches its own jmin = d
 //   (injection of the closed-form start value), and dies by itself at jmax (tables are 0 there).
+//   Why several rows per warp: a lockstep warp spends SPAN-1 + 2 l1/DS + 1 steps on families that are
+//   only 2 l1/DS + 1 steps long (SPAN = pairs per row per warp: the last pair starts SPAN-1 steps after the
+//   first), and the last tile of every row is partly empty.  With one row per warp (SPAN = 32 R) 13.6% of
+//   the executed pair-steps of a covariance job at lmax 6143 were dead; rows l1 and l1+1 share the d window,
+//   the parity class and (to two steps) the family length, so putting NR of them side by side divides SPAN by NR
+//   at the same register rotation depth R: dead pair-steps 13.6% -> 7.2% (NR = 2) -> 3.8% (NR = 4); the price is
+//   one set of per-row tables per row (staging work x (NR TC + 32 R)/(TC + 32 R)).
 //
 // Recurrence (reduced Schulten-Gordon, m1 = 0), t = j-d, m = j+d, L = 2 l1+1:
 //   a(j)^2 = (j^2-d^2)(s^2-j^2) = [t (L-t)] * [m (m+L)]   =>   a(j) = U[t] * V[m]
@@ -30,14 +38,15 @@
 //   f00(d)^2 = g(d) g(l1) / (g(l2) (2 l2+1)),  g(n) = binom(2n,n) / 4^n,
 //   f22(d)^2 = f00(d)^2 * (l2+1)(l2+2)(l1-1) l1 / ((l2-1) l2 (l1+1)(l1+2)),   same sign,
 // so terms with l3 > lenW-1 (25% of every family at nV = lmax+1) are never evaluated.
+// Rows l1 < 2 of the spin-2 jobs (true symbol 0, closed forms 0/0) are not this kernel's: psb200_lowrows.cuh.
 #pragma once
 #include "psb200_common.cuh"
 
 namespace psb {
 
 // Pairs per thread, by job weight.  More pairs per thread = fewer shared-memory bytes per pair-step (each
-// new table entry serves R pairs) but more registers and a longer start skew (32 R - 1 steps).
-// MEASURED (B200, lmax 6143, ms per bench step): R = 4/4/4 154.4, 6/6/4 151.2, 6/6/6 149.5, 8/6/4 150.8,
+// new table entry serves R pairs) but more registers and a longer start skew.
+// MEASURED (B200, lmax 6143, ms per bench step, NR = 1): R = 4/4/4 154.4, 6/6/4 151.2, 6/6/6 149.5, 8/6/4 150.8,
 // 8/6/6 148.5 -- the shared-memory return path, not occupancy, is the co-limiter next to the FP64 pipe.
 #ifndef PSB200_R_LIGHT
 #define PSB200_R_LIGHT 8        // <= 2 accumulators per pair
@@ -53,30 +62,37 @@ __host__ __device__ constexpr int v2_r(int job)
     return job_nacc(job) <= 2 ? PSB200_R_LIGHT : (job_nacc(job) <= 5 ? PSB200_R_MID : PSB200_R_HEAVY);
 }
 constexpr int V2_R_MAX = 8;
-constexpr int V2_NW = 1;                        // warps per block: staging is warp-private, no block barriers
-#ifndef PSB200_LG
-#define PSB200_LG 32
+// Rows per warp (1, 2 or 4), by job weight like R.
+#ifndef PSB200_NR
+#define PSB200_NR 2
 #endif
-// A warp's 128 pairs can be split into G = 32/LG lockstep groups of LG lanes: group q holds the pairs
-// q*GSPAN .. (q+1)*GSPAN-1 and runs GSPAN steps "ahead" in l3 (its j is tau + d_lo + q*GSPAN), so the
-// start skew a warp pays is GSPAN-1 steps instead of 127 while all groups still share the U table
-// and read consecutive windows of the V table.  W' rows are then one address per group instead of
-// a warp-uniform broadcast.  MEASURED (B200, lmax 6143, ms/step): LG=32 153.1, LG=16 156.9, LG=8 163.1 --
-// the extra shared-memory traffic costs more than the skew saves, so the default is one group.
-constexpr int V2_LG = PSB200_LG;                // lanes per lockstep group
-constexpr int V2_G = 32 / V2_LG;                // groups per warp
-__host__ __device__ constexpr int v2_gspan(int r) { return V2_LG * r; }   // pairs per group
+#ifndef PSB200_NR_LIGHT
+#define PSB200_NR_LIGHT PSB200_NR
+#endif
+#ifndef PSB200_NR_MID
+#define PSB200_NR_MID PSB200_NR
+#endif
+#ifndef PSB200_NR_HEAVY
+#define PSB200_NR_HEAVY PSB200_NR
+#endif
+__host__ __device__ constexpr int v2_nr(int job)
+{
+    return job_nacc(job) <= 2 ? PSB200_NR_LIGHT : (job_nacc(job) <= 5 ? PSB200_NR_MID : PSB200_NR_HEAVY);
+}
+static_assert(PSB200_NR_LIGHT == 1 || PSB200_NR_LIGHT == 2 || PSB200_NR_LIGHT == 4, "rows per warp: 1, 2 or 4");
+static_assert(PSB200_NR_MID == 1 || PSB200_NR_MID == 2 || PSB200_NR_MID == 4, "rows per warp: 1, 2 or 4");
+static_assert(PSB200_NR_HEAVY == 1 || PSB200_NR_HEAVY == 2 || PSB200_NR_HEAVY == 4, "rows per warp: 1, 2 or 4");
+// (Measured and dropped in round 1: splitting a warp into lockstep groups that run at DIFFERENT l3 -- it shortens
+// the skew too, but the W' row stops being one broadcast per step: 153.1 -> 156.9 / 163.1 ms per step.)
+__host__ __device__ constexpr int v2_span(int job) { return (32 / v2_nr(job)) * v2_r(job); }   // pairs per row per warp
 constexpr int V2_TC_MAX = 256;                 // upper bound of v2_tc()
 // steps per staged chunk: longer chunks where the W' tile is small (fewer staging events)
 __host__ __device__ constexpr int v2_tc(int job);
-constexpr int V2_THREADS = V2_NW * 32;
+constexpr int V2_THREADS = 32;
 __host__ __device__ constexpr int v2_pb(int r) { return V2_THREADS * r; }            // pairs per block (= per warp)
 constexpr int V2_PB_MAX = V2_THREADS * V2_R_MAX;
-__host__ __device__ constexpr int v2_szu(int tc, int r) { return tc + v2_gspan(r) + r; }   // falling-index entries per chunk
-__host__ __device__ constexpr int v2_szv(int tc, int r) { return tc + (2 * V2_G - 1) * v2_gspan(r) + r; }   // rising-index
-__host__ __device__ constexpr int v2_szw(int tc, int r) { return tc + (V2_G - 1) * v2_gspan(r); }          // W' rows
-__host__ __device__ constexpr int v2_subu(int tc, int r) { return v2_szu(tc, r) / r + 1; }   // de-interleaved sub-table strides
-__host__ __device__ constexpr int v2_subv(int tc, int r) { return v2_szv(tc, r) / r + 1; }
+__host__ __device__ constexpr int v2_szt(int job) { return v2_tc(job) + v2_span(job) + v2_r(job); }   // table entries per row per chunk
+__host__ __device__ constexpr int v2_sub(int job) { return v2_szt(job) / v2_r(job) + 1; }             // de-interleaved sub-table stride
 
 __host__ __device__ constexpr int v2_nqp(int job) { return (job_nw(job) + 1) & ~1; }   // W' columns (even)
 // Family as the TUNED kernel evaluates it.  Jobs that only ever use EVEN-parity terms (M02, M++, EEEE,
@@ -103,10 +119,20 @@ __host__ __device__ constexpr int v2_tc(int job)
     return (v2_nqp(job) <= 2 ? 256 : 128) / v2_r(job) * v2_r(job);
 #endif
 }
+// Doubles between the tables of consecutive rows of a warp.  With 64-bit table loads (NTAB = 1) one shared-memory
+// wavefront serves a half-warp; for NR = 4 that is two row groups of 8 lanes, each reading 8 consecutive doubles at
+// the same relative position of its own table: conflict-free iff the stride is 8 modulo 16 doubles.  (128-bit
+// loads are served per quarter-warp = at most one row group; NR = 2 puts one row group in each half-warp.)
+__host__ __device__ constexpr int v2_tstride(int job)
+{
+    const int n = v2_ntab(job) * v2_r(job) * v2_sub(job);
+    if (v2_ntab(job) == 1 && v2_nr(job) == 4) return n + ((8 - n % 16) + 16) % 16;
+    return n + (n & 1);
+}
 __host__ __device__ constexpr int v2_smem_doubles(int job)
 {
-    return v2_ntab(job) * v2_r(job) * (v2_subu(v2_tc(job), v2_r(job)) + v2_subv(v2_tc(job), v2_r(job)))
-         + v2_szw(v2_tc(job), v2_r(job)) * v2_nqp(job) + v2_pb(v2_r(job)) * (v2_family(job) == FAM_02 ? 2 : 1) + 2;
+    return 2 * v2_nr(job) * v2_tstride(job) + v2_tc(job) * v2_nqp(job)
+         + v2_pb(v2_r(job)) * (v2_family(job) == FAM_02 ? 2 : 1) + 2;
 }
 
 struct V2Tables {
@@ -139,7 +165,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 }
 __device__ __forceinline__ void block_sync()
 {
-    if constexpr (V2_NW == 1) __syncwarp(); else __syncthreads();
+    __syncwarp();            // one warp per block: staging is warp-private
 }
 __device__ __forceinline__ void cp_async_wait_all()
 {
@@ -166,40 +192,42 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     constexpr int NACC = job_nacc(JOB);
     constexpr int NQP = v2_nqp(JOB);
     constexpr int R = v2_r(JOB);
-    constexpr int V2_GSPAN = v2_gspan(R), V2_PB = v2_pb(R);
+    constexpr int NR = v2_nr(JOB), LPR = 32 / NR;     // rows per warp, lanes per row
+    constexpr int SPAN = v2_span(JOB);                // pairs per row per warp
     constexpr int NTAB = v2_ntab(JOB);       // F00: ratio tables only; F22/F02: value + (negated) inverse
     constexpr int DS = (FAM == FAM_00) ? 2 : 1;   // stride of d inside a warp == step of l3
     constexpr int V2_TC = v2_tc(JOB);
-    constexpr int V2_SZU = v2_szu(V2_TC, R), V2_SZV = v2_szv(V2_TC, R), V2_SZW = v2_szw(V2_TC, R);
-    constexpr int V2_SUBU = v2_subu(V2_TC, R), V2_SUBV = v2_subv(V2_TC, R);
+    constexpr int SZT = v2_szt(JOB), SUB = v2_sub(JOB), TSTR = v2_tstride(JOB);
 
     // F22/F02 tables hold (value, inverse) pairs so one 128-bit load fetches both; F00 holds ratios.
     extern __shared__ __align__(16) double smem[];
-    double* shU = smem;                                   // falling index: (U, -1/U) | RT
-    double* shV = shU + NTAB * R * V2_SUBU;               // rising index:  (V, 1/V)  | RV
-    double* shW = shV + NTAB * R * V2_SUBV;               // [V2_SZW][NQP]
-    if ((NTAB * R * (V2_SUBU + V2_SUBV)) & 1) shW += 1;   // keep W' rows 16-byte aligned
-    double* shF = shW + V2_SZW * NQP;                     // start values f22(d) | g(d)
-    double* shH = shF + V2_PB;                            // start values f00(d)     (F02 only)
+    double* shU = smem;                                   // falling index: (U, -1/U) | RT, one table per row
+    double* shV = shU + NR * TSTR;                        // rising index:  (V, 1/V)  | RV
+    double* shW = shV + NR * TSTR;                        // [V2_TC][NQP]   (TSTR is even: 16-byte aligned)
+    double* shF = shW + V2_TC * NQP;                      // start values f22(d) | g(d)
+    double* shH = shF + 32 * R;                           // start values f00(d)     (F02 only)
 
     const int2 blk = T.blocks[blockIdx.x];
-    const int l1 = blk.x, d_lo = blk.y;
-    const int L = 2 * l1 + 1;
+    const int l1_first = blk.x, d_lo = blk.y;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int woff = (lane / V2_LG) * V2_GSPAN;           // pair offset of my lockstep group
-    const int e = (lane % V2_LG) * R;                     // pair offset inside the group
-    const int cV = 2 * woff + e;
-    const int dmax = A.lmax - l1;                         // last valid d of this row
-    // last step: the last pair (offset SPAN-1) finishes its family, or the window spectrum ends
+    const int rg = lane / LPR;                            // my row group
+    const int l1 = l1_first + rg;                         // my row
+    const int L = 2 * l1 + 1;
+    const int e = (lane % LPR) * R;                       // pair offset of my first pair inside the window
+    const int dmax = (l1 < A.row_hi) ? A.lmax - l1 : -1;  // last valid d of my row (rows past the band: none)
+    const int l1_last = min(l1_first + NR, A.row_hi) - 1; // longest family of the warp
+    // last step: the last pair (offset SPAN-1) of the last row finishes its family, or the window spectrum ends
     const int tau_end = (A.lenW - 1 - d_lo < 0) ? -1
-                      : min(V2_GSPAN - 1 + (2 * l1) / DS, (A.lenW - 1 - d_lo) / DS);   // block-uniform
+                      : min(SPAN - 1 + (2 * l1_last) / DS, (A.lenW - 1 - d_lo) / DS);   // block-uniform
+    const double* myU = shU + rg * TSTR;
+    const double* myV = shV + rg * TSTR;
 
     // ---- start values (closed form), one per pair, parked in shared memory ----
     {
-        const double gl1 = T.gam[l1];
+        const double gl1 = T.gam[min(l1, A.lmax)];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int d = d_lo + DS * (woff + e + r);
+            const int d = d_lo + DS * (e + r);
             double g00 = 0.0, g22 = 0.0;
             if (d <= dmax) {
                 const int l2 = l1 + d;
@@ -233,73 +261,78 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
         const double a = (double)l1 * (double)(l1 + 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int l2 = l1 + d_lo + DS * (woff + e + r);
+            const int l2 = l1 + d_lo + DS * (e + r);
             const double b = (double)l2 * (double)(l2 + 1);
             e2_s[r] = a + b;
             e2_ab[r] = a * b;
         }
     }
     // x = j (j+1) of the warp's current l3 (uniform), advanced by 4j+6 per step of 2
-    double xj = (double)(d_lo + DS * woff) * (double)(d_lo + DS * woff + 1);
-    double xinc = 4.0 * (double)(d_lo + DS * woff) + 6.0;
+    double xj = (double)d_lo * (double)(d_lo + 1);
+    double xinc = 4.0 * (double)d_lo + 6.0;
     // rotating windows (2R-1 live entries each)
     double wU0[2 * R - 1], wU1[2 * R - 1], wV0[2 * R - 1], wV1[2 * R - 1];
 #pragma unroll
     for (int k = 0; k < 2 * R - 1; ++k) { wU0[k] = 0.0; wU1[k] = 0.0; wV0[k] = 0.0; wV1[k] = 0.0; }
 
-    double k4 = 4.0 * (double)(2 * (d_lo + woff) + 1);    // 4 (2j+1) at tau = 0   (DS == 1 jobs only)
+    double k4 = 4.0 * (double)(2 * d_lo + 1);             // 4 (2j+1) at tau = 0   (DS == 1 jobs only)
     (void)k4;
-    const bool warp_live = d_lo <= dmax;
+    const bool warp_live = d_lo <= A.lmax - l1_first;     // block-uniform (the first row is the longest in d)
 
     for (int tau0 = 0; tau0 <= tau_end; tau0 += V2_TC) {
         block_sync();
         // ================= stage this chunk's tables =================
         // falling-index tables, entry idx <-> n = tau0 - SPAN + idx  (n = t+1 of the step that uses it)
-        for (int idx = tid; idx < V2_SZU; idx += V2_THREADS) {
-            const int pos = (idx % R) * V2_SUBU + idx / R;
+        // (one table per row of the warp: g = row group, Lg = 2 (l1_first + g) + 1)
+        for (int i = tid; i < NR * SZT; i += V2_THREADS) {
+            const int g = i / SZT, idx = i - g * SZT;
+            const int Lg = 2 * (l1_first + g) + 1;
+            const int pos = (idx % R) * SUB + idx / R;
             if constexpr (FAM == FAM_00) {
                 // ratio a(j+1)^2/a(j+2)^2, falling part at n = t+1.  The windows hand a pair the entry
                 // nu = t/2 + 1 (the "next step" slot), hence n = 2 nu - 1.
-                const int n = 2 * (tau0 - V2_GSPAN + idx) - 1;
+                const int n = 2 * (tau0 - SPAN + idx) - 1;
                 double v = 0.0;
-                if (n >= 1 && n <= L - 2)
-                    v = ((double)n * (double)(L - n)) * (__ldg(T.INV + n + 1) * __ldg(T.INV + (L - n - 1)));
-                shU[pos] = v;
+                if (n >= 1 && n <= Lg - 2)
+                    v = ((double)n * (double)(Lg - n)) * (__ldg(T.INV + n + 1) * __ldg(T.INV + (Lg - n - 1)));
+                shU[g * TSTR + pos] = v;
             } else {
-                const int n = tau0 - V2_GSPAN + idx;
+                const int n = tau0 - SPAN + idx;
                 double u = 0.0, iu = 0.0;
-                if (n >= 1 && n <= L - 1) {
-                    u = __ldg(T.S + n) * __ldg(T.S + (L - n));
-                    iu = -(__ldg(T.IS + n) * __ldg(T.IS + (L - n)));
+                if (n >= 1 && n <= Lg - 1) {
+                    u = __ldg(T.S + n) * __ldg(T.S + (Lg - n));
+                    iu = -(__ldg(T.IS + n) * __ldg(T.IS + (Lg - n)));
                 }
-                reinterpret_cast<double2*>(shU)[pos] = make_double2(u, iu);
+                reinterpret_cast<double2*>(shU + g * TSTR)[pos] = make_double2(u, iu);
             }
         }
         // rising-index tables, entry idx <-> m' = tau0 + idx + 2 d_lo  (m' = m+1 of the step that uses it)
-        for (int idx = tid; idx < V2_SZV; idx += V2_THREADS) {
-            const int pos = (idx % R) * V2_SUBV + idx / R;
+        for (int i = tid; i < NR * SZT; i += V2_THREADS) {
+            const int g = i / SZT, idx = i - g * SZT;
+            const int Lg = 2 * (l1_first + g) + 1;
+            const int pos = (idx % R) * SUB + idx / R;
             if constexpr (FAM == FAM_00) {
                 // rising part at mp = m+1 (m = j + d even); slot mu = m/2 + 1, hence mp = 2 mu - 1
                 const int mp = 2 * (tau0 + idx + d_lo) - 1;
                 double v = 0.0;
                 if (mp >= 1)
-                    v = ((double)mp * (double)(mp + L)) * (__ldg(T.INV + mp + 1) * __ldg(T.INV + (mp + L + 1)));
-                shV[pos] = v;
+                    v = ((double)mp * (double)(mp + Lg)) * (__ldg(T.INV + mp + 1) * __ldg(T.INV + (mp + Lg + 1)));
+                shV[g * TSTR + pos] = v;
             } else {
                 const int mp = tau0 + idx + 2 * d_lo;
                 double v = 0.0, iv = 0.0;
                 if (mp >= 1) {
-                    v = __ldg(T.S + mp) * __ldg(T.S + (mp + L));
-                    iv = __ldg(T.IS + mp) * __ldg(T.IS + (mp + L));
+                    v = __ldg(T.S + mp) * __ldg(T.S + (mp + Lg));
+                    iv = __ldg(T.IS + mp) * __ldg(T.IS + (mp + Lg));
                 }
-                reinterpret_cast<double2*>(shV)[pos] = make_double2(v, iv);
+                reinterpret_cast<double2*>(shV + g * TSTR)[pos] = make_double2(v, iv);
             }
         }
-        // W' rows j = d_lo + DS (tau0 + row), row < SZW   (16-byte cp.async; rows past lenW are zero)
+        // W' rows j = d_lo + DS (tau0 + row), row < V2_TC   (16-byte cp.async; rows past lenW are zero)
         {
             const double* src = T.Wp + (size_t)(d_lo + DS * tau0) * NQP;
             constexpr int CPR = NQP / 2;                    // 16-byte pieces per row
-            constexpr int NCH = V2_SZW * CPR;
+            constexpr int NCH = V2_TC * CPR;
             for (int c = tid; c < NCH; c += V2_THREADS) {
                 const int row = c / CPR, piece = c % CPR;
                 cp_async16(shW + 2 * c, src + (size_t)row * DS * NQP + 2 * piece);
@@ -311,16 +344,16 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
         if (!warp_live) continue;            // dead warps only help staging
 
         if (tau0 == 0) {
-            // prime the carried part of the rising windows (k = 0..R-2 <-> idx = 1 + cV + k)
+            // prime the carried part of the rising windows (k = 0..R-2 <-> idx = 1 + e + k)
 #pragma unroll
             for (int k = 0; k < R - 1; ++k) {
-                const int idx = 1 + cV + k;
-                const int pos = (idx % R) * V2_SUBV + idx / R;
+                const int idx = 1 + e + k;
+                const int pos = (idx % R) * SUB + idx / R;
                 if constexpr (NTAB > 1) {
-                    const double2 v = reinterpret_cast<const double2*>(shV)[pos];
+                    const double2 v = reinterpret_cast<const double2*>(myV)[pos];
                     wV0[k] = v.x; wV1[k] = v.y;
                 } else {
-                    wV0[k] = shV[pos];
+                    wV0[k] = myV[pos];
                 }
             }
         }
@@ -329,20 +362,20 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
         for (int tg = 0; tg < tg_end; tg += R) {
             // ---- the R new entries of every window ----
             {
-                const int bu = (tg - e + V2_GSPAN) / R;    // idx = tg + 1 - e + u + GSPAN
-                const int bv = (tg + cV) / R + 1;          // idx = tg + cV + R + u
+                const int bu = (tg - e + SPAN) / R;        // idx = tg + 1 - e + u + SPAN
+                const int bv = (tg + e) / R + 1;           // idx = tg + e + R + u
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
-                    const int pu = ((1 + u) % R) * V2_SUBU + bu + (1 + u) / R;
-                    const int pv = u * V2_SUBV + bv;
+                    const int pu = ((1 + u) % R) * SUB + bu + (1 + u) / R;
+                    const int pv = u * SUB + bv;
                     if constexpr (NTAB > 1) {
-                        const double2 a = reinterpret_cast<const double2*>(shU)[pu];
-                        const double2 c = reinterpret_cast<const double2*>(shV)[pv];
+                        const double2 a = reinterpret_cast<const double2*>(myU)[pu];
+                        const double2 c = reinterpret_cast<const double2*>(myV)[pv];
                         wU0[R - 1 + u] = a.x; wU1[R - 1 + u] = a.y;
                         wV0[R - 1 + u] = c.x; wV1[R - 1 + u] = c.y;
                     } else {
-                        wU0[R - 1 + u] = shU[pu];
-                        wV0[R - 1 + u] = shV[pv];
+                        wU0[R - 1 + u] = myU[pu];
+                        wV0[R - 1 + u] = myV[pv];
                     }
                 }
             }
@@ -352,7 +385,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
                 // window spectra of this step: warp-uniform broadcast reads
                 double w[NQP];
                 {
-                    const double* wr = shW + (size_t)(tg + s + woff) * NQP;
+                    const double* wr = shW + (size_t)(tg + s) * NQP;
                     if constexpr (NWQ == 1) {
                         w[0] = wr[0];
                     } else {
@@ -465,7 +498,7 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     if (!warp_live) return;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int d = d_lo + DS * (woff + e + r);
+        const int d = d_lo + DS * (e + r);
         if (d <= dmax) {
             if constexpr (E2) {
                 // powers of 1/D; l1 < 2 (|m| > l, true symbol 0): exact zeros, as the recurrence path gives

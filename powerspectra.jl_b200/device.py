@@ -90,6 +90,9 @@ def cov_slab(block, lmin, lmax, spectra, ratios, W, X: torch.Tensor, row_lo=None
     row_hi = lmax + 1 if row_hi is None else row_hi
     _require_cuda(X)
     lenW = min(int(w.numel()) for w in W)
+    for t in list(spectra) + list(ratios):      # the C entry point takes no lengths for these: l = 0..lmax is read
+        if int(t.numel()) < lmax + 1:
+            raise ValueError(f"spectrum / ratio vector of {int(t.numel())} entries, need lmax+1 = {lmax + 1}")
     rc = _lib.lib().psb200_cov_dev(block, lmin, lmax, _vptrs(spectra), len(spectra), _vptrs(ratios), len(ratios),
                                    _vptrs(W), len(W), lenW, C.c_void_p(X.data_ptr()), N, row_lo, row_hi,
                                    _stream_ptr())

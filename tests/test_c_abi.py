@@ -4,6 +4,8 @@ import os
 import subprocess
 import textwrap
 
+import pytest
+
 from conftest import ROOT
 
 C_SRC = textwrap.dedent(r"""
@@ -41,18 +43,42 @@ C_SRC = textwrap.dedent(r"""
         if (ndev() == 0) {
             if (rc != 5 || !strstr(last_error(), "no CPU fallback")) { printf("expected code 5, got %d (%s)\n", rc, last_error()); return 7; }
         } else if (rc != 0) { printf("compute failed: %d %s\n", rc, last_error()); return 8; }
+        if (argc > 2 && !strcmp(argv[2], "--require-gpu")) {
+            /* V == 1 and l1 + l2 <= 7 = nV-1: the l3 sum is complete, Xi = 1/4pi, M[l1,l2] = (2 l2+1)/4pi */
+            if (rc != 0) { printf("a device is required here (rc=%d)\n", rc); return 9; }
+            const double q = 0.07957747154594767;
+            for (int l1 = 0; l1 < 8; ++l1)
+                for (int l2 = 0; l1 + l2 < 8; ++l2) {
+                    const double want = (2 * l2 + 1) * q, got = M[l1 + 8 * l2];
+                    if (!(got > want * (1 - 1e-13) && got < want * (1 + 1e-13))) { printf("M[%d,%d] = %.17g, want %.17g\n", l1, l2, got, want); return 10; }
+                }
+            printf("computed on the device\n");
+        }
         printf("ok rc=%d\n", rc);
         return 0;
     }
 """)
 
 
-def test_c_program_uses_the_abi(tmp_path, ps):
+def _build(tmp_path):
     src = tmp_path / "abi.c"
     exe = tmp_path / "abi"
     src.write_text(C_SRC)
     subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                     str(src), "-o", str(exe), "-ldl"], check=True)
-    out = subprocess.run([str(exe), ps.LIB_PATH], capture_output=True, text=True)
+    return exe
+
+
+def test_c_program_uses_the_abi(tmp_path, ps):
+    """CPU box: symbols resolve, host-side helpers answer, a compute call fails loudly with code 5."""
+    out = subprocess.run([str(_build(tmp_path)), ps.LIB_PATH], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ok rc=" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_computes_on_the_device(tmp_path, ps):
+    """GPU box: the same plain-C client must get a correct matrix out of psb200_mcm."""
+    out = subprocess.run([str(_build(tmp_path)), ps.LIB_PATH, "--require-gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "computed on the device" in out.stdout
