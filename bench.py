@@ -578,7 +578,12 @@ def run_gpu(args, lmax):
                                            "(see f64_oracle_vs_long_double); the test suite gates on the condition-aware bound",
                               "per_matrix": par}
         if not args.no_extra:
-            line["extra"] = extras(args, ps, dev, L, world, torch, cpu=(world == 1 and not args.no_cpu))
+            try:
+                line["extra"] = extras(args, ps, dev, L, world, torch, cpu=(world == 1 and not args.no_cpu))
+            except Exception as e:      # noqa: BLE001 -- the extras never cost the headline line
+                import traceback
+                traceback.print_exc()
+                line["extra"] = {"error": repr(e)}
         print(json.dumps(line))
         if check is not None and not check["bitwise_equal"]:
             sys.stderr.write("bench: multi_gpu_check FAILED: " + json.dumps(check) + "\n")
@@ -623,8 +628,10 @@ def extras(args, ps, dev, L, world, torch, cpu):
     # (1) fused master call vs the separate calls it replaces, lmax 6143, resident, 1 GPU
     lmax = args.lmax
     N = lmax + 1
-    sky_V = syn.mask_spectra(lmax, seeds=(1001, 1002))
-    Vd = {k: torch.tensor(v, device="cuda") for k, v in sky_V.items()}
+    sky_V = syn.mask_spectra(lmax, seeds=(1001, 1002, 1003, 1004))
+    # V_TT (T1 x T2), V_TP (T1 x P2), V_PT (P1 x T2), V_PP (P1 x P2) with T = masks 0, 2 and P = masks 1, 3
+    Vd = {(0, 0): torch.tensor(sky_V[(0, 2)], device="cuda"), (0, 1): torch.tensor(sky_V[(0, 3)], device="cuda"),
+          (1, 0): torch.tensor(sky_V[(1, 2)], device="cuda"), (1, 1): torch.tensor(sky_V[(1, 3)], device="cuda")}
     X = [torch.empty((N, N), dtype=torch.float64, device="cuda") for _ in range(5)]
 
     def fused():

@@ -7,6 +7,7 @@
 #include "psb200_common.cuh"
 #include "psb200_pair_v1.cuh"
 #include "psb200_pair_v2.cuh"
+#include "psb200_pair_v3.cuh"
 #include "psb200_lowrows.cuh"
 #include "psb200_quickpol.cuh"
 
@@ -147,8 +148,12 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 int kernel_version()
 {
     // read on every call so a test can switch kernels inside one process
+    // v1: simple kernel (sqrt/divide recurrence, sum normalisation); v2: tuned recurrence kernel; default v3:
+    // closed-form kernel.  v1 and v2 are on-device cross-checks of v3 by independent methods, not fallbacks.
     const char* e = getenv("PSB200_KERNEL");
-    return (e && strcmp(e, "v1") == 0) ? 1 : 2;       // v1: simple kernel (cross-check); default: tuned kernel
+    if (e && strcmp(e, "v1") == 0) return 1;
+    if (e && strcmp(e, "v2") == 0) return 2;
+    return 3;
 }
 
 // PSB200_TRACE=1: per-phase wall-clock of the host-level calls on stderr (adds stream syncs)
@@ -178,7 +183,7 @@ struct Trace {
 struct DevTables {
     int lmax = -1;
     int nS = 0;
-    double *S = nullptr, *IS = nullptr, *INV = nullptr, *gam = nullptr;
+    double *S = nullptr, *IS = nullptr, *INV = nullptr, *gam = nullptr, *igam = nullptr;
 };
 DevTables g_tables[16];
 std::mutex g_tab_mutex;
@@ -190,8 +195,8 @@ int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
     if (t.lmax >= lmax) { *out = &t; return OK; }
     const int want = std::max(lmax, 1024);
     const int nS = 4 * want + 4096;
-    const int ng = want + 2;
-    std::vector<double> S(nS), IS(nS), INV(nS), G(ng);
+    const int ng = nS;                          // the closed-form kernel reads g(n) up to n ~ 2 lmax + a chunk
+    std::vector<double> S(nS), IS(nS), INV(nS), G(ng), IG(ng);
     for (int n = 0; n < nS; ++n) {
         const long double r = sqrtl((long double)n);
         S[n] = (double)r;
@@ -199,17 +204,22 @@ int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
         INV[n] = n ? (double)(1.0L / (long double)n) : 0.0;
     }
     long double g = 1.0L;                       // binom(2n,n)/4^n = prod (2i-1)/(2i)
-    G[0] = 1.0;
-    for (int n = 1; n < ng; ++n) { g *= (long double)(2 * n - 1) / (long double)(2 * n); G[n] = (double)g; }
+    G[0] = 1.0; IG[0] = 1.0;
+    for (int n = 1; n < ng; ++n) {
+        g *= (long double)(2 * n - 1) / (long double)(2 * n);
+        G[n] = (double)g;
+        IG[n] = (double)(1.0L / g);
+    }
     if (t.S) {                                   // growing: nothing may still be reading the old tables
         CUDA_TRY(cudaDeviceSynchronize());
-        cudaFree(t.S); cudaFree(t.IS); cudaFree(t.INV); cudaFree(t.gam);
+        cudaFree(t.S); cudaFree(t.IS); cudaFree(t.INV); cudaFree(t.gam); cudaFree(t.igam);
         t = DevTables{};
     }
     CUDA_TRY(cudaMalloc(&t.S, nS * sizeof(double)));
     CUDA_TRY(cudaMalloc(&t.IS, nS * sizeof(double)));
     CUDA_TRY(cudaMalloc(&t.INV, nS * sizeof(double)));
     CUDA_TRY(cudaMalloc(&t.gam, ng * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.igam, ng * sizeof(double)));
     // Uploads go on the LAUNCHING stream (the kernels that read the tables run on non-blocking streams, which
     // do not order against the legacy default stream a plain cudaMemcpy uses), and the stream is drained
     // before the pageable host vectors die.
@@ -217,6 +227,7 @@ int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
     CUDA_TRY(cudaMemcpyAsync(t.IS, IS.data(), nS * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(t.INV, INV.data(), nS * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(t.gam, G.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t.igam, IG.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     t.lmax = want; t.nS = nS;
     *out = &t;
@@ -346,11 +357,17 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
     tr.mark("  (inputs uploaded)", dev, st);
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, st, &t)) return rc;
+    const bool v3 = kernel_version() == 3;
     BlockList bl;
-    if (int rc = ensure_blocks(dev, A, psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), psb::v2_nr(JOB), st, &bl)) return rc;
+    if (v3) {
+        if (int rc = ensure_blocks(dev, A, 2, psb::v3_r(JOB), psb::v3_nr(JOB), st, &bl)) return rc;
+    } else {
+        if (int rc = ensure_blocks(dev, A, psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), psb::v2_nr(JOB), st, &bl)) return rc;
+    }
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
     constexpr int nqp = psb::v2_nqp(JOB);
-    const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_PB_MAX);
+    static_assert(psb::v2_nqp(JOB) == psb::v3_nqp(JOB), "both tuned kernels share the W' layout");
+    const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_PB_MAX) + 2;
     double* Wp = nullptr;
     tr.mark("  tables + block list", dev, st);
     if (int rc = wp_reserve(dev, st, (size_t)rows_w * nqp, &Wp)) return rc;
@@ -358,10 +375,18 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
         A.W[0], A.W[1], A.W[2], A.W[3], A.W[4], A.W[5], A.W[6], A.W[7]);
     CUDA_TRY(cudaGetLastError());
     tr.mark("  prep W' kernel", dev, st);
-    psb::V2Tables T{};
-    T.S = t->S; T.IS = t->IS; T.INV = t->INV; T.gam = t->gam; T.nS = t->nS;
-    T.blocks = bl.d; T.Wp = Wp;
-    const int e = psb::launch_pair_v2<JOB>(A, T, bl.n, st);
+    int e = 0;
+    if (v3) {
+        psb::V3Tables T{};
+        T.gam = t->gam; T.igam = t->igam; T.INV = t->INV; T.nS = t->nS;
+        T.blocks = bl.d; T.Wp = Wp;
+        e = psb::launch_pair_v3<JOB>(A, T, bl.n, st);
+    } else {
+        psb::V2Tables T{};
+        T.S = t->S; T.IS = t->IS; T.INV = t->INV; T.gam = t->gam; T.nS = t->nS;
+        T.blocks = bl.d; T.Wp = Wp;
+        e = psb::launch_pair_v2<JOB>(A, T, bl.n, st);
+    }
     if (e != 0) return fail(ERR_CUDA, "pair kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     tr.mark("  pair kernel", dev, st);
     return OK;
@@ -371,7 +396,8 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
 template <int JOB>
 void job_tiling(int* ds, int* r, int* nr)
 {
-    *ds = psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1; *r = psb::v2_r(JOB); *nr = psb::v2_nr(JOB);
+    if (kernel_version() == 2) { *ds = psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1; *r = psb::v2_r(JOB); *nr = psb::v2_nr(JOB); }
+    else { *ds = 2; *r = psb::v3_r(JOB); *nr = psb::v3_nr(JOB); }
 }
 int job_tiling_any(int job, int* ds, int* r, int* nr)
 {
@@ -544,8 +570,8 @@ static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
-    constexpr long NRH = psb::v2_nr(psb::JOB_TTTT);
-    constexpr long SPAN = psb::v2_span(psb::JOB_TTTT);           // the covariance jobs dominate a step
+    constexpr long NRH = psb::v3_nr(psb::JOB_TTTT);
+    constexpr long SPAN = psb::v3_span(psb::JOB_TTTT);           // the covariance jobs dominate a step
     constexpr long SKEW = (130 * SPAN) / 192, OVH = 70;
     long double c = 0;
     for (long base = 0; base <= D; base += 2 * SPAN) {

@@ -292,3 +292,44 @@ def test_even_parity_spin2_identity_exact():
         worst = max(worst, np.max(np.abs(f22[even] - f00[even] * N[even] / D)))
         checked += int(even.sum())
     assert checked > 3000 and worst < 2e-15, (checked, worst)
+
+
+def test_closed_form_products():
+    """The closed forms the default kernel evaluates instead of any recurrence (psb200_pair_v3.cuh), against every exact
+    (sympy) family of tests/golden/w3j_exact.npz (l up to 80).  g(n) = binom(2n,n)/4^n, d = l2-l1, L = 2 l1+1, t = j-d, m = j+d:
+        even parity:  f00(j)^2 = PT[t] PV[m],  PT[t] = g(t/2) g(l1-t/2),  PV[m] = g(m/2) / (g(m/2+l1) (m+L))
+                      2 D f00 f22 = PT PV (u^2 - (2ab+1)),   4 D^2 f22^2 = PT PV (u^2 - (2ab+1))^2,   u = x - (a+b-1)
+        odd parity:   4 D^2 f22^2 = (x-a-b+2)^2 QT[t] QV[m],  QT[t] = t (L-t) PT[t-1],  QV[m] = m (m+L) PV[m-1]."""
+    from math import comb
+    gm = [comb(2 * n, n) / 4.0 ** n for n in range(400)]
+    g = np.load(os.path.join(GOLDEN, "w3j_exact.npz"))
+    fam = {(int(f), int(a), int(b)): g["values"][off:off + n] for f, a, b, off, n in g["index"]}
+    worst = {"f00^2": 0.0, "f00 f22": 0.0, "f22^2 even": 0.0, "f22^2 odd": 0.0}
+    checked = 0
+    for (f, l1, l2), f22 in fam.items():
+        if f != 1 or l1 < 2:
+            continue
+        f00 = fam[(0, l1, l2)]
+        d, L = l2 - l1, 2 * l1 + 1
+        a, b = l1 * (l1 + 1.0), l2 * (l2 + 1.0)
+        D2 = (l1 - 1.0) * l1 * (l1 + 1) * (l1 + 2) * (l2 - 1.0) * l2 * (l2 + 1) * (l2 + 2)
+        for i, j in enumerate(range(d, l1 + l2 + 1)):
+            t, m, x = j - d, j + d, j * (j + 1.0)
+            if t % 2 == 0:
+                PT = gm[t // 2] * gm[l1 - t // 2]
+                PV = gm[m // 2] / (gm[m // 2 + l1] * (m + L))
+                u = x - (a + b - 1.0)
+                nn = u * u - (2.0 * a * b + 1.0)
+                scale = max(abs(f00[i]), abs(f22[i]), 1e-300) ** 2
+                worst["f00^2"] = max(worst["f00^2"], abs(PT * PV - f00[i] ** 2) / f00[i] ** 2)
+                worst["f00 f22"] = max(worst["f00 f22"], abs(PT * PV * nn / (2 * np.sqrt(D2)) - f00[i] * f22[i]) / scale)
+                worst["f22^2 even"] = max(worst["f22^2 even"], abs(PT * PV * nn * nn / (4 * D2) - f22[i] ** 2) / scale)
+            else:
+                assert abs(f00[i]) < 1e-300
+                PT = gm[(t - 1) // 2] * gm[l1 - (t - 1) // 2]
+                PV = gm[(m - 1) // 2] / (gm[(m - 1) // 2 + l1] * (m - 1 + L))
+                uo = x - a - b + 2.0
+                h = (t * (L - t) * PT) * (m * (m + L) * PV) * uo * uo / (4 * D2)
+                worst["f22^2 odd"] = max(worst["f22^2 odd"], abs(h - f22[i] ** 2) / max(f22[i] ** 2, 1e-300))
+            checked += 1
+    assert checked > 5000 and max(worst.values()) < 5e-14, (checked, worst)

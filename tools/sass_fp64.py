@@ -2,7 +2,7 @@
 
     python tools/sass_fp64.py [libpsb200.so] [--json out.json] [--listing out.txt]
 
-For each `psb::pair_kernel_v2<JOB>` the innermost loop with the most FP64-pipe instructions is the main
+For each `psb::pair_kernel_v3<JOB>` (`pair_kernel_v2` under PSB200_KERNEL=v2) the innermost loop with the most FP64-pipe instructions is the main
 loop body: one group of R l3-steps of a thread's R pairs = R*R pair-steps.  DFMA / DMUL / DADD in that body
 divided by R*R is the executed FP64 instruction count per pair-step that bench.py multiplies with the
 executed pair-steps (psb200_job_stats) to get the live roofline fraction.  R is read from the library
@@ -22,6 +22,8 @@ JOBS = ["M00", "M02", "Mpp", "Mmm", "Mpp_Mmm", "TTTT", "EEEE", "TTTE", "TETE", "
 API = {"M00": (0, 0), "M02": (0, 1), "Mpp": (0, 2), "Mmm": (0, 3), "Mpp_Mmm": (0, 4), "TTTT": (1, 0), "EEEE": (1, 1),
        "TTTE": (1, 2), "TETE": (1, 3), "TEEE_planck": (1, 4), "TEEE": (1, 5), "TTEE": (1, 6), "master": (2, 0)}
 FP64 = ("DFMA", "DMUL", "DADD")
+# which tuned kernel the library runs by default (PSB200_KERNEL=v2 selects the recurrence kernel: count that one then)
+KERNEL = "v2" if os.environ.get("PSB200_KERNEL") == "v2" else "v3"
 INS = re.compile(r"^\s*/\*([0-9a-f]{4,})\*/\s+(.*?);")
 
 
@@ -87,7 +89,7 @@ def analyse(lib):
     fns = functions(lib)
     res, listing = {}, []
     for k, name in enumerate(JOBS):
-        key = [f for f in fns if f"pair_kernel_v2ILi{k}E" in f]
+        key = [f for f in fns if f"pair_kernel_{KERNEL}ILi{k}E" in f]
         if not key:
             continue
         ins = fns[key[0]]
@@ -110,7 +112,14 @@ def analyse(lib):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args, skip = [], False
+    for a in sys.argv[1:]:                      # positional = the library; --json / --listing take a value
+        if skip:
+            skip = False
+        elif a in ("--json", "--listing"):
+            skip = True
+        elif not a.startswith("--"):
+            args.append(a)
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = args[0] if args else os.path.join(here, "powerspectra.jl_b200", "libpsb200.so")
     res, listing = analyse(lib)
