@@ -32,7 +32,7 @@
  *     (src/modecoupling.jl:6-8); lmin only crops rows/columns.
  *   - Return value: 0 ok; 1 bad argument (maps to ArgumentError / the @assert at
  *     src/modecoupling.jl:80,225); 2 CUDA error; 3 collective error; 4 out of memory;
- *     5 no usable CUDA device.  psb200_last_error() gives the message.  There is
+ *     5 no usable CUDA device; 6 singular matrix in a device-side solve (Julia: SingularException).  psb200_last_error() gives the message.  There is
  *     NO CPU fallback: without a B200-class device every compute call fails with 5.
  *   - Thread safety: calls may come from any OS thread; they are serialised inside.
  */
@@ -155,6 +155,37 @@ int psb200_quickpol_xi_dev(int nu1, int nu2, int s1, int s2, int lmax, const dou
 
 /* Cost-balanced contiguous column bands of the Xi matrix: edges[0] = 0 .. edges[nbands] = lmax+1. */
 int psb200_quickpol_edges(int lmax, int band_lo, int band_hi, int nbands, int* edges);
+
+/* ---- decoupling on the device (optional, the reference's host solves keep working) ----------------
+ * The mode-coupling matrix is computed on `ngpus` devices, assembled on ONE of them over NVLink (the pair kernels of
+ * the other devices store their row bands straight into that device's memory), LU-factorised there (cuSOLVER getrf,
+ * partial pivoting like the LAPACK call behind Julia's `lu`) and only the decoupled spectra return to the host:
+ * the N^2 x 8 B matrix never crosses PCIe.
+ *
+ * psb200_mcm_solve replaces  `M = mcm(spec, ...); Cl = M \ pCl`   src/modecoupling.jl:359-362, src/blockspectralmatrix.jl:124-129
+ *   system 0..3: the N x N matrix of psb200_mcm kind 0..3;  pCl, Cl: N x nrhs column-major (ldp, ldc >= N)
+ *   system 4: [M++ M--; M-- M++] \ [pCl_EE; pCl_BB]   (M_EE_BB, src/modecoupling.jl:213-216, :365-371)
+ *   system 5: [M++ -M--; -M-- M++] \ [pCl_EB; pCl_BE] (M_EB_BE, :220-223, :373-379);  pCl, Cl: 2N x nrhs (ld >= 2N)
+ *   The LU is that of the dense 2N x 2N block matrix, as src/blockspectralmatrix.jl:89-122 does. */
+enum { PSB200_SYS_M00 = 0, PSB200_SYS_M02 = 1, PSB200_SYS_MPP = 2, PSB200_SYS_MMM = 3, PSB200_SYS_EE_BB = 4, PSB200_SYS_EB_BE = 5 };
+int psb200_mcm_solve(int system, int lmin, int lmax, const double* V, int nV,
+                     const double* pCl, long ldp, int nrhs, double* Cl, long ldc, int ngpus);
+
+/* Everything maskedalm2spectra solves (src/modecoupling.jl:341-377) from ONE fused evaluation of the five matrices
+ * (psb200_mcm_master) without moving any of them: pCl and Cl are N x 9 column-major, columns in the order
+ *   0 TT  1 TE  2 ET  3 TB  4 BT  5 EE  6 BB  7 EB  8 BE
+ * TT = M00(V_TT) \ pTT;  TE, TB = M02(V_TP) \ .;  ET, BT = M02(V_PT) \ .;  [EE; BB] = M_EE_BB \ [pEE; pBB];
+ * [EB; BE] = M_EB_BE \ [pEB; pBE]. */
+int psb200_master_solve(int lmin, int lmax, const double* V_TT, const double* V_TP, const double* V_PT,
+                        const double* V_PP, int nV, const double* pCl, long ldp, double* Cl, long ldc, int ngpus);
+
+/* decouple_covmat (src/covariance.jl:8-14): out = B1^-1 Y (B2^-1)^T through lu(B1'), lu(B2') as the reference does.
+ * Host form: n x n column-major host matrices, computed on the current device.  Device form: device pointers, Y is
+ * overwritten in place (B1, B2 untouched), asynchronous on `stream` except for the pivot-singularity check. */
+int psb200_decouple_covmat(int n, const double* Y, long ldy, const double* B1, long ldb1, const double* B2, long ldb2,
+                           double* out, long ldo);
+int psb200_decouple_covmat_dev(int n, double* dY, long ldy, const double* dB1, long ldb1, const double* dB2, long ldb2,
+                               void* stream);
 
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);

@@ -14,12 +14,14 @@ from .covariance import (ConstantDict, CovarianceWorkspace, coupledcov, coupledc
                          loop_covTEEE, loop_covTEEE_planck, loop_covTETE, loop_covTTEE, loop_covTTTE,
                          loop_covTTTT, window_function_W)
 from .modecoupling import (Alm, alm2cl, inner_mcm00, inner_mcm02, inner_mcmmm, inner_mcmpp,
-                           inner_mcmpp_mcmmm, maskedalm2spectra, mcm, mcm_master)
-from .spectral import (BlockSpectralMatrix, SpectralArray, SpectralVector, decouple_covmat, spectralones,
+                           inner_mcmpp_mcmmm, maskedalm2spectra, maskedalm2spectra_device, mcm,
+                           mcm_master, mcm_solve)
+from .spectral import (BlockSpectralMatrix, SpectralArray, SpectralVector, decouple_covmat, decouple_covmat_device,
+                       spectralones,
                        spectralzeros)
 
 __all__ = [
-    "mcm", "mcm_master", "maskedalm2spectra", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
+    "mcm", "mcm_master", "mcm_solve", "maskedalm2spectra", "maskedalm2spectra_device", "decouple_covmat_device", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
     "SpectralArray", "SpectralVector", "BlockSpectralMatrix", "spectralzeros", "spectralones",
     "decouple_covmat", "BandedSpectralMatrix", "quickpolXi", "quickpolW", "k_u", "Alm", "alm2cl", "lib", "LIB_PATH", "PSB200Error",
 ]

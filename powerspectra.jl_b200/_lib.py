@@ -40,6 +40,11 @@ PROTOTYPES = {
     "psb200_quickpol_xi": (C.c_int, [C.c_int] * 5 + [DP, C.c_int, C.c_int, C.c_int, DP, C.c_long, C.c_int]),
     "psb200_quickpol_xi_dev": (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long,
                                                          C.c_int, C.c_int, C.c_void_p]),
+    "psb200_mcm_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, DP, C.c_int, DP, C.c_long, C.c_int, DP, C.c_long, C.c_int]),
+    "psb200_master_solve": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, DP, C.c_int, DP, C.c_long, DP, C.c_long, C.c_int]),
+    "psb200_decouple_covmat": (C.c_int, [C.c_int, DP, C.c_long, DP, C.c_long, DP, C.c_long, DP, C.c_long]),
+    "psb200_decouple_covmat_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
+                                             C.c_void_p]),
     "psb200_quickpol_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
 }
 
@@ -80,4 +85,7 @@ def check(rc: int):
     msg = lib().psb200_last_error().decode("utf-8", "replace")
     if rc == 1:
         raise ValueError(msg)
+    if rc == 6:
+        import numpy as np
+        raise np.linalg.LinAlgError(msg)       # Julia: LinearAlgebra.SingularException
     raise PSB200Error(rc, msg)

@@ -11,6 +11,9 @@
 #include "psb200_lowrows.cuh"
 #include "psb200_quickpol.cuh"
 
+#include <cusolverDn.h>      // types + prototypes only: the library is loaded with dlopen (psb200_solve.inl)
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
@@ -27,7 +30,7 @@
 
 namespace {
 
-enum { OK = 0, ERR_ARG = 1, ERR_CUDA = 2, ERR_COLL = 3, ERR_OOM = 4, ERR_NODEVICE = 5 };
+enum { OK = 0, ERR_ARG = 1, ERR_CUDA = 2, ERR_COLL = 3, ERR_OOM = 4, ERR_NODEVICE = 5, ERR_SINGULAR = 6 };
 
 thread_local std::string g_err;
 std::mutex g_mutex;
@@ -365,14 +368,17 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
         if (int rc = ensure_blocks(dev, A, psb::v2_family(JOB) == psb::FAM_00 ? 2 : 1, psb::v2_r(JOB), psb::v2_nr(JOB), st, &bl)) return rc;
     }
     // W'[j][q] = (2j+1) W_q[j] / 4pi, zero-padded so staging never reads past the end
-    constexpr int nqp = psb::v2_nqp(JOB);
-    static_assert(psb::v2_nqp(JOB) == psb::v3_nqp(JOB), "both tuned kernels share the W' layout");
+    const int nqp = v3 ? psb::v3_nqp(JOB) : psb::v2_nqp(JOB);
     const int rows_w = A.lenW + 2 * (psb::V2_TC_MAX + psb::V2_PB_MAX) + 2;
     double* Wp = nullptr;
     tr.mark("  tables + block list", dev, st);
     if (int rc = wp_reserve(dev, st, (size_t)rows_w * nqp, &Wp)) return rc;
-    psb::v2_prep_w<<<(rows_w + 255) / 256, 256, 0, st>>>(Wp, rows_w, nqp, psb::job_nw(JOB), A.lenW,
-        A.W[0], A.W[1], A.W[2], A.W[3], A.W[4], A.W[5], A.W[6], A.W[7]);
+    if (v3)
+        psb::v3_prep_w<JOB><<<(rows_w + 255) / 256, 256, 0, st>>>(Wp, rows_w, A.lenW,
+            A.W[0], A.W[1], A.W[2], A.W[3], A.W[4], A.W[5], A.W[6], A.W[7]);
+    else
+        psb::v2_prep_w<<<(rows_w + 255) / 256, 256, 0, st>>>(Wp, rows_w, nqp, psb::job_nw(JOB), A.lenW,
+            A.W[0], A.W[1], A.W[2], A.W[3], A.W[4], A.W[5], A.W[6], A.W[7]);
     CUDA_TRY(cudaGetLastError());
     tr.mark("  prep W' kernel", dev, st);
     int e = 0;
@@ -806,6 +812,8 @@ int run_quickpol_on_device(const QpHostJob& hj, int g, int a, int b, std::string
     return rc;
 }
 
+#include "psb200_solve.inl"
+
 }  // namespace
 
 // =========================================================================================
@@ -1057,6 +1065,110 @@ int psb200_quickpol_xi(int nu1, int nu2, int s1, int s2, int lmax, const double*
     cudaSetDevice(cur);
     for (int g = 0; g < ng; ++g)
         if (rcs[g] != OK) { g_err = "device " + std::to_string(g) + ": " + errs[g]; return rcs[g]; }
+    return OK;
+}
+
+
+// ---- decoupling on the device (psb200_solve.inl) ------------------------------------------------
+int psb200_mcm_solve(int system, int lmin, int lmax, const double* V, int nV, const double* pCl, long ldp, int nrhs,
+                     double* Cl, long ldc, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (system < 0 || system > 5) return fail(ERR_ARG, "unknown system %d", system);
+    const int N = lmax - lmin + 1;
+    if (int rc = check_common(lmin, lmax, N, lmin, lmax + 1)) return rc;
+    const int nb = system >= 4 ? 2 : 1;
+    if (!V || nV < 1 || !pCl || !Cl || nrhs < 1) return fail(ERR_ARG, "null / empty buffer");
+    if (ldp < (long)nb * N || ldc < (long)nb * N) return fail(ERR_ARG, "leading dimension of pCl / Cl below %d", nb * N);
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    HostJob hj{};
+    hj.job = system >= 4 ? (int)psb::JOB_MPPMMM : kMcmJob[system];
+    hj.lmin = lmin; hj.lmax = lmax; hj.lenW = nV;
+    hj.nW = 1; hj.vecs[0] = V; hj.lens[0] = (size_t)nV;
+    hj.nout = nb; hj.scale = 1;
+    int cur = 0, root = 0;
+    cudaGetDevice(&cur);
+    int rc = full_on_root(hj, ng, &root);
+    if (rc == OK) {
+        std::vector<RhsCol> cols(nrhs);
+        for (int k = 0; k < nrhs; ++k) {
+            cols[k].in[0] = pCl + (size_t)k * ldp; cols[k].in[1] = cols[k].in[0] + N;
+            cols[k].out[0] = Cl + (size_t)k * ldc; cols[k].out[1] = cols[k].out[0] + N;
+        }
+        DeviceScratch& R = g_scratch[root];
+        if (nb == 1) rc = solve_on_root(root, R.X[0], N, 1, cols);
+        else rc = solve_block_on_root(root, R.X[0], R.X[1], N, system == 4 ? 1.0 : -1.0, cols);
+    }
+    cudaSetDevice(cur);
+    return rc;
+}
+
+int psb200_master_solve(int lmin, int lmax, const double* V_TT, const double* V_TP, const double* V_PT,
+                        const double* V_PP, int nV, const double* pCl, long ldp, double* Cl, long ldc, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    const int N = lmax - lmin + 1;
+    if (int rc = check_common(lmin, lmax, N, lmin, lmax + 1)) return rc;
+    if (!V_TT || !V_TP || !V_PT || !V_PP || nV < 1 || !pCl || !Cl) return fail(ERR_ARG, "null / empty buffer");
+    if (ldp < N || ldc < N) return fail(ERR_ARG, "leading dimension of pCl / Cl below N=%d", N);
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    HostJob hj{};
+    hj.job = psb::JOB_MASTER;
+    hj.lmin = lmin; hj.lmax = lmax; hj.lenW = nV;
+    hj.nW = 4;
+    const double* Vs[4] = {V_TT, V_TP, V_PT, V_PP};
+    for (int k = 0; k < 4; ++k) { hj.vecs[k] = Vs[k]; hj.lens[k] = (size_t)nV; }
+    hj.nout = 5; hj.scale = 1;
+    int cur = 0, root = 0;
+    cudaGetDevice(&cur);
+    int rc = full_on_root(hj, ng, &root);
+    // columns: 0 TT, 1 TE, 2 ET, 3 TB, 4 BT, 5 EE, 6 BB, 7 EB, 8 BE   (src/modecoupling.jl:348-377)
+    auto col = [&](int a) { RhsCol c{}; c.in[0] = pCl + (size_t)a * ldp; c.out[0] = Cl + (size_t)a * ldc; return c; };
+    auto col2 = [&](int a, int b) { RhsCol c = col(a); c.in[1] = pCl + (size_t)b * ldp; c.out[1] = Cl + (size_t)b * ldc; return c; };
+    DeviceScratch& R = g_scratch[root];
+    // the 2N systems first: they read M++ / M-- , which the in-place LUs below do not touch
+    if (rc == OK) rc = solve_block_on_root(root, R.X[3], R.X[4], N, 1.0, {col2(5, 6)});
+    if (rc == OK) rc = solve_block_on_root(root, R.X[3], R.X[4], N, -1.0, {col2(7, 8)});
+    if (rc == OK) rc = solve_on_root(root, R.X[0], N, 1, {col(0)});
+    if (rc == OK) rc = solve_on_root(root, R.X[1], N, 1, {col(1), col(3)});     // TE and TB share mcm(:TE, maskT1, maskP2)
+    if (rc == OK) rc = solve_on_root(root, R.X[2], N, 1, {col(2), col(4)});     // ET and BT share mcm(:ET, maskP1, maskT2)
+    cudaSetDevice(cur);
+    return rc;
+}
+
+int psb200_decouple_covmat_dev(int n, double* dY, long ldy, const double* dB1, long ld1, const double* dB2, long ld2,
+                               void* stream)
+{
+    if (n < 1 || !dY || !dB1 || !dB2 || ldy < n || ld1 < n || ld2 < n) return fail(ERR_ARG, "decouple_covmat: bad arguments");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    return decouple_on_device(dev, (cudaStream_t)stream, n, dY, ldy, dB1, ld1, dB2, ld2);
+}
+
+int psb200_decouple_covmat(int n, const double* Y, long ldy, const double* B1, long ld1, const double* B2, long ld2,
+                           double* out, long ldo)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (n < 1 || !Y || !B1 || !B2 || !out || ldy < n || ld1 < n || ld2 < n || ldo < n)
+        return fail(ERR_ARG, "decouple_covmat: bad arguments");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    for (int o = 0; o < 3; ++o)
+        if (int rc = scratch_reserve(dev, o, (size_t)n * n)) return rc;
+    DeviceScratch& s = g_scratch[dev];
+    const size_t w = (size_t)n * sizeof(double);
+    CUDA_TRY(cudaMemcpy2DAsync(s.X[0], w, Y, (size_t)ldy * sizeof(double), w, n, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpy2DAsync(s.X[1], w, B1, (size_t)ld1 * sizeof(double), w, n, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpy2DAsync(s.X[2], w, B2, (size_t)ld2 * sizeof(double), w, n, cudaMemcpyHostToDevice, s.stream));
+    if (int rc = decouple_on_device(dev, s.stream, n, s.X[0], n, s.X[1], n, s.X[2], n)) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(double), s.X[0], w, w, n, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
     return OK;
 }
 

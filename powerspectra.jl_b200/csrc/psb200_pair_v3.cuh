@@ -60,7 +60,20 @@ __host__ __device__ constexpr bool v3_has_odd(int job) { return job == JOB_MMM |
 __host__ __device__ constexpr bool v3_spin2(int job) { return job_family(job) != FAM_00; }
 __host__ __device__ constexpr int v3_ntab(int job) { return (v3_has_even(job) ? 1 : 0) + (v3_has_odd(job) ? 1 : 0); }
 __host__ __device__ constexpr int v3_span(int job) { return (32 / v3_nr(job)) * v3_r(job); }   // pairs per row per warp
-__host__ __device__ constexpr int v3_nqp(int job) { return (job_nw(job) + 1) & ~1; }            // W' columns (even)
+// x column(s): the spin-2 jobs read x = j(j+1) of the step (and x+1 for the odd-parity term) from the staged W' row --
+// a broadcast shared-memory load -- instead of advancing it with two or three warp-uniform FP64 adds per step
+// (the FP64 pipe is the bound; the shared-memory path has headroom).
+#ifndef PSB200_V3_XCOL
+#define PSB200_V3_XCOL 1
+#endif
+__host__ __device__ constexpr bool v3_xcol(int job) { return PSB200_V3_XCOL && v3_spin2(job); }
+__host__ __device__ constexpr int v3_xc_even(int job) { return job_nw(job); }                                   // column of x
+__host__ __device__ constexpr int v3_xc_odd(int job) { return job_nw(job) + (v3_has_even(job) ? 1 : 0); }       // column of x+1
+__host__ __device__ constexpr int v3_nqp(int job)                                                                // W' columns (even)
+{
+    const int nx = v3_xcol(job) ? (v3_has_even(job) ? 1 : 0) + (v3_has_odd(job) ? 1 : 0) : 0;
+    return (job_nw(job) + nx + 1) & ~1;
+}
 __host__ __device__ constexpr int v3_tc(int job)                                                 // steps per staged chunk
 {
 #ifdef PSB200_V3_TC
@@ -94,6 +107,29 @@ struct V3Tables {
     const double* Wp;     // [row j][v3_nqp columns] = (2j+1) W_q[j] / 4pi, zero rows past lenW
 };
 
+// W'[j][q] for one call: (2j+1) W_q[j] / 4pi in columns q < NW (zero past lenW), then x_j = j(j+1) and x_j + 1 where
+// the job reads them (v3_xcol), zero padding to the even column count.
+template <int JOB>
+__global__ void v3_prep_w(double* __restrict__ Wp, int rows, int lenW,
+                          const double* w0, const double* w1, const double* w2, const double* w3,
+                          const double* w4, const double* w5, const double* w6, const double* w7)
+{
+    constexpr int NW = job_nw(JOB), NQP = v3_nqp(JOB);
+    const double* W[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rows) return;
+    const double k = (double)(2 * j + 1) * INV_4PI;
+    const double x = (double)j * (double)(j + 1);
+#pragma unroll
+    for (int q = 0; q < NQP; ++q) {
+        double v = 0.0;
+        if (q < NW) v = (j < lenW) ? k * W[q][j] : 0.0;
+        else if (v3_xcol(JOB) && v3_has_even(JOB) && q == v3_xc_even(JOB)) v = x;
+        else if (v3_xcol(JOB) && v3_has_odd(JOB) && q == v3_xc_odd(JOB)) v = x + 1.0;
+        Wp[(size_t)j * NQP + q] = v;
+    }
+}
+
 // Resident warps per SM the register allocation must allow (one warp per block), from an estimate of the live
 // doubles per thread: accumulators, rotating windows, spin-2 constants, the step's window values.
 __host__ __device__ constexpr int v3_reg_estimate(int job)
@@ -120,6 +156,8 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v3(const P
     constexpr int NTAB = v3_ntab(JOB);                 // 1: one parity; 2: (even, odd) entries side by side
     constexpr int RPS = NTAB;                          // W' rows per step
     constexpr int TC = v3_tc(JOB), SZT = v3_szt(JOB), SUB = v3_sub(JOB), TSTR = v3_tstride(JOB);
+    constexpr bool XCOL = v3_xcol(JOB);
+    constexpr int XE = v3_xc_even(JOB), XO = v3_xc_odd(JOB);
 
     extern __shared__ __align__(16) double smem[];
     double* shU = smem;                                // falling index: PT | QT | (PT, QT), one table per row
@@ -269,33 +307,38 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v3(const P
             }
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                // window spectra of this step: warp-uniform broadcast reads
+                // window spectra (and x columns) of this step: warp-uniform broadcast reads
                 double w[NQP], wo[NQP];
                 {
                     const double* wr = shW + (size_t)(tg + s) * (RPS * NQP);
-                    if constexpr (NWQ == 1 && RPS == 1) {
+                    if constexpr (NQP == 2 && NWQ == 1 && !XCOL && RPS == 1) {
                         w[0] = wr[0];
-                    } else if constexpr (NWQ == 1) {
-                        const double2 v = *reinterpret_cast<const double2*>(wr);
-                        const double2 v2 = *reinterpret_cast<const double2*>(wr + NQP);
-                        w[0] = v.x; wo[0] = v2.x;
                     } else {
 #pragma unroll
                         for (int q = 0; q < NQP; q += 2) {
                             const double2 v = *reinterpret_cast<const double2*>(wr + q);
                             w[q] = v.x; w[q + 1] = v.y;
                         }
-                        if constexpr (JOB == JOB_MASTER) {
-                            const double2 v = *reinterpret_cast<const double2*>(wr + NQP + 2);
-                            wo[3] = v.y;
+                    }
+                    if constexpr (RPS == 2) {
+                        // odd-parity row: its window value (the last W) and x+1
+                        constexpr int QW = NWQ - 1;
+#pragma unroll
+                        for (int q = (QW & ~1); q < NQP; q += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(wr + NQP + q);
+                            wo[q] = v.x; wo[q + 1] = v.y;
                         }
                     }
                 }
+                if constexpr (XCOL && EV) xj = w[XE];
+                double xo1 = 0.0;                                   // x_{j+1} + 1 of the odd-parity term
+                if constexpr (XCOL && OD) xo1 = (RPS == 2) ? wo[XO] : w[XO];
+                (void)xo1;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int kU = s - r + R - 1, kV = r + s;
                     double u = 0.0;
-                    if constexpr (S2) u = xj - se[r];
+                    if constexpr (S2 && (EV || !XCOL)) u = xj - se[r];
                     if constexpr (EV) {
                         const double g = wU0[kU] * wV0[kV];                 // f00(j)^2
                         if constexpr (!S2) {
@@ -330,15 +373,14 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v3(const P
                     }
                     if constexpr (OD) {
                         // odd-parity term j+1: 4 D^2 f22^2 = (x' - a - b + 2)^2 QT QV,  x' - a - b + 2 = u + 2j + 3
-                        const double uo = u + k2;
+                        const double uo = XCOL ? xo1 - se[r] : u + k2;       // (x' + 1) - (a + b - 1)
                         const double h = (NTAB > 1 ? wU1[kU] * wV1[kV] : wU0[kU] * wV0[kV]) * uo;
                         if constexpr (JOB == JOB_MMM) acc[r][0] = fma(h * uo, w[0], acc[r][0]);
-                        else if constexpr (JOB == JOB_MPPMMM) acc[r][1] = fma(h * uo, wo[0], acc[r][1]);
-                        else acc[r][4] = fma(h * uo, wo[3], acc[r][4]);     // MASTER
+                        else acc[r][NACC - 1] = fma(h * uo, wo[NWQ - 1], acc[r][NACC - 1]);   // MPPMMM (W0), MASTER (W3)
                     }
                 }
-                if constexpr (S2) { xj += xinc; xinc += 8.0; }
-                if constexpr (OD) k2 += 4.0;
+                if constexpr (S2 && !XCOL) { xj += xinc; xinc += 8.0; }
+                if constexpr (OD && !XCOL) k2 += 4.0;
             }
             // ---- rotate: next group's carried entries ----
 #pragma unroll

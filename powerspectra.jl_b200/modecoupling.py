@@ -137,6 +137,60 @@ def maskedalm2spectra(maskedmap1, maskT1, maskP1, maskedmap2, maskT2, maskP2, *,
     return spectra
 
 
+def maskedalm2spectra_device(maskedmap1, maskT1, maskP1, maskedmap2, maskT2, maskP2, *, lmin=0, ngpus=1):
+    """maskedalm2spectra (src/modecoupling.jl:339-377) with the decoupling on the device: one fused pass builds the five
+    mode-coupling matrices on `ngpus` GPUs, they are assembled and LU-solved on one of them (psb200_master_solve) and
+    only the nine decoupled spectra come back -- no matrix crosses PCIe.  alm2cl of the maps stays on the host."""
+    lmax = min(a.lmax for a in (maskT1, maskP1, maskT2, maskP2))
+    V = [np.ascontiguousarray(alm2cl(a, b)[: lmax + 1]) for a, b in
+         ((maskT1, maskT2), (maskT1, maskP2), (maskP1, maskT2), (maskP1, maskP2))]
+    a1 = dict(zip("TEB", maskedmap1))
+    a2 = dict(zip("TEB", maskedmap2))
+    names = ("TT", "TE", "ET", "TB", "BT", "EE", "BB", "EB", "BE")
+    N = lmax - lmin + 1
+    pcl = np.asfortranarray(np.stack([alm2cl(a1[x], a2[y])[lmin: lmax + 1] for x, y in names], axis=1))
+    cl = np.zeros_like(pcl, order="F")
+    rc = _lib.lib().psb200_master_solve(lmin, lmax, _dp(V[0]), _dp(V[1]), _dp(V[2]), _dp(V[3]), lmax + 1,
+                                        _dp(pcl), N, _dp(cl), N, ngpus)
+    _lib.check(rc)
+    return {n: SpectralVector(np.ascontiguousarray(cl[:, k]), lmin) for k, n in enumerate(names)}
+
+
+_SYSTEMS = {"TT": 0, "M00": 0, "TE": 1, "ET": 1, "TB": 1, "BT": 1, "M02": 1, "M20": 1, "M++": 2, "M--": 3,
+            "EE_BB": 4, "EB_BE": 5}
+
+
+def mcm_solve(spec, alm1, alm2, pcl, *, lmin=0, lmax=None, ngpus=1):
+    """`mcm(spec, alm1, alm2; lmin) \\ pCl` (src/modecoupling.jl:359-379, src/blockspectralmatrix.jl:89-129) without
+    bringing the matrix to the host (psb200_mcm_solve).  pcl: a SpectralVector / array over lmin:lmax, a list of two for
+    the block systems "EE_BB" / "EB_BE" (stacked like `[pCl_EE; pCl_BB]`), or a 2-d array of several right-hand sides
+    as columns.  Returns SpectralVector(s) over lmin:lmax (a 2-d SpectralArray for several right-hand sides)."""
+    if spec not in _SYSTEMS:
+        raise ValueError(f"{spec} not a valid spectrum.")
+    system = _SYSTEMS[spec]
+    V, lmax = _mask_spectrum(alm1, alm2, lmax)
+    N = lmax - lmin + 1
+    nb = 2 if system >= 4 else 1
+    get = lambda v: v.parent if isinstance(v, SpectralArray) else np.asarray(v, dtype=np.float64)
+    if nb == 2 and isinstance(pcl, (list, tuple)):
+        rhs = np.concatenate([get(v) for v in pcl])
+    else:
+        rhs = get(pcl)
+    many = rhs.ndim == 2
+    rhs = np.asfortranarray(rhs.reshape(rhs.shape[0], -1))
+    if rhs.shape[0] != nb * N:
+        raise ValueError(f"right-hand side has {rhs.shape[0]} rows, the system has {nb * N}")
+    out = np.zeros_like(rhs, order="F")
+    rc = _lib.lib().psb200_mcm_solve(system, lmin, lmax, _dp(V.parent), V.parent.size, _dp(rhs), nb * N, rhs.shape[1],
+                                     _dp(out), nb * N, ngpus)
+    _lib.check(rc)
+    if many:
+        return SpectralArray(out, (lmin, 0))
+    if nb == 2:
+        return SpectralVector(out[:N, 0].copy(), lmin), SpectralVector(out[N:, 0].copy(), lmin)
+    return SpectralVector(out[:, 0].copy(), lmin)
+
+
 def _mask_spectrum(alm1, alm2, lmax):
     if isinstance(alm1, SpectralArray) and alm2 is None:      # already a cross-spectrum V
         if lmax is None:

@@ -175,7 +175,22 @@ class BlockSpectralMatrix:
 
 
 def decouple_covmat(Y: SpectralArray, B1: SpectralArray, B2: SpectralArray) -> SpectralArray:
-    """B1^-1 Y (B2^-1)^T on the host (src/covariance.jl:8-14)."""
+    """B1^-1 Y (B2^-1)^T on the host (src/covariance.jl:8-14), as the reference does it (LAPACK)."""
     C = np.linalg.solve(B1.parent, Y.parent)
     C = np.linalg.solve(B2.parent, C.T).T
     return SpectralArray(C, Y.offsets)
+
+
+def decouple_covmat_device(Y: SpectralArray, B1: SpectralArray, B2: SpectralArray) -> SpectralArray:
+    """The same on the GPU: both LU factorisations (of B1', B2' like the reference) and the two
+    n-right-hand-side solves run in libpsb200 (psb200_decouple_covmat: cuSOLVER getrf/getrs on the current device)."""
+    from . import _lib
+    n = Y.parent.shape[0]
+    if Y.parent.shape != (n, n) or B1.parent.shape != (n, n) or B2.parent.shape != (n, n):
+        raise ValueError("decouple_covmat needs three square matrices of one size")
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    y, b1, b2 = f(Y.parent), f(B1.parent), f(B2.parent)
+    out = np.zeros((n, n), order="F")
+    dp = lambda a: a.ctypes.data_as(_lib.DP)
+    _lib.check(_lib.lib().psb200_decouple_covmat(n, dp(y), n, dp(b1), n, dp(b2), n, dp(out), n))
+    return SpectralArray(out, Y.offsets)
