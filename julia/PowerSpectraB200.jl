@@ -20,6 +20,7 @@
 module PowerSpectraB200
 
 using PowerSpectra
+using LinearAlgebra
 import PowerSpectra: SpectralArray, SpectralVector
 
 const LIB = Ref{String}("libpsb200.so")
@@ -39,7 +40,9 @@ end
 function check(rc::Cint)
     rc == 0 && return
     msg = unsafe_string(ccall((:psb200_last_error, LIB[]), Cstring, ()))
-    rc == 1 ? throw(ArgumentError(msg)) : error("libpsb200 error $rc: $msg")
+    rc == 1 && throw(ArgumentError(msg))
+    rc == 6 && throw(LinearAlgebra.SingularException(0))      # exactly singular system in a device-side solve
+    error("libpsb200 error $rc: $msg")
 end
 
 function mcm_call!(kind::Int, 𝐌::SpectralArray{Float64,2}, V::SpectralVector{Float64};
@@ -193,6 +196,83 @@ function mcm_master(maskT₁, maskP₁, maskT₂, maskP₂; lmin = 0, lmax = not
     end
     check(rc)
     return Tuple(out)
+end
+
+"""
+    mcm_solve(spec, alm₁, alm₂, pCl; lmin = 0, lmax = nothing)
+
+Optional extra entry point: `mcm(spec, alm₁, alm₂; lmin) \\ pCl` (src/modecoupling.jl:359-362,
+src/blockspectralmatrix.jl:124-129) with the LU solve on the GPU that holds the matrix -- only the spectrum
+crosses PCIe.  `spec` ∈ (:TT, :TE, :ET, :TB, :BT, :M⁺⁺); for the block systems pass `:EE_BB` / `:EB_BE` and
+`pCl = (pCl_1, pCl_2)` (stacked like `[pCl_EE; pCl_BB]`, src/modecoupling.jl:365-379); returns a SpectralVector
+(a tuple of two for the block systems).
+"""
+function mcm_solve(spec::Symbol, alm₁, alm₂, pCl; lmin = 0, lmax = nothing)
+    lmax = isnothing(lmax) ? min(alm₁.lmax, alm₂.lmax) : lmax
+    sys = spec in (:TT, :M⁰⁰) ? 0 : spec in (:TE, :ET, :TB, :BT, :M⁰², :M²⁰) ? 1 : spec == :M⁺⁺ ? 2 :
+          spec == :M⁻⁻ ? 3 : spec == :EE_BB ? 4 : spec == :EB_BE ? 5 : throw(ArgumentError("$(spec) not a valid spectrum."))
+    v = collect(PowerSpectra.alm2cl(alm₁, alm₂)[1:(lmax + 1)])
+    N = lmax - lmin + 1
+    rhs = sys >= 4 ? vcat((Float64[p[l] for l in lmin:lmax] for p in pCl)...) : Float64[pCl[l] for l in lmin:lmax]
+    out = similar(rhs)
+    GC.@preserve v rhs out begin
+        rc = ccall((:psb200_mcm_solve, LIB[]), Cint,
+                   (Cint, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Clong, Cint, Ptr{Cdouble}, Clong, Cint),
+                   sys, lmin, lmax, v, length(v), rhs, length(rhs), 1, out, length(out), NGPUS[])
+    end
+    check(rc)
+    wrap(x) = SpectralVector(x, lmin:lmax)      # same axes as `M \ pCl` returns (B.parent.offsets)
+    return sys >= 4 ? (wrap(out[1:N]), wrap(out[(N + 1):end])) : wrap(out)
+end
+
+"""
+    maskedalm2spectra_device(maskedmap₁vec, maskT₁, maskP₁, maskedmap₂vec, maskT₂, maskP₂; lmin = 0)
+
+`maskedalm2spectra` (src/modecoupling.jl:341-377) with the five mode-coupling matrices built in one fused GPU pass and
+ALL its solves done on the device (psb200_master_solve): returns the same Dict of nine decoupled spectra; no matrix is
+ever copied to the host.
+"""
+function maskedalm2spectra_device(m₁::Vector, maskT₁, maskP₁, m₂::Vector, maskT₂, maskP₂; lmin = 0)
+    lmax = minimum(a.lmax for a in (maskT₁, maskP₁, maskT₂, maskP₂))
+    V = [collect(PowerSpectra.alm2cl(a, b)[1:(lmax + 1)]) for (a, b) in
+         ((maskT₁, maskT₂), (maskT₁, maskP₂), (maskP₁, maskT₂), (maskP₁, maskP₂))]
+    names = (:TT, :TE, :ET, :TB, :BT, :EE, :BB, :EB, :BE)
+    idx = Dict('T' => 1, 'E' => 2, 'B' => 3)
+    N = lmax - lmin + 1
+    pcl = Matrix{Float64}(undef, N, 9)
+    for (k, n) in enumerate(names)
+        x, y = String(n)
+        pcl[:, k] = PowerSpectra.alm2cl(m₁[idx[x]], m₂[idx[y]])[(lmin + 1):(lmax + 1)]
+    end
+    cl = similar(pcl)
+    GC.@preserve V pcl cl begin
+        rc = ccall((:psb200_master_solve, LIB[]), Cint,
+                   (Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint,
+                    Ptr{Cdouble}, Clong, Ptr{Cdouble}, Clong, Cint),
+                   lmin, lmax, V[1], V[2], V[3], V[4], lmax + 1, pcl, N, cl, N, NGPUS[])
+    end
+    check(rc)
+    return Dict{Symbol,SpectralVector}(n => SpectralVector(cl[:, k], lmin:lmax) for (k, n) in enumerate(names))
+end
+
+"""
+    decouple_covmat_device(Y, B1, B2)
+
+`decouple_covmat` (src/covariance.jl:8-14) on the GPU: lu(B1'), lu(B2') and both n-right-hand-side solves in
+libpsb200 (cuSOLVER getrf/getrs).
+"""
+function decouple_covmat_device(Y::SpectralArray{Float64,2}, B1::SpectralArray{Float64,2}, B2::SpectralArray{Float64,2})
+    M = deepcopy(Y)
+    C, P1, P2 = parent(M), parent(B1), parent(B2)
+    n = size(C, 1)
+    (size(C) == size(P1) == size(P2) == (n, n)) || throw(ArgumentError("decouple_covmat needs three square matrices of one size"))
+    GC.@preserve C P1 P2 begin
+        rc = ccall((:psb200_decouple_covmat, LIB[]), Cint,
+                   (Cint, Ptr{Cdouble}, Clong, Ptr{Cdouble}, Clong, Ptr{Cdouble}, Clong, Ptr{Cdouble}, Clong),
+                   n, C, stride(C, 2), P1, stride(P1, 2), P2, stride(P2, 2), C, stride(C, 2))
+    end
+    check(rc)
+    return M
 end
 
 end # module

@@ -8,6 +8,7 @@
 #include "psb200_pair_v1.cuh"
 #include "psb200_pair_v2.cuh"
 #include "psb200_pair_v3.cuh"
+#include "psb200_pair_v4.cuh"
 #include "psb200_lowrows.cuh"
 #include "psb200_quickpol.cuh"
 
@@ -151,12 +152,14 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 int kernel_version()
 {
     // read on every call so a test can switch kernels inside one process
-    // v1: simple kernel (sqrt/divide recurrence, sum normalisation); v2: tuned recurrence kernel; default v3:
-    // closed-form kernel.  v1 and v2 are on-device cross-checks of v3 by independent methods, not fallbacks.
+    // v1: simple kernel (sqrt/divide recurrence, sum normalisation); v2: tuned recurrence kernel; v3: closed-form
+    // kernel with per-chunk table staging; default v4: closed-form kernel with asynchronous ring staging.  v1 and v2
+    // are on-device cross-checks of the closed forms by independent methods, v3 the A/B partner of v4; none is a fallback.
     const char* e = getenv("PSB200_KERNEL");
     if (e && strcmp(e, "v1") == 0) return 1;
     if (e && strcmp(e, "v2") == 0) return 2;
-    return 3;
+    if (e && strcmp(e, "v3") == 0) return 3;
+    return 4;
 }
 
 // PSB200_TRACE=1: per-phase wall-clock of the host-level calls on stderr (adds stream syncs)
@@ -187,6 +190,7 @@ struct DevTables {
     int lmax = -1;
     int nS = 0;
     double *S = nullptr, *IS = nullptr, *INV = nullptr, *gam = nullptr, *igam = nullptr;
+    double* seq[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // v4: G0 G1 G2 H0 H1, each nS + V4_PAD doubles
 };
 DevTables g_tables[16];
 std::mutex g_tab_mutex;
@@ -213,9 +217,21 @@ int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
         G[n] = (double)g;
         IG[n] = (double)(1.0L / g);
     }
+    // v4 sequences (psb200_pair_v4.cuh), V4_PAD zeros in front: g, (2n+1) g, 2n g, 1/((2n+1) g), (2n+2)/((2n+1) g)
+    std::vector<double> Q[5];
+    for (auto& q : Q) q.assign((size_t)nS + psb::V4_PAD, 0.0);
+    g = 1.0L;
+    for (int n = 0; n < nS; ++n) {
+        if (n) g *= (long double)(2 * n - 1) / (long double)(2 * n);
+        const size_t i = (size_t)n + psb::V4_PAD;
+        const long double h0 = 1.0L / ((long double)(2 * n + 1) * g);
+        Q[0][i] = (double)g; Q[1][i] = (double)((long double)(2 * n + 1) * g); Q[2][i] = (double)((long double)(2 * n) * g);
+        Q[3][i] = (double)h0; Q[4][i] = (double)((long double)(2 * n + 2) * h0);
+    }
     if (t.S) {                                   // growing: nothing may still be reading the old tables
         CUDA_TRY(cudaDeviceSynchronize());
         cudaFree(t.S); cudaFree(t.IS); cudaFree(t.INV); cudaFree(t.gam); cudaFree(t.igam);
+        for (double* q : t.seq) cudaFree(q);
         t = DevTables{};
     }
     CUDA_TRY(cudaMalloc(&t.S, nS * sizeof(double)));
@@ -231,6 +247,10 @@ int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
     CUDA_TRY(cudaMemcpyAsync(t.INV, INV.data(), nS * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(t.gam, G.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(t.igam, IG.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 5; ++k) {
+        CUDA_TRY(cudaMalloc(&t.seq[k], Q[k].size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(t.seq[k], Q[k].data(), Q[k].size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     t.lmax = want; t.nS = nS;
     *out = &t;
@@ -360,7 +380,8 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
     tr.mark("  (inputs uploaded)", dev, st);
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, st, &t)) return rc;
-    const bool v3 = kernel_version() == 3;
+    const int kv = kernel_version();
+    const bool v3 = kv >= 3;                    // v3 and v4 share tiling, W' layout and work accounting
     BlockList bl;
     if (v3) {
         if (int rc = ensure_blocks(dev, A, 2, psb::v3_r(JOB), psb::v3_nr(JOB), st, &bl)) return rc;
@@ -382,7 +403,13 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
     CUDA_TRY(cudaGetLastError());
     tr.mark("  prep W' kernel", dev, st);
     int e = 0;
-    if (v3) {
+    if (kv == 4) {
+        psb::V4Tables T{};
+        T.G0 = t->seq[0] + psb::V4_PAD; T.G1 = t->seq[1] + psb::V4_PAD; T.G2 = t->seq[2] + psb::V4_PAD;
+        T.H0 = t->seq[3] + psb::V4_PAD; T.H1 = t->seq[4] + psb::V4_PAD; T.nS = t->nS;
+        T.blocks = bl.d; T.Wp = Wp;
+        e = psb::launch_pair_v4<JOB>(A, T, bl.n, st);
+    } else if (v3) {
         psb::V3Tables T{};
         T.gam = t->gam; T.igam = t->igam; T.INV = t->INV; T.nS = t->nS;
         T.blocks = bl.d; T.Wp = Wp;
@@ -566,19 +593,18 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
     return launch_any(hj.job, A, s.stream);
 }
 
-// Cost of row l1 as the tuned kernel executes it.  Most jobs run the two-step f00^2 recurrence: one warp per
-// NR rows x SPAN pairs of one parity of d (SPAN = (32/NR) R), stepping l3 by 2 from its first d to
-// min(d + 2 l1, lenW-1), plus the start skew of the warp and a fixed per-block overhead (start values, first
-// table staging, epilogue).  Skew and overhead weights come from a least-squares fit over the per-rank
-// pair-kernel times of the round-1 2-, 4- and 8-GPU runs (NR = 1, SPAN = 192: only SKEW + OVH ~ 200 steps was
-// constrained, RMS residual 0.12 ms per rank); the skew term scales with SPAN, the overhead does not.
+// Cost of row l1 as the default kernel executes it: one warp per NR rows x SPAN pairs of one parity of d
+// (SPAN = (32/NR) R), stepping l3 by 2 from its first d to min(d + 2 l1, lenW-1) in lockstep -- SPAN-1 + l1 + 1 steps,
+// cut at the window length -- plus a fixed per-block overhead (ring prologue: five staging passes with exposed
+// latency, epilogue), expressed in steps.  The tiling of the 8-accumulator covariance jobs is used for every job (they
+// dominate a step).
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
     constexpr long NRH = psb::v3_nr(psb::JOB_TTTT);
     constexpr long SPAN = psb::v3_span(psb::JOB_TTTT);           // the covariance jobs dominate a step
-    constexpr long SKEW = (130 * SPAN) / 192, OVH = 70;
+    constexpr long SKEW = SPAN - 1, OVH = 30;
     long double c = 0;
     for (long base = 0; base <= D; base += 2 * SPAN) {
         for (long par = 0; par < 2; ++par) {

@@ -52,8 +52,27 @@ __host__ __device__ constexpr int v3_r(int job)
     if (job == JOB_MPPMMM || job == JOB_MASTER) return PSB200_V3_R_BOTH;
     return job_nacc(job) <= 2 ? PSB200_V3_R_LIGHT : (job_nacc(job) <= 5 ? PSB200_V3_R_MID : PSB200_V3_R_HEAVY);
 }
-__host__ __device__ constexpr int v3_nr(int job) { (void)job; return PSB200_V3_NR; }
-static_assert(PSB200_V3_NR == 1 || PSB200_V3_NR == 2 || PSB200_V3_NR == 4, "rows per warp: 1, 2 or 4");
+// rows per warp, by job class like R (defaults: PSB200_V3_NR everywhere)
+#ifndef PSB200_V3_NR_LIGHT
+#define PSB200_V3_NR_LIGHT PSB200_V3_NR
+#endif
+#ifndef PSB200_V3_NR_MID
+#define PSB200_V3_NR_MID PSB200_V3_NR
+#endif
+#ifndef PSB200_V3_NR_HEAVY
+#define PSB200_V3_NR_HEAVY PSB200_V3_NR
+#endif
+#ifndef PSB200_V3_NR_BOTH
+#define PSB200_V3_NR_BOTH PSB200_V3_NR
+#endif
+__host__ __device__ constexpr int v3_nr(int job)
+{
+    if (job == JOB_MPPMMM || job == JOB_MASTER) return PSB200_V3_NR_BOTH;
+    return job_nacc(job) <= 2 ? PSB200_V3_NR_LIGHT : (job_nacc(job) <= 5 ? PSB200_V3_NR_MID : PSB200_V3_NR_HEAVY);
+}
+__host__ __device__ constexpr bool v3_nr_ok(int n) { return n == 1 || n == 2 || n == 4 || n == 8; }
+static_assert(v3_nr_ok(PSB200_V3_NR_LIGHT) && v3_nr_ok(PSB200_V3_NR_MID) && v3_nr_ok(PSB200_V3_NR_HEAVY) && v3_nr_ok(PSB200_V3_NR_BOTH),
+              "rows per warp: 1, 2, 4 or 8");
 
 __host__ __device__ constexpr bool v3_has_even(int job) { return job != JOB_MMM; }
 __host__ __device__ constexpr bool v3_has_odd(int job) { return job == JOB_MMM || job == JOB_MPPMMM || job == JOB_MASTER; }

@@ -197,9 +197,12 @@ int full_on_root(const HostJob& hj, int ngpus, int* root_out)
         if (int rc = run_on_device(hj, g, a, b, Xs, N)) return rc;             // also creates g's streams
         DeviceScratch& s = g_scratch[g];
         if (!direct)
-            for (int o = 0; o < hj.nout; ++o)
-                CUDA_TRY(cudaMemcpyPeerAsync(R.X[o] + (size_t)(a - hj.lmin) * N, root, s.X[o], g,
-                                             (size_t)(b - a) * N * sizeof(double), s.stream));
+            for (int o = 0; o < hj.nout; ++o) {
+                const cudaError_t ce = cudaMemcpyPeerAsync(R.X[o] + (size_t)(a - hj.lmin) * N, root, s.X[o], g,
+                                                           (size_t)(b - a) * N * sizeof(double), s.stream);
+                if (ce != cudaSuccess)
+                    return fail(ERR_COLL, "band of device %d could not be moved to device %d: %s", g, root, cudaGetErrorString(ce));
+            }
         CUDA_TRY(cudaStreamSynchronize(s.stream));
         return OK;
     };
