@@ -187,6 +187,17 @@ int psb200_decouple_covmat(int n, const double* Y, long ldy, const double* B1, l
 int psb200_decouple_covmat_dev(int n, double* dY, long ldy, const double* dB1, long ldb1, const double* dB2, long ldb2,
                                void* stream);
 
+/* ---- W-spectrum production, first slice -------------------------------------------------
+ * The window spectra W of the covariance come from map2alm of mask products (effective_weight_alm!,
+ * src/workspace.jl:141-171) and alm2cl of pairs of them (window_function_W!, :174-213).  The general HEALPix transform
+ * stays on the host; for AZIMUTHALLY SYMMETRIC maps only m = 0 survives and map2alm is the Legendre quadrature
+ *     alm[i][l] = sqrt(pi (2l+1)) sum_k w[k] fields[i][k] P_l(x[k]),   l = 0..lmax
+ * over Gauss-Legendre nodes x (cos theta) and weights w, evaluated here for a batch of fields (rows of `fields`, leading
+ * dimension ldf >= nnodes; rows of `alm`, leading dimension lda >= lmax+1) on the current device.  alm2cl of two zonal
+ * maps is a_l0 b_l0 / (2l+1). */
+int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, const double* fields, long ldf,
+                     int lmax, double* alm, long lda);
+
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);
 

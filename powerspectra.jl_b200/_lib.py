@@ -45,6 +45,7 @@ PROTOTYPES = {
     "psb200_decouple_covmat": (C.c_int, [C.c_int, DP, C.c_long, DP, C.c_long, DP, C.c_long, DP, C.c_long]),
     "psb200_decouple_covmat_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long,
                                              C.c_void_p]),
+    "psb200_zonal_alm": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, C.c_long, C.c_int, DP, C.c_long]),
     "psb200_quickpol_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
 }
 

@@ -11,6 +11,7 @@
 #include "psb200_pair_v4.cuh"
 #include "psb200_lowrows.cuh"
 #include "psb200_quickpol.cuh"
+#include "psb200_zonal.cuh"
 
 #include <cusolverDn.h>      // types + prototypes only: the library is loaded with dlopen (psb200_solve.inl)
 #include <dlfcn.h>
@@ -1195,6 +1196,44 @@ int psb200_decouple_covmat(int n, const double* Y, long ldy, const double* B1, l
     if (int rc = decouple_on_device(dev, s.stream, n, s.X[0], n, s.X[1], n, s.X[2], n)) return rc;
     CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(double), s.X[0], w, w, n, cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return OK;
+}
+
+
+// ---- W-spectrum production, first slice: zonal map2alm (psb200_zonal.cuh) -----------------------
+int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, const double* fields, long ldf,
+                     int lmax, double* alm, long lda)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (nfields < 1 || nnodes < 1 || lmax < 0 || !x || !w || !fields || !alm || ldf < nnodes || lda < (long)lmax + 1)
+        return fail(ERR_ARG, "zonal_alm: bad arguments");
+    if (lmax > 65535) return fail(ERR_ARG, "zonal_alm: lmax %d above the supported 65535", lmax);
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    const int nblocks = (nnodes + psb::ZN_THREADS - 1) / psb::ZN_THREADS;
+    const size_t L = (size_t)lmax + 1;
+    for (int f0 = 0; f0 < nfields; f0 += psb::ZN_FMAX) {
+        const int nf = std::min(psb::ZN_FMAX, nfields - f0);
+        // scratch: [x | w | fields nf x n | alm nf x L] in slot 0, partial sums in slot 1
+        const size_t nin = 2 * (size_t)nnodes + (size_t)nf * nnodes + (size_t)nf * L;
+        if (int rc = scratch_reserve(dev, 0, nin)) return rc;
+        if (int rc = scratch_reserve(dev, 1, (size_t)nblocks * nf * L)) return rc;
+        DeviceScratch& s = g_scratch[dev];
+        double *dx = s.X[0], *dw = dx + nnodes, *df = dw + nnodes, *da = df + (size_t)nf * nnodes;
+        CUDA_TRY(cudaMemcpyAsync(dx, x, nnodes * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(dw, w, nnodes * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpy2DAsync(df, nnodes * sizeof(double), fields + (size_t)f0 * ldf, ldf * sizeof(double),
+                                   nnodes * sizeof(double), nf, cudaMemcpyHostToDevice, s.stream));
+        psb::zonal_partial_kernel<<<nblocks, psb::ZN_THREADS, 0, s.stream>>>(dx, dw, df, nnodes, nf, nnodes, lmax, s.X[1]);
+        CUDA_TRY(cudaGetLastError());
+        psb::zonal_finish_kernel<<<dim3((unsigned)((L + 127) / 128), nf), 128, 0, s.stream>>>(s.X[1], nblocks, nf, lmax, da, (long)L);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy2DAsync(alm + (size_t)f0 * lda, lda * sizeof(double), da, L * sizeof(double), L * sizeof(double), nf,
+                                   cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+    }
     return OK;
 }
 

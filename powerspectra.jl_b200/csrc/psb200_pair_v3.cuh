@@ -32,13 +32,13 @@
 namespace psb {
 
 #ifndef PSB200_V3_R_LIGHT
-#define PSB200_V3_R_LIGHT 8        // <= 2 accumulators per pair
+#define PSB200_V3_R_LIGHT 12       // <= 2 accumulators per pair (the shared-memory path is their co-limiter: fewer bytes per pair-step)
 #endif
 #ifndef PSB200_V3_R_MID
-#define PSB200_V3_R_MID 6          // 4-5 accumulators
+#define PSB200_V3_R_MID 8          // 4-5 accumulators
 #endif
 #ifndef PSB200_V3_R_HEAVY
-#define PSB200_V3_R_HEAVY 6        // 8 accumulators
+#define PSB200_V3_R_HEAVY 8        // 8 accumulators
 #endif
 #ifndef PSB200_V3_R_BOTH
 #define PSB200_V3_R_BOTH 6         // even + odd parity (fused M++/M--, MASTER)
@@ -53,17 +53,20 @@ __host__ __device__ constexpr int v3_r(int job)
     return job_nacc(job) <= 2 ? PSB200_V3_R_LIGHT : (job_nacc(job) <= 5 ? PSB200_V3_R_MID : PSB200_V3_R_HEAVY);
 }
 // rows per warp, by job class like R (defaults: PSB200_V3_NR everywhere)
+// MEASURED with the ring-staged kernel (B200, lmax 6143, ms per bench step; profiles/r02_v4_variants_probe_*.jsonl):
+// NR 1 / 2 / 4 / 8 everywhere 99.4 / 93.7 / 91.6 / 104.2; NR 4 with R 8 for the covariance jobs 90.3; the light jobs
+// (TT: 5.0 vs 5.3 ms) prefer NR 2 at R 8, and NR 4 at R 12 (4.7 ms).
 #ifndef PSB200_V3_NR_LIGHT
-#define PSB200_V3_NR_LIGHT PSB200_V3_NR
+#define PSB200_V3_NR_LIGHT (2 * PSB200_V3_NR)
 #endif
 #ifndef PSB200_V3_NR_MID
-#define PSB200_V3_NR_MID PSB200_V3_NR
+#define PSB200_V3_NR_MID (2 * PSB200_V3_NR)
 #endif
 #ifndef PSB200_V3_NR_HEAVY
-#define PSB200_V3_NR_HEAVY PSB200_V3_NR
+#define PSB200_V3_NR_HEAVY (2 * PSB200_V3_NR)
 #endif
 #ifndef PSB200_V3_NR_BOTH
-#define PSB200_V3_NR_BOTH PSB200_V3_NR
+#define PSB200_V3_NR_BOTH (2 * PSB200_V3_NR)
 #endif
 __host__ __device__ constexpr int v3_nr(int job)
 {

@@ -24,6 +24,16 @@ namespace psb {
 
 constexpr int V4_PAD = 1024;          // zero entries in front of every global sequence (indices down to -V4_PAD are valid)
 
+// PSB200_V4_EMBED = 1: the products of pass c+1 are computed INSIDE the groups of sub-chunk c (one row of the warp per
+// group), from raw factors issued a whole sub-chunk earlier, so that the boundary shrinks to a wait that never waits, a
+// warp sync and the next copies.  MEASURED (B200, lmax 6143): no gain for the covariance jobs (TTTT 18.02 vs 18.12 ms,
+// EEEE 26.07 vs 26.10), a loss for the light and two-parity jobs (TT 5.29 vs 4.92, fused M++/M-- 24.5 vs 21.2: the
+// extra sub-chunk of ring lookahead costs shared memory) -- the boundary is not what keeps the FP64 pipe at 82-85 %.
+// Default 0: products at the boundary.
+#ifndef PSB200_V4_EMBED
+#define PSB200_V4_EMBED 0
+#endif
+constexpr bool V4_EMBED = PSB200_V4_EMBED != 0;
 __host__ __device__ constexpr int v4_p(int job) { return (32 / v3_r(job)) * v3_r(job); }          // steps per sub-chunk
 __host__ __device__ constexpr int v4_g(int job) { return 32 / v3_r(job); }                         // groups per sub-chunk
 // Ring length / R: the live range is LPR + G sub-indices; rounded up to a power of two so that the wrap is a mask and
@@ -32,20 +42,28 @@ __host__ __device__ constexpr int v4_g(int job) { return 32 / v3_r(job); }      
 // 17 % of the shared-memory wavefronts of the first build were conflict replays).
 __host__ __device__ constexpr int v4_sublen(int job)
 {
-    const int need = 32 / v3_nr(job) + v4_g(job);
+    // live sub-indices: LPR + G with products at the boundary; one more sub-chunk of lookahead when they are embedded
+    const int need = V4_EMBED ? 32 / v3_nr(job) - 1 + 2 * v4_g(job) : 32 / v3_nr(job) + v4_g(job);
     return need <= 16 ? 16 : (need <= 32 ? 32 : 64);
 }
+// Distance of the R residue sub-tables of a ring: odd, so that the staging lanes of one sub-index (consecutive residues)
+// store to distinct banks (with the power-of-two distance the stores of a pass were R-way conflicts).
+__host__ __device__ constexpr int v4_subp(int job) { return v4_sublen(job) + 1; }
 // Doubles between the rings of consecutive rows of a warp.  With 64-bit loads a half-warp is one wavefront; for NR = 4
 // it holds two row groups of 8 lanes reading the same sub-indices of their own rings: conflict-free iff the stride is
 // 8 modulo 16 doubles (NR = 8: four groups of 4 lanes, stride 4 modulo 16).
 __host__ __device__ constexpr int v4_tstride(int job)
 {
-    const int n = v3_ntab(job) * v3_r(job) * v4_sublen(job), nr = v3_nr(job);
-    if (v3_ntab(job) == 1) return n + (nr >= 4 ? 32 / nr : 0);     // 64-bit loads: 2 (NR 4) or 4 (NR 8) groups per half-warp
-    return n + (nr == 8 ? 8 : 0);                                  // 128-bit loads: a quarter-warp holds 2 groups only for NR 8
+    const int n = v3_ntab(job) * v3_r(job) * v4_subp(job), nr = v3_nr(job);
+    int want = -1;                                             // required stride modulo 16 doubles
+    if (v3_ntab(job) == 1 && nr >= 4) want = 32 / nr;          // 64-bit loads: 2 (NR 4) or 4 (NR 8) row groups per half-warp
+    if (v3_ntab(job) == 2 && nr == 8) want = 8;                // 128-bit loads: a quarter-warp holds 2 groups only for NR 8
+    if (want < 0) return n + (n & 1);
+    return n + ((want - n % 16) + 16) % 16;
 }
 __host__ __device__ constexpr int v4_wrows(int job) { return 2 * v4_p(job); }
-__host__ __device__ constexpr int v4_raw_doubles(int job) { return v3_ntab(job) * (2 + 2 * v3_nr(job)) * 32; }
+__host__ __device__ constexpr int v4_raw_slot(int job) { return v3_ntab(job) * (2 + 2 * v3_nr(job)) * 32; }   // one pass
+__host__ __device__ constexpr int v4_raw_doubles(int job) { return (V4_EMBED ? 2 : 1) * v4_raw_slot(job); }
 __host__ __device__ constexpr int v4_smem_doubles(int job)
 {
     return 2 * v3_nr(job) * (v4_tstride(job) + (v4_tstride(job) & 1)) + v4_wrows(job) * v3_ntab(job) * v3_nqp(job)
@@ -74,7 +92,9 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
     constexpr int NTAB = v3_ntab(JOB), RPS = NTAB;
     constexpr bool XCOL = v3_xcol(JOB);
     constexpr int XE = v3_xc_even(JOB), XO = v3_xc_odd(JOB);
-    constexpr int P = v4_p(JOB), G = v4_g(JOB), SUBLEN = v4_sublen(JOB);
+    constexpr int P = v4_p(JOB), G = v4_g(JOB), SUBLEN = v4_sublen(JOB), SUBP = v4_subp(JOB);
+    constexpr int RS = 32, RSLOT = v4_raw_slot(JOB);    // stride of the raw arrays, doubles per raw slot
+    constexpr int RPG = (NR + G - 1) / G;               // rows whose products one group computes (embedded mode)
     constexpr int TSTR = v4_tstride(JOB) + (v4_tstride(JOB) & 1);
     constexpr int WR = v4_wrows(JOB), ROWD = RPS * NQP;       // W' ring rows, doubles per ring row
     constexpr int CMIN = -((LPR + G - 1) / G);                // first prologue pass: covers the priming entries
@@ -83,7 +103,7 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
     double* shU = smem;                                // product rings, falling index: PT | QT | (PT, QT) per row
     double* shV = shU + NR * TSTR;                     // rising index:  PV | QV | (PV, QV)
     double* shW = shV + NR * TSTR;                     // [WR][RPS][NQP]
-    double* raw = shW + WR * ROWD;                     // raw factors of one pass: [NTAB][2 + 2 NR][32]
+    double* raw = shW + WR * ROWD;                     // raw factors: [slot][NTAB][2 + 2 NR][32]
 
     const int2 blk = T.blocks[blockIdx.x];
     const int l1_first = blk.x, d_lo = blk.y;
@@ -114,57 +134,60 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
     const double* seqA0 = EV ? T.G0 : T.G1;            // falling: [nu]
     const double* seqB0 = EV ? T.G0 : T.G2;            //          [l - nu]
     const double* seqD0 = EV ? T.H0 : T.H1;            // rising:  [sigma + l]   (C = A sequences at [sigma])
-    auto issue = [&](int c) {
+    auto issue_raw = [&](int c) {                      // raw factors of pass c into slot c & 1 (embedded) / slot 0
         if (tid < P) {
             const int nu = c * P + tid;
-            const int sg = d_lo + c * P + SPAN + tid - 1;          // sigma = d_lo + mu' - 1
+            const int sg = d_lo + c * P + SPAN + tid - 1;              // sigma = d_lo + mu' - 1
 #pragma unroll
             for (int h = 0; h < NTAB; ++h) {
                 const double* sA = h == 0 ? seqA0 : T.G1;
                 const double* sB = h == 0 ? seqB0 : T.G2;
                 const double* sD = h == 0 ? seqD0 : T.H1;
-                double* rw = raw + h * (2 + 2 * NR) * 32;
+                double* rw = raw + (V4_EMBED ? (c & 1) * RSLOT : 0) + h * (2 + 2 * NR) * RS;
                 cp_async8(rw + tid, sA + nu);
-                cp_async8(rw + (1 + NR) * 32 + tid, sA + sg);
+                cp_async8(rw + (1 + NR) * RS + tid, sA + sg);
 #pragma unroll
                 for (int g = 0; g < NR; ++g) {
-                    cp_async8(rw + (1 + g) * 32 + tid, sB + (l1_first + g - nu));
-                    cp_async8(rw + (2 + NR + g) * 32 + tid, sD + (sg + l1_first + g));
+                    cp_async8(rw + (1 + g) * RS + tid, sB + (l1_first + g - nu));
+                    cp_async8(rw + (2 + NR + g) * RS + tid, sD + (sg + l1_first + g));
                 }
             }
         }
-        if (c >= 0) {
-            // W' ring rows of steps [cP, (c+1)P): rows j = d_lo + 2 tau (+1: odd-only jobs), RPS consecutive rows per step
-            constexpr int CPR = ROWD / 2;                          // 16-byte pieces per ring row
-            double* dst = shW + (size_t)((c & 1) * P) * ROWD;
-            const double* src = T.Wp + (size_t)(d_lo + 2 * c * P + ((EV || RPS == 2) ? 0 : 1)) * NQP;
-            for (int i = tid; i < P * CPR; i += 32) {
-                const int row = i / CPR, piece = i - row * CPR;
-                cp_async16(dst + row * ROWD + 2 * piece, src + (size_t)row * 2 * NQP + 2 * piece);
-            }
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    // ring sub-index of pass c: U (cG + kq) mod SUBLEN, V (cG + LPR + kq) mod SUBLEN; `cgm` = (cG) mod SUBLEN
-    auto product = [&](int cgm) {
+    auto issue_w = [&](int c) {
+        // W' ring row of step cP + k: row j = d_lo + 2 tau (+1: odd-only jobs), RPS consecutive rows per step; lane k
+        // copies ring row k piece by piece (immediate offsets, no index arithmetic)
+        if (tid < P) {
+            constexpr int CPR = ROWD / 2;                              // 16-byte pieces per ring row
+            double* dst = shW + (size_t)((c & 1) * P + tid) * ROWD;
+            const double* src = T.Wp + (size_t)(d_lo + 2 * (c * P + tid) + ((EV || RPS == 2) ? 0 : 1)) * NQP;
+#pragma unroll
+            for (int piece = 0; piece < CPR; ++piece) cp_async16(dst + 2 * piece, src + 2 * piece);
+        }
+    };
+    auto commit = [&]() { asm volatile("cp.async.commit_group;\n" ::: "memory"); };
+    auto wait_all = [&]() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); };
+    // products of rows [g0, g1) of pass c: lane k owns element k; ring sub-index U (cG + k/R) mod SUBLEN,
+    // V (cG + LPR + k/R) mod SUBLEN with cgm = (cG) mod SUBLEN
+    auto product_rows = [&](int c, int cgm, int g0, int g1) {
         if (tid < P) {
             const int su = (cgm + kq) & (SUBLEN - 1);
             const int sv = (cgm + LPR + kq) & (SUBLEN - 1);
-#pragma unroll
-            for (int g = 0; g < NR; ++g) {
+            const double* slot = raw + (V4_EMBED ? (c & 1) * RSLOT : 0);
+            for (int g = g0; g < g1; ++g) {
                 double pu[NTAB], pv[NTAB];
 #pragma unroll
                 for (int h = 0; h < NTAB; ++h) {
-                    const double* rw = raw + h * (2 + 2 * NR) * 32;
-                    pu[h] = rw[tid] * rw[(1 + g) * 32 + tid];
-                    pv[h] = rw[(1 + NR) * 32 + tid] * rw[(2 + NR + g) * 32 + tid];
+                    const double* rw = slot + h * (2 + 2 * NR) * RS;
+                    pu[h] = rw[tid] * rw[(1 + g) * RS + tid];
+                    pv[h] = rw[(1 + NR) * RS + tid] * rw[(2 + NR + g) * RS + tid];
                 }
                 if constexpr (NTAB > 1) {
-                    reinterpret_cast<double2*>(shU + g * TSTR)[kr * SUBLEN + su] = make_double2(pu[0], pu[1]);
-                    reinterpret_cast<double2*>(shV + g * TSTR)[kr * SUBLEN + sv] = make_double2(pv[0], pv[1]);
+                    reinterpret_cast<double2*>(shU + g * TSTR)[kr * SUBP + su] = make_double2(pu[0], pu[1]);
+                    reinterpret_cast<double2*>(shV + g * TSTR)[kr * SUBP + sv] = make_double2(pv[0], pv[1]);
                 } else {
-                    shU[g * TSTR + kr * SUBLEN + su] = pu[0];
-                    shV[g * TSTR + kr * SUBLEN + sv] = pv[0];
+                    shU[g * TSTR + kr * SUBP + su] = pu[0];
+                    shV[g * TSTR + kr * SUBP + sv] = pv[0];
                 }
             }
         }
@@ -198,23 +221,29 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
         if constexpr (NTAB > 1) { wU1[k] = 0.0; wV1[k] = 0.0; }
     }
 
-    // ---- prologue: passes CMIN .. 0 (the V ring needs mu' from 1, the U ring zeros for nu < 0), then pass 1 in flight ----
+    // ---- prologue: passes CMIN .. 0 synchronously (the V ring needs mu' from 1, the U ring zeros for nu < 0) ----
     {
         int cgm = ((CMIN * G) % SUBLEN + SUBLEN) % SUBLEN;
         for (int c = CMIN; c <= 0; ++c) {
-            issue(c);
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            issue_raw(c);
+            if (c == 0) issue_w(0);
+            commit();
+            wait_all();
             __syncwarp();
-            product(cgm);
+            product_rows(c, cgm, 0, NR);
             __syncwarp();
             cgm = (cgm + G) & (SUBLEN - 1);
         }
-        issue(1);
+        // embedded mode: the raw factors of pass 1 must have landed when sub-chunk 0 starts (its groups multiply them);
+        // boundary mode: pass 1 (raw + W') just takes off
+        issue_raw(1);
+        if constexpr (!V4_EMBED) issue_w(1);
+        commit();
     }
     // prime the carried part of the rising windows: k = 0..R-2 <-> mu' = e + k + 1: residue k+1, sub-index eR
 #pragma unroll
     for (int k = 0; k < R - 1; ++k) {
-        const int pos = (k + 1) * SUBLEN + eR;
+        const int pos = (k + 1) * SUBP + eR;
         if constexpr (NTAB > 1) {
             const double2 v = reinterpret_cast<const double2*>(myV)[pos];
             wV0[k] = v.x; wV1[k] = v.y;
@@ -225,30 +254,45 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
 
     // reader ring coordinates at group t = tau / R: U sub-index (t - eR) mod SUBLEN, V (t + eR + 1) mod SUBLEN, W' row tau mod WR
     int qU = (SUBLEN - eR) % SUBLEN, qV = (eR + 1) % SUBLEN, wrow = 0;
-    int cgm1 = G % SUBLEN;                                   // (c G) mod SUBLEN of the pass in flight (c = 1)
+    int cgm1 = G % SUBLEN;                                   // (c G) mod SUBLEN of the pass whose products come next (c + 1)
     for (int c = 0; c * P <= tau_end; ++c) {
-        if (c > 0) {
-            // boundary: the copies of pass c have landed -> products into the rings -> copies of pass c+1 take off
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if constexpr (V4_EMBED) {
+            // boundary: raw(c+1) -- issued a sub-chunk ago -- and W'(c) are in; the products of pass c that the groups
+            // of the previous sub-chunk stored become visible; raw(c+2) and W'(c+1) take off
+            wait_all();
             __syncwarp();
-            product(cgm1);
+            if ((c + 1) * P <= tau_end) {
+                issue_raw(c + 2);
+                issue_w(c + 1);
+                commit();
+            }
+        } else if (c > 0) {
+            // boundary: the copies of pass c have landed -> products into the rings -> copies of pass c+1 take off
+            wait_all();
+            __syncwarp();
+            product_rows(c, cgm1, 0, NR);
             __syncwarp();
             cgm1 = (cgm1 + G) & (SUBLEN - 1);
-            if ((c + 1) * P <= tau_end) issue(c + 1);
+            if ((c + 1) * P <= tau_end) { issue_raw(c + 1); issue_w(c + 1); commit(); }
         }
         const int g_end = min(G, (tau_end - c * P) / R + 1);
         for (int gi = 0; gi < g_end; ++gi) {
+            if constexpr (V4_EMBED) {
+                // my share of the products of pass c+1 (rows gi RPG ..): independent of everything below, so its
+                // LDS -> DMUL -> STS chains run under the group's FP64 stream
+                if (gi * RPG < NR) product_rows(c + 1, cgm1, gi * RPG, min(NR, (gi + 1) * RPG));
+            }
             // ---- the R new entries of every window: residue u, one sub-index for all u ----
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 if constexpr (NTAB > 1) {
-                    const double2 a = reinterpret_cast<const double2*>(myU)[u * SUBLEN + qU];
-                    const double2 b = reinterpret_cast<const double2*>(myV)[u * SUBLEN + qV];
+                    const double2 a = reinterpret_cast<const double2*>(myU)[u * SUBP + qU];
+                    const double2 b = reinterpret_cast<const double2*>(myV)[u * SUBP + qV];
                     wU0[R - 1 + u] = a.x; wU1[R - 1 + u] = a.y;
                     wV0[R - 1 + u] = b.x; wV1[R - 1 + u] = b.y;
                 } else {
-                    wU0[R - 1 + u] = myU[u * SUBLEN + qU];
-                    wV0[R - 1 + u] = myV[u * SUBLEN + qV];
+                    wU0[R - 1 + u] = myU[u * SUBP + qU];
+                    wV0[R - 1 + u] = myV[u * SUBP + qV];
                 }
             }
             const double* wgrp = shW + (size_t)wrow * ROWD;
@@ -337,6 +381,7 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
             qV = (qV + 1) & (SUBLEN - 1);
             wrow += R; if (wrow == WR) wrow = 0;
         }
+        if constexpr (V4_EMBED) cgm1 = (cgm1 + G) & (SUBLEN - 1);
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");      // nothing may be in flight when the block retires
 

@@ -151,10 +151,11 @@ int enable_peer(int from, int to, bool* direct)
 {
     *direct = false;
     if (from == to) { *direct = true; return OK; }
+    if (getenv("PSB200_NO_PEER_STORES")) return OK;            // test hook: force the explicit peer-copy path
     if (g_peer_on[from][to]) { *direct = true; return OK; }
     int can = 0;
     CUDA_TRY(cudaDeviceCanAccessPeer(&can, from, to));
-    if (!can || getenv("PSB200_NO_PEER_STORES")) return OK;
+    if (!can) return OK;
     cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);          // current device == from
     if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
     if (e != cudaSuccess) { cudaGetLastError(); return OK; }     // fall back to explicit peer copies

@@ -73,6 +73,17 @@ class ZonalSky:
         ls = np.arange(self.lmax + 1)
         return out * np.sqrt(np.pi * (2 * ls + 1))
 
+    def al0_device(self, fields):
+        """The same transform on the GPU (psb200_zonal_alm: W-spectrum production, first slice -- SURVEY.md 8f-4)."""
+        from . import _lib
+        F = np.ascontiguousarray(np.atleast_2d(np.asarray(fields, dtype=np.float64)))
+        out = np.zeros((F.shape[0], self.lmax + 1))
+        dp = lambda a: a.ctypes.data_as(_lib.DP)
+        x, w = np.ascontiguousarray(self.x), np.ascontiguousarray(self.w)
+        _lib.check(_lib.lib().psb200_zonal_alm(F.shape[0], F.shape[1], dp(x), dp(w), dp(F), F.shape[1], self.lmax, dp(out),
+                                               self.lmax + 1))
+        return out
+
     def cross(self, a, b):
         """alm2cl of two zonal fields: a_l0 b_l0 / (2l+1)."""
         return a * b / (2.0 * np.arange(self.lmax + 1) + 1.0)

@@ -132,3 +132,37 @@ def test_solve_error_codes(ps, masks):
     assert lib.psb200_mcm_solve(0, 0, 15, dp(Z), 16, dp(p), 16, 1, dp(c), 16, 1) == 6
     with pytest.raises(np.linalg.LinAlgError):
         ps.mcm_solve("TT", ps.SpectralVector(Z), None, p)
+
+
+def test_solves_across_gpus(ps, masks):
+    """ngpus = 2: the row bands of the other device arrive in the root's matrix through peer stores of its pair kernel
+    (or one peer copy); the assembled matrix -- hence the LU and the solution -- must be bit-identical to the 1-GPU call.
+    Also with the explicit-copy path forced (PSB200_NO_PEER_STORES)."""
+    import os
+    if ps.lib().psb200_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    lmax, (mT1, mP1, mT2, mP2) = masks
+    lmin = 2
+    rng = np.random.default_rng(8)
+    N = lmax + 1 - lmin
+    p1 = rng.normal(size=N)
+    one = ps.mcm_solve("TT", mT1, mT2, ps.SpectralVector(p1, lmin), lmin=lmin, ngpus=1).parent
+    two = ps.mcm_solve("TT", mT1, mT2, ps.SpectralVector(p1, lmin), lmin=lmin, ngpus=2).parent
+    assert np.array_equal(one, two)
+    pb = [ps.SpectralVector(rng.normal(size=N), lmin), ps.SpectralVector(rng.normal(size=N), lmin)]
+    b1 = ps.mcm_solve("EE_BB", mP1, mP2, pb, lmin=lmin, ngpus=1)
+    b2 = ps.mcm_solve("EE_BB", mP1, mP2, pb, lmin=lmin, ngpus=2)
+    assert np.array_equal(b1[0].parent, b2[0].parent) and np.array_equal(b1[1].parent, b2[1].parent)
+    maps1 = [ps.Alm.zonal(rng.normal(size=lmax + 1)) for _ in range(3)]
+    maps2 = [ps.Alm.zonal(rng.normal(size=lmax + 1)) for _ in range(3)]
+    d1 = ps.maskedalm2spectra_device(maps1, mT1, mP1, maps2, mT2, mP2, lmin=lmin, ngpus=1)
+    d2 = ps.maskedalm2spectra_device(maps1, mT1, mP1, maps2, mT2, mP2, lmin=lmin, ngpus=2)
+    for k in d1:
+        assert np.array_equal(d1[k].parent, d2[k].parent), k
+    os.environ["PSB200_NO_PEER_STORES"] = "1"
+    try:
+        # a fresh pair of devices is not needed: the flag is read per call, peer access already enabled is simply not used
+        three = ps.mcm_solve("TT", mT1, mT2, ps.SpectralVector(p1, lmin), lmin=lmin, ngpus=2).parent
+    finally:
+        del os.environ["PSB200_NO_PEER_STORES"]
+    assert np.array_equal(one, three)
