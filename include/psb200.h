@@ -132,6 +132,12 @@ int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void*
  * (2 l1+1)(lmax-l1+1) instead. */
 int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges);
 
+/* Bands of the HOST-level calls (psb200_mcm / psb200_cov / psb200_mcm_master with ngpus > 1; api/code as in
+ * psb200_job_stats).  There every device also copies its own L-shaped region of the result to the caller's array, and
+ * kernel time and copy time do not balance alike (low rows: cheap kernels, long columns), so these edges minimise the
+ * largest max(kernel seconds, copy seconds) over the bands instead of the kernel cost alone. */
+int psb200_host_band_edges(int api, int code, int lmin, int lmax, int lenW, int nbands, int* edges);
+
 /* ---- QuickPol Xi matrix -------------------------------------------------
  * Replaces the pair loop of quickpolXi! (/root/reference/src/beam.jl:72-101) with Xisum (:16-28)
  * and the WignerF / wigner3j_f! calls it makes (:86-93):
@@ -166,7 +172,9 @@ int psb200_quickpol_edges(int lmax, int band_lo, int band_hi, int nbands, int* e
  *   system 0..3: the N x N matrix of psb200_mcm kind 0..3;  pCl, Cl: N x nrhs column-major (ldp, ldc >= N)
  *   system 4: [M++ M--; M-- M++] \ [pCl_EE; pCl_BB]   (M_EE_BB, src/modecoupling.jl:213-216, :365-371)
  *   system 5: [M++ -M--; -M-- M++] \ [pCl_EB; pCl_BE] (M_EB_BE, :220-223, :373-379);  pCl, Cl: 2N x nrhs (ld >= 2N)
- *   The LU is that of the dense 2N x 2N block matrix, as src/blockspectralmatrix.jl:89-122 does. */
+ *   The block systems are block-circulant and split exactly into the two N x N systems of M++ + M-- and M++ - M--
+ *   (8x fewer flops than the LU of the dense 2N x 2N hvcat that src/blockspectralmatrix.jl:89-122 factorises; same
+ *   solution up to rounding). */
 enum { PSB200_SYS_M00 = 0, PSB200_SYS_M02 = 1, PSB200_SYS_MPP = 2, PSB200_SYS_MMM = 3, PSB200_SYS_EE_BB = 4, PSB200_SYS_EB_BE = 5 };
 int psb200_mcm_solve(int system, int lmin, int lmax, const double* V, int nV,
                      const double* pCl, long ldp, int nrhs, double* Cl, long ldc, int ngpus);

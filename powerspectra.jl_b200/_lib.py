@@ -34,6 +34,7 @@ PROTOTYPES = {
                                  C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
     "psb200_finish_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "psb200_band_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "psb200_host_band_edges": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)]),
     "psb200_terms": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "psb200_dfma_peak": (C.c_double, [C.c_int]),
     "psb200_job_stats": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_longlong)]),

@@ -715,6 +715,71 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
     return rc;
 }
 
+// FP64 instructions per pair-step of the default kernel (profiles/r02_sass_fp64.json), for the time model below.
+static double job_fp64_per_pair_step(int job)
+{
+    using namespace psb;
+    switch (job) {
+        case JOB_M00: return 2; case JOB_M02: return 5; case JOB_MPP: return 6; case JOB_MMM: return 5;
+        case JOB_MPPMMM: return 11; case JOB_TTTT: return 9; case JOB_EEEE: return 13; case JOB_TTTE: return 5;
+        case JOB_TETE: return 9; case JOB_TEEEP: return 9; case JOB_TEEE: return 8; case JOB_TTEE: return 3;
+        case JOB_MASTER: return 14;
+    }
+    return 9;
+}
+
+// Bands of the HOST-level multi-GPU call.  Every device delivers its own L-shaped region of the result straight to
+// the caller's array while it computes the next sub-band, so its time is max(kernel time, D2H time) -- and the two
+// do not balance alike: the low rows are cheap to compute but long (band 0 of an 8-way kernel-balanced split owns
+// 43 % of the bytes: 14 ms of copies against 11 ms of kernels per step at lmax 6143, the exposed D2H of the round-1
+// 8-GPU line).  Rows carry two weights, kernel seconds (row_cost x the job's FP64 work per pair-step / the sustained
+// FP64 issue rate) and copy seconds (bytes of the row's part of the L region / the PCIe rate); the split minimises the
+// largest max(sum kernel + a quarter of sum copy, sum copy) over contiguous bands (bisection on that bound, greedy
+// feasibility).
+// PSB200_HOST_SPLIT=kernel restores the kernel-balanced edges of psb200_band_edges.
+static void host_band_edges(const HostJob& hj, int nb, int* edges)
+{
+    const char* mode = getenv("PSB200_HOST_SPLIT");
+    if (mode && strcmp(mode, "kernel") == 0) { psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, nb, edges); return; }
+    const int N = hj.lmax - hj.lmin + 1;
+    constexpr double kIssue = 1.83e13 * 0.82;                 // FP64 lane-instructions per second, as measured
+    constexpr double kPcie = 50e9;                            // bytes per second per device, pinned destination
+    // row_cost sums to warp-steps of the TTTT tiling (a warp's steps are shared out over its NR rows): 32 R pair-steps each
+    const double per_unit = 32.0 * psb::v3_r(psb::JOB_TTTT) * job_fp64_per_pair_step(hj.job) / kIssue;   // seconds per unit
+    std::vector<double> c(N), d(N);
+    double sc = 0, sd = 0;
+    for (int i = 0; i < N; ++i) {
+        c[i] = (double)row_cost(hj.lmin + i, hj.lmax, hj.lenW) * per_unit;
+        d[i] = 8.0 * hj.nout * (2.0 * (N - i) - 1.0) / kPcie;
+        sc += c[i]; sd += d[i];
+    }
+    auto bands_needed = [&](double lam, int* e) {
+        int k = 0, i = 0;
+        if (e) e[0] = hj.lmin;
+        while (i < N) {
+            double a = 0, b = 0;
+            int j = i;
+            // time of a band: its copies run behind its kernels sub-band by sub-band, the last quarter or so is exposed
+            while (j < N && a + c[j] + 0.25 * (b + d[j]) <= lam && b + d[j] <= lam) { a += c[j]; b += d[j]; ++j; }
+            if (j == i) ++j;                                  // a single row above the bound: its own band
+            ++k;
+            if (e && k <= nb) e[k] = hj.lmin + j;
+            i = j;
+        }
+        return k;
+    };
+    double lo = std::max(sc, sd) / nb * 0.5, hi = std::max(sc, sd);
+    for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (bands_needed(mid, nullptr) <= nb) hi = mid; else lo = mid;
+    }
+    std::vector<int> e(nb + 1, hj.lmax + 1);
+    const int k = bands_needed(hi, e.data());
+    for (int b = k + 1; b <= nb; ++b) e[b] = hj.lmax + 1;     // fewer bands than devices: the rest stay empty
+    e[nb] = hj.lmax + 1;
+    for (int b = 0; b <= nb; ++b) edges[b] = e[b];
+}
+
 int run_host_job(const HostJob& hj, int ngpus)
 {
     int cur = 0;
@@ -726,7 +791,12 @@ int run_host_job(const HostJob& hj, int ngpus)
     }
     Trace tr;
     std::vector<int> edges(ngpus + 1);
-    psb200_band_edges(hj.lmin, hj.lmax, hj.lenW, ngpus, edges.data());
+    host_band_edges(hj, ngpus, edges.data());
+    if (tr.on) {
+        fprintf(stderr, "[psb200] host bands:");
+        for (int g = 0; g <= ngpus; ++g) fprintf(stderr, " %d", edges[g]);
+        fprintf(stderr, "\n");
+    }
     std::vector<int> rcs(ngpus, OK);
     std::vector<std::string> errs(ngpus);
     std::vector<std::thread> th;
@@ -865,6 +935,19 @@ int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges)
         while (b < nbands && run >= total * b / nbands) edges[b++] = l + 1;
     }
     while (b <= nbands) edges[b++] = lmax + 1;
+    return OK;
+}
+
+int psb200_host_band_edges(int api, int code, int lmin, int lmax, int lenW, int nbands, int* edges)
+{
+    if (lmin < 0 || lmax < lmin || nbands < 1 || nbands > 16 || !edges) return fail(ERR_ARG, "host_band_edges: bad arguments");
+    HostJob hj{};
+    if (api == 0 && code >= 0 && code <= 4) { hj.job = kMcmJob[code]; hj.nout = code == 4 ? 2 : 1; }
+    else if (api == 1 && code >= 0 && code <= 6) { hj.job = kCovJob[code]; hj.nout = 1; }
+    else if (api == 2) { hj.job = psb::JOB_MASTER; hj.nout = 5; }
+    else return fail(ERR_ARG, "host_band_edges: unknown api/code %d/%d", api, code);
+    hj.lmin = lmin; hj.lmax = lmax; hj.lenW = lenW;
+    host_band_edges(hj, nbands, edges);
     return OK;
 }
 
@@ -1125,7 +1208,8 @@ int psb200_mcm_solve(int system, int lmin, int lmax, const double* V, int nV, co
         }
         DeviceScratch& R = g_scratch[root];
         if (nb == 1) rc = solve_on_root(root, R.X[0], N, 1, cols);
-        else rc = solve_block_on_root(root, R.X[0], R.X[1], N, system == 4 ? 1.0 : -1.0, cols);
+        else if (system == 4) rc = solve_block_systems_on_root(root, R.X[0], R.X[1], N, cols, {});
+        else rc = solve_block_systems_on_root(root, R.X[0], R.X[1], N, {}, cols);
     }
     cudaSetDevice(cur);
     return rc;
@@ -1155,9 +1239,8 @@ int psb200_master_solve(int lmin, int lmax, const double* V_TT, const double* V_
     auto col = [&](int a) { RhsCol c{}; c.in[0] = pCl + (size_t)a * ldp; c.out[0] = Cl + (size_t)a * ldc; return c; };
     auto col2 = [&](int a, int b) { RhsCol c = col(a); c.in[1] = pCl + (size_t)b * ldp; c.out[1] = Cl + (size_t)b * ldc; return c; };
     DeviceScratch& R = g_scratch[root];
-    // the 2N systems first: they read M++ / M-- , which the in-place LUs below do not touch
-    if (rc == OK) rc = solve_block_on_root(root, R.X[3], R.X[4], N, 1.0, {col2(5, 6)});
-    if (rc == OK) rc = solve_block_on_root(root, R.X[3], R.X[4], N, -1.0, {col2(7, 8)});
+    // both block systems from one LU of M++ + M-- and one of M++ - M--
+    if (rc == OK) rc = solve_block_systems_on_root(root, R.X[3], R.X[4], N, {col2(5, 6)}, {col2(7, 8)});
     if (rc == OK) rc = solve_on_root(root, R.X[0], N, 1, {col(0)});
     if (rc == OK) rc = solve_on_root(root, R.X[1], N, 1, {col(1), col(3)});     // TE and TB share mcm(:TE, maskT1, maskP2)
     if (rc == OK) rc = solve_on_root(root, R.X[2], N, 1, {col(2), col(4)});     // ET and BT share mcm(:ET, maskP1, maskT2)

@@ -3,7 +3,8 @@
 // What it replaces on the host side of the reference (which stays available):
 //   M \ pCl                         /root/reference/src/blockspectralmatrix.jl:124-129 (lu + solve of parent(M))
 //   M_EE_BB \ [pCl_EE; pCl_BB]      src/blockspectralmatrix.jl:89-122 (lu of the dense 2N x 2N hvcat), with the block
-//                                   matrices of src/modecoupling.jl:213-223: [M++ M--; M-- M++] and [M++ -M--; -M-- M++]
+//                                   matrices of src/modecoupling.jl:213-223: [M++ M--; M-- M++] and [M++ -M--; -M-- M++];
+//                                   here split exactly into the two N x N systems of M++ + M-- and M++ - M--
 //   maskedalm2spectra's solves      src/modecoupling.jl:348-377
 //   decouple_covmat(Y, B1, B2)      src/covariance.jl:8-14:  B1^-1 Y (B2^-1)^T through lu(B1'), lu(B2')
 //
@@ -93,19 +94,6 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
         const int j = bj + r, i = bi + tx;
         if (i < n && j < n) out[(long)j * ldo + i] = tile[tx][r];
     }
-}
-
-// 2N x 2N block matrix [P  s Q; s Q  P] (column-major, leading dimension 2N) from the N x N matrices P, Q (ld = N)
-__global__ void __launch_bounds__(256) block_assemble_kernel(const double* __restrict__ P, const double* __restrict__ Q,
-                                                             double* __restrict__ B, int N, double s)
-{
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // row inside a block
-    const long j = blockIdx.y;                                         // column inside a block
-    if (i >= N) return;
-    const double p = P[j * N + i], q = s * Q[j * N + i];
-    const long L2 = 2L * N;
-    B[j * L2 + i] = p;            B[(j + N) * L2 + i] = q;
-    B[j * L2 + i + N] = q;        B[(j + N) * L2 + i + N] = p;
 }
 
 // LU of the n x n matrix dA (in place) on the current device + solve of nrhs right-hand sides dB (in place).
@@ -255,15 +243,59 @@ int solve_on_root(int root, double* dA, int N, int nb, const std::vector<RhsCol>
     return OK;
 }
 
-// [P sQ; sQ P] \ rhs  (2N rows)
-int solve_block_on_root(int root, const double* dP, const double* dQ, int N, double sgn, const std::vector<RhsCol>& cols)
+// S = P + Q, D = P - Q  (N x N, ld = N)
+__global__ void __launch_bounds__(256) sumdiff_kernel(const double* __restrict__ P, const double* __restrict__ Q,
+                                                      double* __restrict__ S, double* __restrict__ D, size_t n2)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const double p = P[i], q = Q[i];
+    S[i] = p + q;
+    D[i] = p - q;
+}
+
+// The 2N x 2N block systems of src/modecoupling.jl:213-223,
+//     [P Q; Q P] [x; y] = [p; q]   (M_EE_BB)        [P -Q; -Q P] [x; y] = [p; q]   (M_EB_BE),
+// are block-circulant: with S = P + Q, D = P - Q they split exactly into two N x N systems,
+//     EE_BB:  S (x+y) = p+q,  D (x-y) = p-q          EB_BE:  D (x+y) = p+q,  S (x-y) = p-q,
+// so ONE LU of S and ONE of D serve both systems: 2 x (2/3) N^3 flops instead of the 2 x (2/3)(2N)^3 of factorising the
+// dense hvcat twice (what src/blockspectralmatrix.jl:89-122 does on the host) -- 8x less work, same solution up to
+// rounding (the split is an orthogonal similarity; checked against the dense host LU in tests/test_gpu_solve.py).
+// plus / minus: right-hand-side columns of the EE_BB / EB_BE system (two N-pieces each).
+int solve_block_systems_on_root(int root, const double* dP, const double* dQ, int N, const std::vector<RhsCol>& plus,
+                                const std::vector<RhsCol>& minus)
 {
     DeviceScratch& R = g_scratch[root];
     SolveScratch& s = g_solve[root];
-    if (int rc = grow(&s.A, &s.capA, (size_t)4 * N * N)) return rc;
-    block_assemble_kernel<<<dim3((N + 255) / 256, N), 256, 0, R.stream>>>(dP, dQ, s.A, N, sgn);
+    const size_t n2 = (size_t)N * N;
+    if (int rc = grow(&s.A, &s.capA, 2 * n2)) return rc;
+    double *dS = s.A, *dD = s.A + n2;
+    sumdiff_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, R.stream>>>(dP, dQ, dS, dD, n2);
     CUDA_TRY(cudaGetLastError());
-    return solve_on_root(root, s.A, N, 2, cols);
+    const size_t np = plus.size(), nm = minus.size(), nc = np + nm;
+    if (nc == 0) return OK;
+    // host staging: column k of `hs` goes to S, of `hd` to D
+    std::vector<double> hs(nc * N), hd(nc * N), xs(nc * N), xd(nc * N);
+    for (size_t k = 0; k < nc; ++k) {
+        const RhsCol& c = k < np ? plus[k] : minus[k - np];
+        double* sum = (k < np ? hs.data() : hd.data()) + k * N;      // p + q
+        double* dif = (k < np ? hd.data() : hs.data()) + k * N;      // p - q
+        for (int i = 0; i < N; ++i) { sum[i] = c.in[0][i] + c.in[1][i]; dif[i] = c.in[0][i] - c.in[1][i]; }
+    }
+    std::vector<RhsCol> cs(nc), cd(nc);
+    for (size_t k = 0; k < nc; ++k) {
+        cs[k].in[0] = hs.data() + k * N; cs[k].out[0] = xs.data() + k * N;
+        cd[k].in[0] = hd.data() + k * N; cd[k].out[0] = xd.data() + k * N;
+    }
+    if (int rc = solve_on_root(root, dS, N, 1, cs)) return rc;
+    if (int rc = solve_on_root(root, dD, N, 1, cd)) return rc;
+    for (size_t k = 0; k < nc; ++k) {
+        const RhsCol& c = k < np ? plus[k] : minus[k - np];
+        const double* a = (k < np ? xs.data() : xd.data()) + k * N;  // x + y
+        const double* b = (k < np ? xd.data() : xs.data()) + k * N;  // x - y
+        for (int i = 0; i < N; ++i) { c.out[0][i] = 0.5 * (a[i] + b[i]); c.out[1][i] = 0.5 * (a[i] - b[i]); }
+    }
+    return OK;
 }
 
 // B1^-1 Y (B2^-1)^T on the current device, Y in place; all N x N column-major device matrices.

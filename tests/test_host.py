@@ -131,6 +131,23 @@ def test_alm2cl_and_workspace(ps):
     assert w1 is w2 and len(calls) == 1                      # cached like workspace.W_spectra
 
 
+def test_host_band_edges_follow_the_copies(ps):
+    """TT at lmax 6143 is copy-bound on several GPUs (302 MB of result, 5 ms of kernels): the host-call bands must move
+    towards equal bytes (first band much shorter than the kernel-balanced one); EEEE is kernel-bound and keeps the
+    kernel-balanced edges to within a few per cent."""
+    import ctypes as C
+    from powerspectra_jl_b200 import device as dev
+    kb = dev.band_edges(0, 6143, 8, lenW=6144)
+    tt, ee = (C.c_int * 9)(), (C.c_int * 9)()
+    assert ps.lib().psb200_host_band_edges(0, 0, 0, 6143, 6144, 8, tt) == 0
+    assert ps.lib().psb200_host_band_edges(1, 1, 0, 6143, 6144, 8, ee) == 0
+    assert tt[1] < 0.6 * kb[1]
+    assert abs(ee[1] - kb[1]) < 0.1 * kb[1]
+    N = 6144
+    share = lambda e, g: sum(2 * (N - i) - 1 for i in range(e[g], e[g + 1])) / N ** 2
+    assert max(share(tt, g) for g in range(8)) < 0.2 < max(share(kb, g) for g in range(8))
+
+
 def test_band_edges_properties_random(ps):
     """Property test (hypothesis): for any shape the two partitioners return a monotone cover with the right ends,
     no band is empty while rows remain for the later ones only if the cost demands it, and with the reference
@@ -154,6 +171,13 @@ def test_band_edges_properties_random(ps):
             assert cum[i] >= cum[-1] * k / nb * (1 - 1e-12)
             if i > 0 and e[k] > e[k - 1]:
                 assert cum[i - 1] < cum[-1] * k / nb * (1 + 1e-12)
+        # bands of the host-level multi-GPU calls (kernel seconds and copy seconds balanced jointly)
+        import ctypes as C
+        for api, code in ((0, 0), (0, 4), (1, 1), (2, 0)):
+            h = (C.c_int * (nb + 1))()
+            assert ps.lib().psb200_host_band_edges(api, code, lmin, lmax, max(lenW, 1), nb, h) == 0
+            h = list(h)
+            assert h[0] == lmin and h[-1] == lmax + 1 and all(b >= a for a, b in zip(h, h[1:]))
         # QuickPol column bands
         bl, bh = min(span, lenW % 50), min(span, lenW % 37)
         q = dev.quickpol_edges(lmax, bl, bh, nb)
