@@ -503,7 +503,9 @@ struct DeviceScratch {
     double* T = nullptr;        // transposed block row of a band (multi-GPU host path)
     size_t capT = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;         // odd sub-bands of a host-level call (consecutive sub-bands overlap their tails)
     cudaStream_t copy_stream = nullptr;     // D2H of finished column bands, overlapped with compute
+    cudaEvent_t ev_in = nullptr;            // inputs of the call are on the device
     cudaEvent_t ev[16] = {};
 };
 DeviceScratch g_scratch[16];
@@ -513,7 +515,9 @@ int scratch_reserve(int dev, int which, size_t n)
     DeviceScratch& s = g_scratch[dev];
     if (!s.stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         for (auto& e : s.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     if (which < 5) {
@@ -662,26 +666,33 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
         for (int o = 0; o < hj.nout; ++o) Xs[o] = s.X[o] - rowoff * ldX;   // kernels index rows from lmin
         psb::PairArgs A{};
         if (int rc = run_on_device(hj, g, a, b, Xs, ldX, &A)) return rc;
+        // Sub-bands alternate between two streams: they touch disjoint rows, so the blocks of sub-band k+1 fill the SMs
+        // that the last, longest blocks of sub-band k leave idle (on one stream every sub-band paid its own drain: 8 x 5
+        // drains per step were most of the 9.5 ms the host calls lost against the resident kernels at lmax 6143).
+        CUDA_TRY(cudaEventRecord(s.ev_in, s.stream));
+        CUDA_TRY(cudaStreamWaitEvent(s.stream2, s.ev_in, 0));
         Trace tr;
         for (int k = 0; k < ns; ++k) {
             const int sa = sub[k], sb = sub[k + 1], nbs = sb - sa;
+            cudaStream_t sk = (k & 1) && !getenv("PSB200_ONE_STREAM") ? s.stream2 : s.stream;
             A.row_lo = sa; A.row_hi = sb;
-            if (int rc = launch_any(hj.job, A, s.stream)) return rc;
+            if (int rc = launch_any(hj.job, A, sk)) return rc;
             const int nt = (nbs + 31) / 32;
             const int c0 = sb - hj.lmin;                  // first column right of this diagonal block
             for (int o = 0; o < hj.nout; ++o) {
                 double* slab = s.X[o] + (size_t)(sa - a) * ldX;         // row sa of the slab
-                finish_kernel<<<dim3(nt, nt), 256, 0, s.stream>>>(slab + (sa - hj.lmin), ldX, sa, nbs, hj.scale, 0);
+                finish_kernel<<<dim3(nt, nt), 256, 0, sk>>>(slab + (sa - hj.lmin), ldX, sa, nbs, hj.scale, 0);
                 CUDA_TRY(cudaGetLastError());
                 if (c0 < N) {
                     double* Tk = s.T + toff[k] + (size_t)o * nbs * (N - c0);
-                    band_transpose_kernel<<<dim3((N - c0 + 31) / 32, nt), 256, 0, s.stream>>>(
+                    band_transpose_kernel<<<dim3((N - c0 + 31) / 32, nt), 256, 0, sk>>>(
                         slab, ldX, Tk, nbs, sa, hj.lmin, c0, N, hj.scale);
                     CUDA_TRY(cudaGetLastError());
                 }
             }
-            CUDA_TRY(cudaEventRecord(s.ev[k], s.stream));
+            CUDA_TRY(cudaEventRecord(s.ev[k], sk));
         }
+
         // everything is queued; now the copies on the second stream (a copy into pageable memory blocks
         // this host thread, which is harmless once nothing is left to launch)
         for (int k = 0; k < ns; ++k) {
@@ -706,6 +717,7 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
         }
         tr.mark("   band: kernels + finish + transpose", g, s.stream);
         CUDA_TRY(cudaStreamSynchronize(s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream2));
         CUDA_TRY(cudaStreamSynchronize(s.copy_stream));
         tr.mark("   band: tail of D2H", g, s.copy_stream);
         return OK;

@@ -588,33 +588,46 @@ def test_band_sharding_device_api(ps, oracle):
                 assert_parity(Gm, oracle.mcm(k, lmin, lmax, V, ld=True), S)
 
 
-def test_simple_kernel_cross_check(ps, oracle, monkeypatch):
-    """PSB200_KERNEL=v1 selects the straightforward kernel (inline sqrt/divide, sum normalisation
-    over the full family); the tuned kernel (tables, closed-form start, truncated l3 range) must
-    agree with it.  Both are CUDA; neither is a fallback for the other."""
+def test_kernel_cross_checks(ps, oracle, monkeypatch):
+    """Four CUDA evaluations by independent methods must agree: the default kernel (closed-form table products, ring
+    staging), PSB200_KERNEL=v3 (same closed forms, per-chunk staging), v2 (forward three-term recurrence from the
+    closed-form start, even-parity identity) and v1 (inline sqrt/divide recurrence, sum normalisation over the full
+    family).  None is a fallback for another."""
     from powerspectra_jl_b200 import synthetic as syn
     lmax = 400
     V = syn.mask_spectra(lmax, seeds=(1001, 1004))[(0, 1)]
-    for spec, kind in (("TT", 0), ("TE", 1), ("M++", 2), ("M--", 3)):
-        monkeypatch.setenv("PSB200_KERNEL", "v2")
-        A = ps.mcm(spec, ps.SpectralVector(V)).parent
-        monkeypatch.setenv("PSB200_KERNEL", "v1")
-        B = ps.mcm(spec, ps.SpectralVector(V)).parent
-        monkeypatch.delenv("PSB200_KERNEL")
+
+    def run(fn, which):
+        if which:
+            monkeypatch.setenv("PSB200_KERNEL", which)
+        try:
+            return fn()
+        finally:
+            if which:
+                monkeypatch.delenv("PSB200_KERNEL")
+    for spec, kind in (("TT", 0), ("TE", 1), ("M++", 2), ("M--", 3), ("EE_BB", 4)):
+        if kind == 4:
+            fn = lambda: np.hstack([b.parent for b in (lambda B: (B.getblock(0, 0), B.getblock(0, 1)))(
+                ps.mcm("EE_BB", ps.SpectralVector(V)))])
+        else:
+            fn = lambda: ps.mcm(spec, ps.SpectralVector(V)).parent
+        A = run(fn, None)
         with oracle.abs_mode():
-            S = oracle.mcm(kind, 0, lmax, V)
-        assert parity_worst(A, B, S) <= 1.0, spec
-        if kind:      # rows l1 < 2 of the spin-2 kinds come from the same low-rows kernel whichever pair kernel runs
-            assert np.array_equal(A[:2], B[:2]) and np.array_equal(A[:, :2], B[:, :2])
+            S = oracle.mcm(kind, 0, lmax, V) if kind < 4 else np.hstack([oracle.mcm(2, 0, lmax, V), oracle.mcm(3, 0, lmax, V)])
+        for which in ("v3", "v2", "v1"):
+            B = run(fn, which)
+            assert parity_worst(A, B, S) <= 1.0, (spec, which)
+            if kind:  # rows l1 < 2 of the spin-2 kinds come from the same low-rows kernel whichever pair kernel runs
+                assert np.array_equal(A[:2], B[:2]), (spec, which)
+        # same closed forms, same tiling, same summation order: v3 and the default agree to the last bits of the products
+        assert np.max(np.abs(run(fn, "v3") - A)) <= 1e-13 * np.max(np.abs(A)), spec
     ws, sp, rt = _cov_case(ps, 200)
     for chans in (("TT", "TT"), ("EE", "EE"), ("TE", "TE"), ("TT", "TE"), ("TT", "EE"), ("TE", "EE")):
-        monkeypatch.setenv("PSB200_KERNEL", "v2")
-        A = ps.coupledcov(chans[0], chans[1], ws, sp, rt, lmin=2).parent
-        monkeypatch.setenv("PSB200_KERNEL", "v1")
-        B = ps.coupledcov(chans[0], chans[1], ws, sp, rt, lmin=2).parent
-        monkeypatch.delenv("PSB200_KERNEL")
+        fn = lambda: ps.coupledcov(chans[0], chans[1], ws, sp, rt, lmin=2).parent
+        A = run(fn, None)
         _, S = _oracle_cov(oracle, ps, chans[0] + chans[1], ws, sp, rt, 2, 200)
-        assert parity_worst(A, B, S) <= 1.0, chans
+        for which in ("v3", "v2", "v1"):
+            assert parity_worst(A, run(fn, which), S) <= 1.0, (chans, which)
 
 
 def test_fused_master_call(ps, oracle):
