@@ -163,16 +163,18 @@ int kernel_version()
     return 4;
 }
 
-// PSB200_TRACE=1: per-phase wall-clock of the host-level calls on stderr (adds stream syncs)
-bool trace_on()
+// PSB200_TRACE=1: wall-clock of the host-level calls per band on stderr (syncs only where the call syncs anyway);
+// PSB200_TRACE=2: also every phase of every launch (adds a stream sync per phase: serialises the sub-bands, so the
+// totals of that mode say nothing about overlap)
+int trace_level()
 {
     const char* e = getenv("PSB200_TRACE");
-    return e && *e && *e != '0';
+    return (e && *e) ? atoi(e) : 0;
 }
 struct Trace {
     bool on;
     std::chrono::steady_clock::time_point t0;
-    Trace() : on(trace_on()), t0(std::chrono::steady_clock::now()) {}
+    explicit Trace(int level = 1) : on(trace_level() >= level), t0(std::chrono::steady_clock::now()) {}
     void mark(const char* what, int dev, cudaStream_t st)
     {
         if (!on) return;
@@ -302,7 +304,7 @@ int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, int nr, cudaSt
     // drained: lists of other devices may be in use by their own worker threads)
     size_t mine = 0;
     for (auto& kv : g_blocks) if (std::get<0>(kv.first) == dev) ++mine;
-    if (mine >= 96) {
+    if (mine >= 1024) {            // 16 sub-bands x a dozen jobs x a few sizes; a list is a few hundred KB at most
         auto old = g_blocks.end();
         for (auto jt = g_blocks.begin(); jt != g_blocks.end(); ++jt)
             if (std::get<0>(jt->first) == dev && (old == g_blocks.end() || jt->second.stamp < old->second.stamp)) old = jt;
@@ -377,7 +379,7 @@ int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
-    Trace tr;
+    Trace tr(2);
     tr.mark("  (inputs uploaded)", dev, st);
     DevTables* t = nullptr;
     if (int rc = ensure_tables(dev, A.lmax, st, &t)) return rc;
@@ -506,7 +508,7 @@ struct DeviceScratch {
     cudaStream_t stream2 = nullptr;         // odd sub-bands of a host-level call (consecutive sub-bands overlap their tails)
     cudaStream_t copy_stream = nullptr;     // D2H of finished column bands, overlapped with compute
     cudaEvent_t ev_in = nullptr;            // inputs of the call are on the device
-    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev[32] = {};
 };
 DeviceScratch g_scratch[16];
 
@@ -652,8 +654,10 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
             if (int rc = scratch_reserve(g, o, (size_t)nb * N)) return rc;
         // sub-bands: each is a complete band of its own (L-shaped region), so its copies can start
         // while the next sub-band computes
-        int nsub = nb >= 4096 ? 8 : (nb >= 2048 ? 4 : (nb >= 512 ? 2 : 1));
-        if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(16, atoi(e)));
+        // MEASURED (1 GPU, lmax 6143, e2e ms per bench step over the 89.0 ms of the resident kernels): 4 sub-bands 104.1,
+        // 8: 99.3, 16: 96.3 -- what a call exposes is the delivery of its last pieces, which shrinks with the piece
+        int nsub = nb >= 4096 ? 16 : (nb >= 2048 ? 8 : (nb >= 512 ? 4 : (nb >= 128 ? 2 : 1)));
+        if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(32, atoi(e)));
         const std::vector<int> sub = split_rows(a, b, hj.lmax, hj.lenW, nsub);
         const int ns = (int)sub.size() - 1;
         std::vector<size_t> toff(ns + 1, 0);             // one transposed block row per (sub-band, output)

@@ -14,4 +14,7 @@ step "trace TT ngpus=2"
 timeout 120 python tools/e2e_probe.py 6143 2 0 > gpurun_out/r02_trace_n2_tt.log 2>&1; tail -40 gpurun_out/r02_trace_n2_tt.log
 step "trace EEBB ngpus=2"
 timeout 120 python tools/e2e_probe.py 6143 2 4 > gpurun_out/r02_trace_n2_eebb.log 2>&1; tail -24 gpurun_out/r02_trace_n2_eebb.log
+step "1-GPU e2e with 32 sub-bands"
+PSB200_NSUB=32 timeout 200 python bench.py --no-cpu --no-extra > gpurun_out/r02_2gpu_bench_n1_nsub32.json 2> /dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/r02_2gpu_bench_n1_nsub32.json').read().strip().splitlines()[-1]); print('nsub32 ms/step', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2))"
 step "done"
