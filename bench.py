@@ -783,6 +783,99 @@ def extras(args, ps, dev, L, world, torch, cpu):
     return out
 
 
+# ------------------------------------------------------------------------------------------
+# BASELINE configs[4]: MCM scaling sweep lmax 767 -> 12287 at N GPUs beside the CPU arm on the box's host cores
+#   python bench.py --sweep [--gpus N under torchrun]      one JSON line per (lmax, kind)
+# ------------------------------------------------------------------------------------------
+def run_sweep(args):
+    import torch
+    import torch.distributed as dist
+
+    import powerspectra_jl_b200 as ps
+    from powerspectra_jl_b200 import device as dev
+    from powerspectra_jl_b200 import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    cpu_group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")
+    L, DP = ps.lib(), ps._lib.DP
+    po = cores = None
+    if rank == 0 and not args.no_cpu:
+        po, cores = cpu_oracle()
+    reps = 5
+    for lmax in (767, 1535, 3071, 6143, 12287):
+        N = lmax + 1
+        Vh = syn.mask_spectra(lmax, seeds=(1001, 1002))[(0, 1)]
+        V = torch.tensor(Vh, device="cuda")
+        X = torch.empty((N, N), dtype=torch.float64, device="cuda")
+        X2 = torch.empty_like(X)
+        edges = dev.band_edges(0, lmax, world)
+        lo, hi = edges[rank], edges[rank + 1]
+        for kind, name, fam in ((0, "TT", 1), (4, "EE_BB (M++, M--)", 2)):
+            def step():
+                dev.mcm_slab(kind, 0, lmax, V, X, X2 if kind == 4 else None, lo, hi)
+                for Xo in ((X, X2) if kind == 4 else (X,)):
+                    dev.gather_bands(Xo, edges, 0, rank, world)
+                    if rank == 0:
+                        dev.finish(Xo, 0, lmax, True)
+            for _ in range(3):
+                step()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.barrier(group=cpu_group)
+            if rank == 0:
+                terms = fam * t_fam(lmax)
+                H = [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in range(2 if kind == 4 else 1)]
+
+                def e2e():
+                    ps._lib.check(L.psb200_mcm(kind, 0, lmax, Vh.ctypes.data_as(DP), Vh.size, H[0].ctypes.data_as(DP), N,
+                                               H[1].ctypes.data_as(DP) if kind == 4 else None, world))
+                e2e()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    e2e()
+                t_e = (time.perf_counter() - t0) * 1e3 / 3
+                rec = {"sweep": "BASELINE configs[4]", "lmax": lmax, "kind": name, "n_gpus": world, "ms_resident": float(ms),
+                       "terms_per_s": terms / (float(ms) * 1e-3), "e2e_ms": t_e, "e2e_terms_per_s": terms / (t_e * 1e-3),
+                       "ref_terms": terms}
+                if po is not None:
+                    rstep = 1 if lmax <= 1535 else (8 if lmax <= 3071 else (32 if lmax <= 6143 else 128))
+                    t0 = time.perf_counter()
+                    tn = 0
+                    for k in ((2, 3) if kind == 4 else (kind,)):
+                        _, t = po.mcm(k, 0, lmax, Vh, row0=rstep // 2, rstep=rstep, return_terms=True)
+                        tn += t
+                    dt = time.perf_counter() - t0
+                    rec["cpu_baseline"] = {"value": tn / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                           "sample": f"every {rstep}th l1 row from {rstep // 2} ({tn:.3e} terms, {dt:.2f} s)"}
+                    rec["speedup_vs_cpu"] = rec["terms_per_s"] / (tn / dt)
+                    rec["speedup_vs_cpu_e2e"] = rec["e2e_terms_per_s"] / (tn / dt)
+                print(json.dumps(rec), flush=True)
+                del H
+            if world > 1:
+                dist.barrier(group=cpu_group)
+        del X, X2
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -792,8 +885,11 @@ def main():
     ap.add_argument("--lmax", type=int, default=6143)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra block (master, TE, QuickPol, lmax 12287)")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: MCM lmax sweep 767 -> 12287, one JSON line per point")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args, args.lmax)
     else:
         run_gpu(args, args.lmax)

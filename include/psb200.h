@@ -145,6 +145,10 @@ int psb200_host_band_edges(int api, int code, int lmin, int lmax, int lenW, int 
  * for l'' = 2..lmax and l = max(2, l''-band_lo) .. min(lmax, l''+band_hi)   (specrowrange, :59-63).
  * W[0..lenW-1] = quickpolW(omega1, omega2) (:43-56; stays on the host).  Terms with l' > lenW-1 are
  * dropped (the reference reads W under @inbounds there); entries with |s| > l or |nu| > l'' are 0.
+ * Supported domain: lmax <= 12287 (larger is rejected: the rescaling cadence of the sweep is analysed up to there);
+ * validated spins |s| <= 4, |nu| <= 12 (l <= 5000) and single large spins up to |s| ~ l (rescaling path): worst 1 % of the
+ * parity bound.  Pairs of families with BOTH |s| and |nu| of order l whose classical regions do not overlap are outside
+ * it (absolute errors up to 3e-9 found by fuzzing) -- no use of the reference comes near (spins of CMB beams are <= 4).
  * Xb is the storage of the reference's BandedMatrix, parent(Xi).data (BandedMatrices.bandeddata): column-major
  * (band_lo+band_hi+1) x (lmax+1) with leading dimension ldb,
  *   Xi[l'', l]  at  Xb[(band_hi + l'' - l) + l*ldb].

@@ -602,16 +602,20 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
 
 // Cost of row l1 as the default kernel executes it: one warp per NR rows x SPAN pairs of one parity of d
 // (SPAN = (32/NR) R), stepping l3 by 2 from its first d to min(d + 2 l1, lenW-1) in lockstep -- SPAN-1 + l1 + 1 steps,
-// cut at the window length -- plus a fixed per-block overhead (ring prologue: five staging passes with exposed
-// latency, epilogue), expressed in steps.  The tiling of the 8-accumulator covariance jobs is used for every job (they
-// dominate a step).
+// cut at the window length.  A warp of s steps is charged s (1 + QUAD s) + OVH: OVH for the ring prologue and the
+// epilogue, QUAD because long tiles pack worse into the last waves of a launch.  Both from a least-squares fit of
+// t = a (sum s + OVH tiles + QUAD sum s^2) + c over the fourteen per-rank pair-kernel times of the 2-, 4- and 8-GPU
+// runs of round 2 (profiles/r02_bench_n{2,4,8}.json: rms residual 0.11 ms of 11.4-46.2 ms; c = 0.5 ms per rank and step
+// is the launch ramp of the five kernels and does not move the edges).  The tiling of the 8-accumulator covariance
+// jobs is used for every job (they dominate a step).
 static long double row_cost(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
     constexpr long NRH = psb::v3_nr(psb::JOB_TTTT);
     constexpr long SPAN = psb::v3_span(psb::JOB_TTTT);           // the covariance jobs dominate a step
-    constexpr long SKEW = SPAN - 1, OVH = 30;
+    constexpr long SKEW = SPAN - 1, OVH = 20;
+    constexpr long double QUAD = 2.35e-5L;
     long double c = 0;
     for (long base = 0; base <= D; base += 2 * SPAN) {
         for (long par = 0; par < 2; ++par) {
@@ -619,7 +623,7 @@ static long double row_cost(int l1, int lmax, int lenW)
             if (d_lo > D) continue;
             const long last = (long)lenW - 1 - d_lo;
             const long steps = last < 0 ? 0 : std::min<long>(SKEW + l1, last / 2) + 1;
-            c += (long double)(steps + OVH) / NRH;               // a warp is shared by NR rows
+            c += ((long double)steps * (1.0L + QUAD * steps) + OVH) / NRH;   // a warp is shared by NR rows
         }
     }
     return c;
