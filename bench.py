@@ -315,8 +315,15 @@ def run_gpu(args, lmax):
             for k, d in inp.items() if k in {j[0] for j in JOBS}}
     to_dev = lambda d: {kk: (v.cuda(non_blocking=True) if torch.is_tensor(v) else [x.cuda(non_blocking=True) for x in v])
                         for kk, v in d.items()}
-    edges = dev.band_edges(0, lmax, world)
-    lo, hi = edges[rank], edges[rank + 1]
+    # folded split: rank r owns pieces r and 2 world - 1 - r of a 2 world-way kernel-cost split, launched as one tile list
+    # (PSB200_BENCH_SPLIT=contiguous: one contiguous band per rank, the round-1 scheme)
+    if os.environ.get("PSB200_BENCH_SPLIT") == "contiguous" and world > 1:
+        e1 = dev.band_edges(0, lmax, world)
+        owners = [[(e1[r], e1[r + 1])] for r in range(world)]
+    else:
+        owners = dev.folded_bands(0, lmax, world)
+    mine = owners[rank]
+    edges = [list(b) for bands in owners for b in bands]      # reported in config.band_edges
 
     # output buffers: full matrix on every rank (N^2 x 8 B = 302 MB each at lmax 6143)
     outs = {}
@@ -347,10 +354,10 @@ def run_gpu(args, lmax):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             if api == "mcm":
-                dev.mcm_slab(code, 0, lmax, a["V"], X[0], X[1] if len(X) > 1 else None, lo, hi)
+                dev.mcm_slab(code, 0, lmax, a["V"], X[0], X[1] if len(X) > 1 else None, bands=mine)
             else:
-                dev.cov_slab(code, 0, lmax, a["sp"], a["rt"], a["W"], X[0], lo, hi)
-            launches["n"] += 2 + (1 if (name in SPIN2_JOBS and lo < 2) else 0)   # v3_prep_w + pair_kernel_v4 (+ low_rows_kernel)
+                dev.cov_slab(code, 0, lmax, a["sp"], a["rt"], a["W"], X[0], bands=mine)
+            launches["n"] += 2 + (1 if (name in SPIN2_JOBS and mine[0][0] < 2) else 0)   # v3_prep_w + pair_kernel_v4 (+ low_rows_kernel)
             if record:
                 e1.record()
                 kernel_events.append((name, e0, e1))
@@ -359,7 +366,7 @@ def run_gpu(args, lmax):
             with torch.cuda.stream(comm):
                 comm.wait_event(done)
                 for k, Xo in enumerate(X):
-                    dev.gather_bands(Xo, edges, 0, rank, world)
+                    dev.gather_slabs(Xo, owners, 0, rank)
                     if rank == 0:
                         dev.finish(Xo, 0, lmax, api == "mcm")
                         launches["n"] += 1
@@ -505,12 +512,13 @@ def run_gpu(args, lmax):
         peak = dev.dfma_peak(1 << 14) / 1e12                     # TFLOP/s, 2 flops per DFMA lane-instruction
         issue_peak = peak * 1e12 / 2.0                           # FP64 lane-instructions per second
         sass, sass_src = sass_counts(ps._lib.LIB_PATH)
-        band_tfam = t_fam(lmax, lo, hi)
+        band_tfam = sum(t_fam(lmax, lo, hi) for lo, hi in mine)
         kern = {}
         for job in JOBS:
             name, api, code = job[0], job[1], job[2]
             lenW = inp[name]["V"].size if api == "mcm" else inp[name]["W"][0].size
-            st = job_stats(L, api, code, lmax, lenW, lo, hi)
+            parts = [job_stats(L, api, code, lmax, lenW, lo, hi) for lo, hi in mine]
+            st = {k: sum(p[k] for p in parts) for k in parts[0]}
             sc = sass[name]
             t = mean_ms[name] * 1e-3
             kern[name] = {
@@ -528,7 +536,8 @@ def run_gpu(args, lmax):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload(lmax),
-                       "parallelism": f"l1 row bands x{world}, NCCL gather to rank 0" if world > 1 else "1 GPU",
+                       "parallelism": (f"l1 row bands x{world} (folded: a low and a high band per rank, one tile list), "
+                                       "NCCL gather to rank 0") if world > 1 else "1 GPU",
                        "band_edges": edges, "pair_kernel_ms_per_rank": per_rank_ms,
                        "l2": "outputs (6 x N^2 x 8 B = 1.8 GB per step) exceed L2; inputs are O(lmax) vectors",
                        "kernel": os.environ.get("PSB200_KERNEL", "default")},

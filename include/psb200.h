@@ -124,6 +124,19 @@ int psb200_cov_dev(int block, int lmin, int lmax,
                    double* dX, long ldX,
                    int row_lo, int row_hi, void* stream);
 
+/* The same over SEVERAL disjoint row bands in ONE launch: bands[2k], bands[2k+1] = [lo, hi) of band k, 1 <= nbands <= 4.
+ * What a rank of the folded multi-GPU split passes -- a low band (many short l3 families) and a high band (few long
+ * ones) merged into one heaviest-first tile list, so that every rank fills the tail of its long tiles with short ones. */
+int psb200_mcm_dev_bands(int kind, int lmin, int lmax, const double* dV, int nV,
+                         double* dX, long ldX, double* dX2,
+                         const int* bands, int nbands, void* stream);
+int psb200_cov_dev_bands(int block, int lmin, int lmax,
+                         const double* const* d_spectra, int nspec,
+                         const double* const* d_ratios, int nratio,
+                         const double* const* d_W, int nW, int lenW,
+                         double* dX, long ldX,
+                         const int* bands, int nbands, void* stream);
+
 int psb200_finish_dev(double* dX, long ldX, int lmin, int lmax, int scale, void* stream);
 
 /* Work-balanced contiguous l1 bands: edges[0..nbands] with edges[0] = lmin, edges[nbands] = lmax+1.

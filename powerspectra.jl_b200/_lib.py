@@ -32,6 +32,11 @@ PROTOTYPES = {
     "psb200_cov_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
                                  C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                  C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
+    "psb200_mcm_dev_bands": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_long,
+                                       C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
+    "psb200_cov_dev_bands": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                       C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                       C.c_void_p, C.c_long, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "psb200_finish_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "psb200_band_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "psb200_host_band_edges": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)]),

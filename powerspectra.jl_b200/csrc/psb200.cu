@@ -263,8 +263,8 @@ int ensure_tables(int dev, int lmax, cudaStream_t st, DevTables** out)
 // Block list of one launch: (first l1, d_lo) tiles of the band's upper triangle, heaviest first
 // (longest-processing-time order keeps the 148 SMs balanced to the last wave).  A tile is nr consecutive rows
 // x (32/nr) r pairs of each: consecutive d (ds = 1) or d of one parity (ds = 2, (0,0,0)-recurrence jobs).
-struct BlockList { int2* d = nullptr; int n = 0; unsigned long stamp = 0; };
-typedef std::tuple<int, int, int, int, int, int, int, int> BlockKey;     // dev, lmax, lenW, row_lo, row_hi, d stride, pairs per thread, rows per warp
+struct BlockList { int4* d = nullptr; int n = 0; unsigned long stamp = 0; };
+typedef std::tuple<int, int, int, std::vector<int>, int, int, int> BlockKey;     // dev, lmax, lenW, bands (lo, hi, lo, hi ...), d stride, pairs per thread, rows per warp
 std::map<BlockKey, BlockList> g_blocks;
 unsigned long g_block_stamp = 0;
 
@@ -291,14 +291,19 @@ void for_each_tile(int lmax, int lenW, int row_lo, int row_hi, int ds, int r, in
 int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, int nr, cudaStream_t st, BlockList* out)
 {
     std::lock_guard<std::mutex> lk(g_tab_mutex);
-    const BlockKey key(dev, A.lmax, A.lenW, A.row_lo, A.row_hi, ds, r, nr);
+    std::vector<int> bands{A.row_lo, A.row_hi};
+    for (int k = 0; k < A.nxb; ++k) { bands.push_back(A.xb[2 * k]); bands.push_back(A.xb[2 * k + 1]); }
+    const BlockKey key(dev, A.lmax, A.lenW, bands, ds, r, nr);
     auto it = g_blocks.find(key);
     if (it != g_blocks.end()) { it->second.stamp = ++g_block_stamp; *out = it->second; return OK; }
-    std::vector<std::pair<long, int2>> v;
-    for_each_tile(A.lmax, A.lenW, A.row_lo, A.row_hi, ds, r, nr,
-                  [&](int l1, int d_lo, long steps) { v.push_back({steps, make_int2(l1, d_lo)}); });
-    std::stable_sort(v.begin(), v.end(), [](const std::pair<long, int2>& a, const std::pair<long, int2>& b) { return a.first > b.first; });
-    std::vector<int2> h(v.size());
+    // tiles of all bands of the launch in ONE list, heaviest first: a rank that owns a low and a high band (folded
+    // split) fills the tail of its long tiles with its short ones
+    std::vector<std::pair<long, int4>> v;
+    for (size_t b = 0; b + 1 < bands.size(); b += 2)
+        for_each_tile(A.lmax, A.lenW, bands[b], bands[b + 1], ds, r, nr,
+                      [&](int l1, int d_lo, long steps) { v.push_back({steps, make_int4(l1, d_lo, bands[b + 1], 0)}); });
+    std::stable_sort(v.begin(), v.end(), [](const std::pair<long, int4>& a, const std::pair<long, int4>& b) { return a.first > b.first; });
+    std::vector<int4> h(v.size());
     for (size_t i = 0; i < v.size(); ++i) h[i] = v[i].second;
     // LRU per device (a list is only ever evicted by a call on the device that owns it, after that device has
     // drained: lists of other devices may be in use by their own worker threads)
@@ -316,9 +321,9 @@ int ensure_blocks(int dev, const psb::PairArgs& A, int ds, int r, int nr, cudaSt
     bl.n = (int)h.size();
     bl.stamp = ++g_block_stamp;
     if (bl.n) {
-        CUDA_TRY(cudaMalloc(&bl.d, h.size() * sizeof(int2)));
+        CUDA_TRY(cudaMalloc(&bl.d, h.size() * sizeof(int4)));
         // on the launching stream, drained before the pageable host vector dies (see ensure_tables)
-        CUDA_TRY(cudaMemcpyAsync(bl.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(bl.d, h.data(), h.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     g_blocks[key] = bl;
@@ -355,25 +360,39 @@ int wp_reserve(int dev, cudaStream_t st, size_t n, double** out)
 template <int JOB>
 int launch_job(const psb::PairArgs& A_in, cudaStream_t st)
 {
-    if (A_in.row_hi - A_in.row_lo <= 0) return OK;
-    psb::PairArgs A = A_in;
-    if constexpr (psb::job_has_spin2(JOB)) {
-        // rows l1 < 2 of the spin-2 jobs (true symbol 0; what the reference's family routine yields): psb200_lowrows.cuh
-        if (A.row_lo < 2) {
-            const int nlow = std::min(A.row_hi, 2) - A.row_lo;
-            dim3 grid((A.lmax - A.row_lo + 1 + 127) / 128, nlow);
-            psb::low_rows_kernel<JOB><<<grid, 128, 0, st>>>(A);
-            CUDA_TRY(cudaGetLastError());
-            A.row_lo = std::min(A.row_hi, 2);
+    // the bands of the launch: [row_lo, row_hi) and the extra ones, empty ones dropped
+    std::vector<int> bands;
+    auto add_band = [&](int lo, int hi) {
+        if constexpr (psb::job_has_spin2(JOB)) {
+            // rows l1 < 2 of the spin-2 jobs (true symbol 0; what the reference's family routine yields): psb200_lowrows.cuh
+            if (lo < 2 && hi > lo) {
+                psb::PairArgs L = A_in;
+                L.row_lo = lo; L.row_hi = hi; L.nxb = 0;
+                const int nlow = std::min(hi, 2) - lo;
+                dim3 grid((L.lmax - lo + 1 + 127) / 128, nlow);
+                psb::low_rows_kernel<JOB><<<grid, 128, 0, st>>>(L);
+                lo = std::min(hi, 2);
+            }
         }
-    }
-    const int rows = A.row_hi - A.row_lo;
-    if (rows <= 0) return OK;
+        if (hi > lo) { bands.push_back(lo); bands.push_back(hi); }
+    };
+    add_band(A_in.row_lo, A_in.row_hi);
+    for (int k = 0; k < A_in.nxb; ++k) add_band(A_in.xb[2 * k], A_in.xb[2 * k + 1]);
+    CUDA_TRY(cudaGetLastError());
+    if (bands.empty()) return OK;
+    psb::PairArgs A = A_in;
+    A.row_lo = bands[0]; A.row_hi = bands[1];
+    A.nxb = (int)bands.size() / 2 - 1;
+    for (size_t k = 2; k < bands.size(); ++k) A.xb[k - 2] = bands[k];
     if (kernel_version() == 1) {
-        const int maxcols = A.lmax - A.row_lo + 1;
-        dim3 grid((maxcols + psb::V1_THREADS - 1) / psb::V1_THREADS, rows);
-        psb::pair_kernel_v1<JOB><<<grid, psb::V1_THREADS, 0, st>>>(A);
-        CUDA_TRY(cudaGetLastError());
+        for (size_t b = 0; b + 1 < bands.size(); b += 2) {          // the simple kernel runs one grid per band
+            psb::PairArgs B = A;
+            B.row_lo = bands[b]; B.row_hi = bands[b + 1]; B.nxb = 0;
+            const int maxcols = B.lmax - B.row_lo + 1;
+            dim3 grid((maxcols + psb::V1_THREADS - 1) / psb::V1_THREADS, B.row_hi - B.row_lo);
+            psb::pair_kernel_v1<JOB><<<grid, psb::V1_THREADS, 0, st>>>(B);
+            CUDA_TRY(cudaGetLastError());
+        }
         return OK;
     }
     int dev = 0;
@@ -1049,6 +1068,54 @@ int psb200_cov_dev(int block, int lmin, int lmax, const double* const* dsp, int 
     if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
     psb::PairArgs A{};
     A.lmin = lmin; A.lmax = lmax; A.lenW = lenW; A.row_lo = row_lo; A.row_hi = row_hi; A.ld = ldX;
+    for (int k = 0; k < nW; ++k) { if (!dW[k]) return fail(ERR_ARG, "W[%d] is null", k); A.W[k] = dW[k]; }
+    for (int k = 0; k < nspec; ++k) { if (!dsp[k]) return fail(ERR_ARG, "spectra[%d] is null", k); A.sp[k] = dsp[k]; }
+    for (int k = 0; k < nratio; ++k) { if (!drt[k]) return fail(ERR_ARG, "ratios[%d] is null", k); A.rt[k] = drt[k]; }
+    A.out0 = dX;
+    return launch_any(kCovJob[block], A, (cudaStream_t)stream);
+}
+
+// Device-level calls over SEVERAL row bands in one launch (bands[2k], bands[2k+1] = [lo, hi) of band k, nbands <= 4,
+// disjoint): what a rank of the folded multi-GPU split passes -- a low and a high band, so that every rank owns short
+// and long tiles.
+static int fill_bands(psb::PairArgs& A, int lmin, int lmax, long ld, const int* bands, int nbands)
+{
+    if (!bands || nbands < 1 || nbands > 4) return fail(ERR_ARG, "need 1..4 row bands");
+    for (int k = 0; k < nbands; ++k)
+        if (int rc = check_common(lmin, lmax, ld, bands[2 * k], bands[2 * k + 1])) return rc;
+    A.row_lo = bands[0]; A.row_hi = bands[1];
+    A.nxb = nbands - 1;
+    for (int k = 2; k < 2 * nbands; ++k) A.xb[k - 2] = bands[k];
+    return OK;
+}
+
+int psb200_mcm_dev_bands(int kind, int lmin, int lmax, const double* dV, int nV, double* dX, long ldX, double* dX2,
+                         const int* bands, int nbands, void* stream)
+{
+    if (kind < 0 || kind > 4) return fail(ERR_ARG, "unknown mcm kind %d", kind);
+    if (!dV || nV < 1 || !dX) return fail(ERR_ARG, "null / empty buffer");
+    if (kind == 4 && !dX2) return fail(ERR_ARG, "kind 4 needs a second output");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::PairArgs A{};
+    A.lmin = lmin; A.lmax = lmax; A.lenW = nV; A.ld = ldX;
+    if (int rc = fill_bands(A, lmin, lmax, ldX, bands, nbands)) return rc;
+    A.W[0] = dV; A.out0 = dX; A.out1 = dX2;
+    return launch_any(kMcmJob[kind], A, (cudaStream_t)stream);
+}
+
+int psb200_cov_dev_bands(int block, int lmin, int lmax, const double* const* dsp, int nspec,
+                         const double* const* drt, int nratio, const double* const* dW, int nW, int lenW,
+                         double* dX, long ldX, const int* bands, int nbands, void* stream)
+{
+    if (block < 0 || block > 6) return fail(ERR_ARG, "unknown covariance block %d", block);
+    if (nspec != kCovNeedSp[block] || nratio != kCovNeedRt[block] || nW != kCovNeedW[block])
+        return fail(ERR_ARG, "block %d takes %d spectra, %d ratios, %d W (got %d, %d, %d)", block,
+                    kCovNeedSp[block], kCovNeedRt[block], kCovNeedW[block], nspec, nratio, nW);
+    if (!dX || lenW < 1 || !dsp || !dW || (nratio && !drt)) return fail(ERR_ARG, "null / empty buffer");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::PairArgs A{};
+    A.lmin = lmin; A.lmax = lmax; A.lenW = lenW; A.ld = ldX;
+    if (int rc = fill_bands(A, lmin, lmax, ldX, bands, nbands)) return rc;
     for (int k = 0; k < nW; ++k) { if (!dW[k]) return fail(ERR_ARG, "W[%d] is null", k); A.W[k] = dW[k]; }
     for (int k = 0; k < nspec; ++k) { if (!dsp[k]) return fail(ERR_ARG, "spectra[%d] is null", k); A.sp[k] = dsp[k]; }
     for (int k = 0; k < nratio; ++k) { if (!drt[k]) return fail(ERR_ARG, "ratios[%d] is null", k); A.rt[k] = drt[k]; }

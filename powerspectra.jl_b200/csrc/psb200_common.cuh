@@ -53,6 +53,8 @@ struct PairArgs {
     int lmin, lmax;        // rows / columns kept
     int lenW;              // valid length of every window vector (l3 sum stops at lenW-1)
     int row_lo, row_hi;    // l1 band [row_lo, row_hi)
+    int nxb;               // further bands of the same launch (host side only: the tile list carries each tile's band end)
+    int xb[6];             // [lo, hi) of up to three further bands
     long ld;               // leading dimension of the outputs
     const double* W[8];    // window spectra, 0-based in l3
     const double* sp[4];   // signal spectra, 0-based in l

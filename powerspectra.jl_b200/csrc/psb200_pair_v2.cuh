@@ -141,7 +141,7 @@ struct V2Tables {
     const double* INV;    // 1/n, INV[0] = 0
     const double* gam;    // binom(2n,n)/4^n
     int nS;
-    const int2* blocks;   // (l1, d_lo), heaviest first
+    const int4* blocks;   // (first l1, d_lo, end of the row band the tile belongs to, -), heaviest first
     const double* Wp;     // [row j][v2_nqp columns] = (2j+1) W_q[j] / 4pi, zero rows past lenW
 };
 
@@ -207,15 +207,15 @@ __global__ void __launch_bounds__(V2_THREADS, v2_min_blocks(JOB)) pair_kernel_v2
     double* shF = shW + V2_TC * NQP;                      // start values f22(d) | g(d)
     double* shH = shF + 32 * R;                           // start values f00(d)     (F02 only)
 
-    const int2 blk = T.blocks[blockIdx.x];
-    const int l1_first = blk.x, d_lo = blk.y;
+    const int4 blk = T.blocks[blockIdx.x];
+    const int l1_first = blk.x, d_lo = blk.y, band_hi = blk.z;
     const int tid = threadIdx.x, lane = tid & 31;
     const int rg = lane / LPR;                            // my row group
     const int l1 = l1_first + rg;                         // my row
     const int L = 2 * l1 + 1;
     const int e = (lane % LPR) * R;                       // pair offset of my first pair inside the window
-    const int dmax = (l1 < A.row_hi) ? A.lmax - l1 : -1;  // last valid d of my row (rows past the band: none)
-    const int l1_last = min(l1_first + NR, A.row_hi) - 1; // longest family of the warp
+    const int dmax = (l1 < band_hi) ? A.lmax - l1 : -1;  // last valid d of my row (rows past the band: none)
+    const int l1_last = min(l1_first + NR, band_hi) - 1; // longest family of the warp
     // last step: the last pair (offset SPAN-1) of the last row finishes its family, or the window spectrum ends
     const int tau_end = (A.lenW - 1 - d_lo < 0) ? -1
                       : min(SPAN - 1 + (2 * l1_last) / DS, (A.lenW - 1 - d_lo) / DS);   // block-uniform

@@ -125,7 +125,7 @@ struct V3Tables {
     const double* igam;   // 1/g(n)
     const double* INV;    // 1/n, INV[0] = 0
     int nS;               // length of all three
-    const int2* blocks;   // (first l1, d_lo), heaviest first
+    const int4* blocks;   // (first l1, d_lo, end of the row band the tile belongs to, -), heaviest first
     const double* Wp;     // [row j][v3_nqp columns] = (2j+1) W_q[j] / 4pi, zero rows past lenW
 };
 
@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v3(const P
     double* shV = shU + NR * TSTR;                     // rising index:  PV | QV | (PV, QV)
     double* shW = shV + NR * TSTR;                     // [TC][RPS][NQP]   (TSTR is even: 16-byte aligned)
 
-    const int2 blk = T.blocks[blockIdx.x];
-    const int l1_first = blk.x, d_lo = blk.y;
+    const int4 blk = T.blocks[blockIdx.x];
+    const int l1_first = blk.x, d_lo = blk.y, band_hi = blk.z;
     const int tid = threadIdx.x;
     const int rg = tid / LPR;                          // my row group
     const int l1 = l1_first + rg;                      // my row
     const int e = (tid % LPR) * R;                     // offset of my first pair inside the window
-    const int dmax = (l1 < A.row_hi) ? A.lmax - l1 : -1;   // last valid d of my row (rows past the band: none)
-    const int l1_last = min(l1_first + NR, A.row_hi) - 1;  // longest family of the warp
+    const int dmax = (l1 < band_hi) ? A.lmax - l1 : -1;   // last valid d of my row (rows past the band: none)
+    const int l1_last = min(l1_first + NR, band_hi) - 1;  // longest family of the warp
     // last step: the last pair (offset SPAN-1) of the last row finishes its family, or the window spectrum ends
     const int tau_end = (A.lenW - 1 - d_lo < 0) ? -1 : min(SPAN - 1 + l1_last, (A.lenW - 1 - d_lo) / 2);
     if (d_lo > A.lmax - l1_first || tau_end < 0) {     // nothing to sum: the stored values are exact zeros

@@ -73,7 +73,7 @@ __host__ __device__ constexpr int v4_smem_doubles(int job)
 struct V4Tables {
     const double *G0, *G1, *G2, *H0, *H1;   // element 0 of each sequence; [-V4_PAD, 0) are zeros
     int nS;
-    const int2* blocks;                      // (first l1, d_lo), heaviest first
+    const int4* blocks;                      // (first l1, d_lo, end of the tile's row band, -), heaviest first
     const double* Wp;                        // [row j][v3_nqp columns], see v3_prep_w
 };
 
@@ -105,14 +105,14 @@ __global__ void __launch_bounds__(32, v3_min_blocks(JOB)) pair_kernel_v4(const P
     double* shW = shV + NR * TSTR;                     // [WR][RPS][NQP]
     double* raw = shW + WR * ROWD;                     // raw factors: [slot][NTAB][2 + 2 NR][32]
 
-    const int2 blk = T.blocks[blockIdx.x];
-    const int l1_first = blk.x, d_lo = blk.y;
+    const int4 blk = T.blocks[blockIdx.x];
+    const int l1_first = blk.x, d_lo = blk.y, band_hi = blk.z;
     const int tid = threadIdx.x;
     const int rg = tid / LPR, eR = tid % LPR;          // my row group; my pair offset / R
     const int l1 = l1_first + rg;
     const int e = eR * R;
-    const int dmax = (l1 < A.row_hi) ? A.lmax - l1 : -1;
-    const int l1_last = min(l1_first + NR, A.row_hi) - 1;
+    const int dmax = (l1 < band_hi) ? A.lmax - l1 : -1;
+    const int l1_last = min(l1_first + NR, band_hi) - 1;
     const int tau_end = (A.lenW - 1 - d_lo < 0) ? -1 : min(SPAN - 1 + l1_last, (A.lenW - 1 - d_lo) / 2);
     if (d_lo > A.lmax - l1_first || tau_end < 0) {     // nothing to sum: the stored values are exact zeros
         if (d_lo <= A.lmax - l1_first) {

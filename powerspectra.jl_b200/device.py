@@ -52,9 +52,10 @@ def _vptrs(ts):
 
 
 def mcm_slab(kind, lmin, lmax, V: torch.Tensor, X: torch.Tensor, X2: torch.Tensor | None = None,
-             row_lo=None, row_hi=None):
+             row_lo=None, row_hi=None, bands=None):
     """Stage 1 for one band: X is the FULL (N, N) buffer (X[l1-lmin, l2-lmin], torch row-major =
-    the column-major result's transpose) or any view whose data_ptr is row `lmin` of it."""
+    the column-major result's transpose) or any view whose data_ptr is row `lmin` of it.
+    bands = [(lo, hi), ...] (up to 4, disjoint): several bands in ONE launch (psb200_mcm_dev_bands; folded split)."""
     kind = MCM_KINDS.get(kind, kind)
     N = lmax - lmin + 1
     row_lo = lmin if row_lo is None else row_lo
@@ -65,8 +66,12 @@ def mcm_slab(kind, lmin, lmax, V: torch.Tensor, X: torch.Tensor, X2: torch.Tenso
     if X2 is not None:
         _require_cuda(X2)
         x2 = C.c_void_p(X2.data_ptr())
-    rc = _lib.lib().psb200_mcm_dev(kind, lmin, lmax, C.c_void_p(V.data_ptr()), V.numel(),
-                                   C.c_void_p(X.data_ptr()), N, x2, row_lo, row_hi, _stream_ptr())
+    if bands is not None:
+        rc = _lib.lib().psb200_mcm_dev_bands(kind, lmin, lmax, C.c_void_p(V.data_ptr()), V.numel(),
+                                             C.c_void_p(X.data_ptr()), N, x2, _bands(bands), len(bands), _stream_ptr())
+    else:
+        rc = _lib.lib().psb200_mcm_dev(kind, lmin, lmax, C.c_void_p(V.data_ptr()), V.numel(),
+                                       C.c_void_p(X.data_ptr()), N, x2, row_lo, row_hi, _stream_ptr())
     _lib.check(rc)
 
 
@@ -83,7 +88,7 @@ def master_slab(lmin, lmax, V_TT, V_TP, V_PT, V_PP, Xs, row_lo=None, row_hi=None
     _lib.check(rc)
 
 
-def cov_slab(block, lmin, lmax, spectra, ratios, W, X: torch.Tensor, row_lo=None, row_hi=None):
+def cov_slab(block, lmin, lmax, spectra, ratios, W, X: torch.Tensor, row_lo=None, row_hi=None, bands=None):
     block = COV_BLOCKS.get(block, block)
     N = lmax - lmin + 1
     row_lo = lmin if row_lo is None else row_lo
@@ -93,9 +98,14 @@ def cov_slab(block, lmin, lmax, spectra, ratios, W, X: torch.Tensor, row_lo=None
     for t in list(spectra) + list(ratios):      # the C entry point takes no lengths for these: l = 0..lmax is read
         if int(t.numel()) < lmax + 1:
             raise ValueError(f"spectrum / ratio vector of {int(t.numel())} entries, need lmax+1 = {lmax + 1}")
-    rc = _lib.lib().psb200_cov_dev(block, lmin, lmax, _vptrs(spectra), len(spectra), _vptrs(ratios), len(ratios),
-                                   _vptrs(W), len(W), lenW, C.c_void_p(X.data_ptr()), N, row_lo, row_hi,
-                                   _stream_ptr())
+    if bands is not None:
+        rc = _lib.lib().psb200_cov_dev_bands(block, lmin, lmax, _vptrs(spectra), len(spectra), _vptrs(ratios), len(ratios),
+                                             _vptrs(W), len(W), lenW, C.c_void_p(X.data_ptr()), N, _bands(bands), len(bands),
+                                             _stream_ptr())
+    else:
+        rc = _lib.lib().psb200_cov_dev(block, lmin, lmax, _vptrs(spectra), len(spectra), _vptrs(ratios), len(ratios),
+                                       _vptrs(W), len(W), lenW, C.c_void_p(X.data_ptr()), N, row_lo, row_hi,
+                                       _stream_ptr())
     _lib.check(rc)
 
 
@@ -105,6 +115,44 @@ def finish(X: torch.Tensor, lmin, lmax, scale: bool):
     N = lmax - lmin + 1
     _lib.check(_lib.lib().psb200_finish_dev(C.c_void_p(X.data_ptr()), N, lmin, lmax, 1 if scale else 0,
                                             _stream_ptr()))
+
+
+def _bands(bands):
+    flat = [int(v) for b in bands for v in b]
+    return (C.c_int * len(flat))(*flat)
+
+
+def folded_bands(lmin: int, lmax: int, world: int, lenW: int | None = None):
+    """Folded split for `world` ranks: the rows are cut into 2*world pieces of equal kernel cost and rank r owns pieces
+    r and 2*world-1-r -- a low band (many short tiles) and a high band (few long ones) -- launched as ONE tile list, so
+    every rank packs its last waves with short tiles and errors of the cost model average out.  Returns
+    [[(lo, hi), (lo, hi)] for each rank] (one band per rank when world == 1)."""
+    if world == 1:
+        return [[(lmin, lmax + 1)]]
+    e = band_edges(lmin, lmax, 2 * world, lenW)
+    return [[(e[r], e[r + 1]), (e[2 * world - 1 - r], e[2 * world - r])] for r in range(world)]
+
+
+def gather_slabs(X: torch.Tensor, owners, lmin, rank, group=None):
+    """Send every band slab X[lo-lmin : hi-lmin, :] of `owners` = [[(lo, hi), ...] per rank] to rank 0 (grouped
+    send/recv).  Works for NCCL (cuda) and gloo (cpu)."""
+    import torch.distributed as dist
+    if len(owners) == 1:
+        return
+    ops = []
+    for r, bands in enumerate(owners):
+        if r == 0:
+            continue
+        for lo, hi in bands:
+            if hi <= lo:
+                continue
+            if rank == 0:
+                ops.append(dist.P2POp(dist.irecv, X[lo - lmin:hi - lmin], r, group))
+            elif rank == r:
+                ops.append(dist.P2POp(dist.isend, X[lo - lmin:hi - lmin], 0, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
 
 
 def gather_bands(X: torch.Tensor, edges, lmin, rank, world, group=None):

@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, lmin, lmax, out_path):
+def _worker(rank, world, port, lmin, lmax, out_path, folded=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -35,14 +35,19 @@ def _worker(rank, world, port, lmin, lmax, out_path):
     V = syn.mask_spectra(lmax, seeds=(1001, 1002))[(0, 1)]
     N = lmax - lmin + 1
     edges = dev.band_edges(lmin, lmax, world)
-    lo, hi = edges[rank], edges[rank + 1]
-    # X[l1-lmin, l2-lmin] row-major == the column-major result transposed; stage 1 fills rows of my band
+    owners = dev.folded_bands(lmin, lmax, world) if folded else [[(edges[r], edges[r + 1])] for r in range(world)]
+    # X[l1-lmin, l2-lmin] row-major == the column-major result transposed; stage 1 fills rows of my band(s)
     X = torch.full((N, N), float("nan"), dtype=torch.float64)
     full = po.mcm(0, lmin, lmax, V)                       # oracle: M[l1,l2] = (2 l2+1) Xi
     xi = full / (2.0 * np.arange(lmin, lmax + 1) + 1.0)[None, :]
-    for l1 in range(lo, hi):
-        X[l1 - lmin, l1 - lmin:] = torch.from_numpy(xi[l1 - lmin, l1 - lmin:])
-    dev.gather_bands(X, edges, lmin, rank, world)
+    for lo, hi in owners[rank]:
+        for l1 in range(lo, hi):
+            X[l1 - lmin, l1 - lmin:] = torch.from_numpy(xi[l1 - lmin, l1 - lmin:])
+    if folded:
+        dev.gather_slabs(X, owners, lmin, rank)
+        edges = [lmin, owners[0][0][1]]                   # rank 0's low band ends here
+    else:
+        dev.gather_bands(X, edges, lmin, rank, world)
     if rank == 0:
         # stage 2 (what psb200_finish_dev does on the GPU), in numpy
         Xn = X.numpy()
@@ -64,6 +69,17 @@ def test_band_gather_two_ranks(tmp_path, lmin, lmax):
     err, edge = np.load(out)
     assert err < 1e-15          # (x / s) * s rounding only: every band arrived in the right place
     assert lmin < edge <= lmax          # both ranks own rows
+
+
+@pytest.mark.parametrize("lmin,lmax", [(0, 95), (3, 140)])
+def test_folded_band_gather_two_ranks(tmp_path, lmin, lmax):
+    """The folded split of the N-GPU driver: each rank owns a low and a high band (device.folded_bands), both slabs of
+    every rank reach rank 0 (device.gather_slabs)."""
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(2, _free_port(), lmin, lmax, out, True), nprocs=2, join=True)
+    err, edge = np.load(out)
+    assert err < 1e-15
+    assert lmin < edge < lmax
 
 
 def _qp_worker(rank, world, port, lmax, bl, bh, out_path):

@@ -576,6 +576,12 @@ def test_band_sharding_device_api(ps, oracle):
         assert edges[0] == lmin and edges[-1] == lmax + 1 and all(b >= a for a, b in zip(edges, edges[1:]))
         for a, b in zip(edges[::-1][1:], edges[::-1][:-1]):      # any order
             dev.mcm_slab(kind, lmin, lmax, Vd, X, X2, a, b)
+        # the folded split: two bands per launch (psb200_mcm_dev_bands) must write the very same bits
+        Y = torch.zeros_like(X)
+        Y2 = torch.zeros_like(X) if kind == 4 else None
+        for bands in dev.folded_bands(lmin, lmax, 3):
+            dev.mcm_slab(kind, lmin, lmax, Vd, Y, Y2, bands=bands)
+        assert torch.equal(torch.triu(X), torch.triu(Y)) and (kind != 4 or torch.equal(torch.triu(X2), torch.triu(Y2)))
         dev.finish(X, lmin, lmax, True)
         got = X.cpu().numpy().T                                  # torch row-major == column-major transposed
         if kind == 0:
@@ -586,6 +592,31 @@ def test_band_sharding_device_api(ps, oracle):
                 with oracle.abs_mode():
                     S = oracle.mcm(k, lmin, lmax, V)
                 assert_parity(Gm, oracle.mcm(k, lmin, lmax, V, ld=True), S)
+
+
+def test_cov_bands_device_api(ps):
+    """psb200_cov_dev over the whole matrix == psb200_cov_dev_bands over the folded bands of 4 ranks, bit for bit
+    (TETE: two parities of windows, spin-2 low rows in the first band)."""
+    import torch
+    import bench
+    from powerspectra_jl_b200 import device as dev
+    lmax = 300
+    a = bench.make_inputs(lmax)["TETE"]
+    t = lambda x: torch.tensor(np.ascontiguousarray(x), device="cuda")
+    sp, rt, W = [t(x) for x in a["sp"]], [t(x) for x in a["rt"]], [t(x) for x in a["W"]]
+    N = lmax + 1
+    X = torch.zeros((N, N), dtype=torch.float64, device="cuda")
+    Y = torch.zeros_like(X)
+    dev.cov_slab(3, 0, lmax, sp, rt, W, X)
+    for bands in dev.folded_bands(0, lmax, 4):
+        dev.cov_slab(3, 0, lmax, sp, rt, W, Y, bands=bands)
+    assert torch.equal(torch.triu(X), torch.triu(Y))
+    lib = ps.lib()
+    import ctypes as C
+    bad = (C.c_int * 4)(0, 10, 5, 400)                       # second band beyond lmax
+    rc = lib.psb200_mcm_dev_bands(0, 0, lmax, C.c_void_p(W[0].data_ptr()), N, C.c_void_p(X.data_ptr()), N, None, bad, 2, None)
+    assert rc == 1
+    assert lib.psb200_mcm_dev_bands(0, 0, lmax, C.c_void_p(W[0].data_ptr()), N, C.c_void_p(X.data_ptr()), N, None, bad, 5, None) == 1
 
 
 def test_kernel_cross_checks(ps, oracle, monkeypatch):

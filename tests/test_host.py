@@ -148,6 +148,23 @@ def test_host_band_edges_follow_the_copies(ps):
     assert max(share(tt, g) for g in range(8)) < 0.2 < max(share(kb, g) for g in range(8))
 
 
+def test_folded_bands_partition(ps):
+    """device.folded_bands: every row belongs to exactly one band of exactly one rank; each rank owns a low and a high piece."""
+    from powerspectra_jl_b200 import device as dev
+    for lmin, lmax, world in ((0, 6143, 8), (2, 767, 4), (0, 40, 2), (5, 9, 3), (0, 6143, 1)):
+        owners = dev.folded_bands(lmin, lmax, world)
+        assert len(owners) == world
+        seen = np.zeros(lmax + 1 - lmin, dtype=int)
+        for bands in owners:
+            assert len(bands) == (1 if world == 1 else 2)
+            for lo, hi in bands:
+                assert lmin <= lo <= hi <= lmax + 1
+                seen[lo - lmin:hi - lmin] += 1
+        assert np.all(seen == 1)
+        if world > 1 and lmax - lmin > 8 * world:
+            assert all(b[0][1] <= b[1][0] for b in owners)        # low piece below the high piece
+
+
 def test_band_edges_properties_random(ps):
     """Property test (hypothesis): for any shape the two partitioners return a monotone cover with the right ends,
     no band is empty while rows remain for the later ones only if the cost demands it, and with the reference
