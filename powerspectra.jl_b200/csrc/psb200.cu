@@ -627,7 +627,7 @@ int run_on_device(const HostJob& hj, int dev, int row_lo, int row_hi, double* co
 // runs of round 2 (profiles/r02_bench_n{2,4,8}.json: rms residual 0.11 ms of 11.4-46.2 ms; c = 0.5 ms per rank and step
 // is the launch ramp of the five kernels and does not move the edges).  The tiling of the 8-accumulator covariance
 // jobs is used for every job (they dominate a step).
-static long double row_cost(int l1, int lmax, int lenW)
+static long double row_cost_raw(int l1, int lmax, int lenW)
 {
     const long n = 2L * l1 + 1, D = lmax - l1;                  // family length, last d
     if (lenW <= 0) return (long double)n * (D + 1);              // full families (reference term count)
@@ -648,17 +648,34 @@ static long double row_cost(int l1, int lmax, int lenW)
     return c;
 }
 
+// Row costs are asked for on the critical path of every host-level call (sub-band split, band edges): 2 x 6144 rows x
+// ~50 tiles of long-double arithmetic were 1.4 ms per call at lmax 6143 -- 7 ms of the 10 ms a benchmark step lost
+// end to end against the resident kernels.  One vector per (lmax, lenW), computed once.
+static const std::vector<long double>& row_costs(int lmax, int lenW)
+{
+    static std::mutex m;
+    static std::map<std::pair<int, int>, std::vector<long double>> cache;
+    std::lock_guard<std::mutex> lk(m);
+    auto it = cache.find({lmax, lenW});
+    if (it != cache.end()) return it->second;
+    if (cache.size() > 64) cache.clear();
+    std::vector<long double> c(lmax + 1);
+    for (int l = 0; l <= lmax; ++l) c[l] = row_cost_raw(l, lmax, lenW);
+    return cache.emplace(std::make_pair(lmax, lenW), std::move(c)).first->second;
+}
+
 // cost-balanced split of rows [a, b) into at most nsub consecutive pieces
 static std::vector<int> split_rows(int a, int b, int lmax, int lenW, int nsub)
 {
     std::vector<int> e{a};
     if (nsub <= 1 || b - a < 2 * nsub) { e.push_back(b); return e; }
+    const std::vector<long double>& rc = row_costs(lmax, lenW);
     long double total = 0;
-    for (int l = a; l < b; ++l) total += row_cost(l, lmax, lenW);
+    for (int l = a; l < b; ++l) total += rc[l];
     long double run = 0;
     int k = 1;
     for (int l = a; l < b && k < nsub; ++l) {
-        run += row_cost(l, lmax, lenW);
+        run += rc[l];
         if (run >= total * k / nsub) { if (l + 1 > e.back() && l + 1 < b) e.push_back(l + 1); ++k; }
     }
     e.push_back(b);
@@ -785,10 +802,20 @@ static void host_band_edges(const HostJob& hj, int nb, int* edges)
     constexpr double kPcie = 50e9;                            // bytes per second per device, pinned destination
     // row_cost sums to warp-steps of the TTTT tiling (a warp's steps are shared out over its NR rows): 32 R pair-steps each
     const double per_unit = 32.0 * psb::v3_r(psb::JOB_TTTT) * job_fp64_per_pair_step(hj.job) / kIssue;   // seconds per unit
+    // the edges of a (job, shape, nb) never change: computed once
+    static std::mutex cm;
+    static std::map<std::tuple<int, int, int, int, int, int>, std::vector<int>> done;
+    const auto key = std::make_tuple(hj.job, hj.nout, hj.lmin, hj.lmax, hj.lenW, nb);
+    {
+        std::lock_guard<std::mutex> lk(cm);
+        auto it = done.find(key);
+        if (it != done.end()) { for (int b = 0; b <= nb; ++b) edges[b] = it->second[b]; return; }
+    }
+    const std::vector<long double>& rcv = row_costs(hj.lmax, hj.lenW);
     std::vector<double> c(N), d(N);
     double sc = 0, sd = 0;
     for (int i = 0; i < N; ++i) {
-        c[i] = (double)row_cost(hj.lmin + i, hj.lmax, hj.lenW) * per_unit;
+        c[i] = (double)rcv[hj.lmin + i] * per_unit;
         d[i] = 8.0 * hj.nout * (2.0 * (N - i) - 1.0) / kPcie;
         sc += c[i]; sd += d[i];
     }
@@ -817,6 +844,9 @@ static void host_band_edges(const HostJob& hj, int nb, int* edges)
     for (int b = k + 1; b <= nb; ++b) e[b] = hj.lmax + 1;     // fewer bands than devices: the rest stay empty
     e[nb] = hj.lmax + 1;
     for (int b = 0; b <= nb; ++b) edges[b] = e[b];
+    std::lock_guard<std::mutex> lk(cm);
+    if (done.size() > 256) done.clear();
+    done[key] = e;
 }
 
 int run_host_job(const HostJob& hj, int ngpus)
@@ -964,13 +994,14 @@ int psb200_device_count(void) { return device_count(); }
 int psb200_band_edges(int lmin, int lmax, int lenW, int nbands, int* edges)
 {
     if (lmin < 0 || lmax < lmin || nbands < 1 || !edges) return fail(ERR_ARG, "band_edges: bad arguments");
+    const std::vector<long double>& rc = row_costs(lmax, lenW);
     long double total = 0;
-    for (int l = lmin; l <= lmax; ++l) total += row_cost(l, lmax, lenW);
+    for (int l = lmin; l <= lmax; ++l) total += rc[l];
     edges[0] = lmin;
     long double run = 0;
     int b = 1;
     for (int l = lmin; l <= lmax && b < nbands; ++l) {
-        run += row_cost(l, lmax, lenW);
+        run += rc[l];
         while (b < nbands && run >= total * b / nbands) edges[b++] = l + 1;
     }
     while (b <= nbands) edges[b++] = lmax + 1;
