@@ -699,6 +699,10 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
         int nsub = nb >= 4096 ? 16 : (nb >= 2048 ? 8 : (nb >= 512 ? 4 : (nb >= 128 ? 2 : 1)));
         if (const char* e = getenv("PSB200_NSUB")) nsub = std::max(1, std::min(32, atoi(e)));
         const std::vector<int> sub = split_rows(a, b, hj.lmax, hj.lenW, nsub);
+        // (Measured and dropped: when one device owns the whole matrix, finishing both triangles in place sub-band by
+        // sub-band and copying full columns as contiguous runs.  The L-shaped regions front-load the bytes -- the first
+        // sub-bands carry the long columns -- while full columns leave a fifth of the matrix behind the last kernel:
+        // 97.2 vs 94.6 ms per step end to end at lmax 6143.)
         const int ns = (int)sub.size() - 1;
         std::vector<size_t> toff(ns + 1, 0);             // one transposed block row per (sub-band, output)
         for (int k = 0; k < ns; ++k)
@@ -710,9 +714,9 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
         for (int o = 0; o < hj.nout; ++o) Xs[o] = s.X[o] - rowoff * ldX;   // kernels index rows from lmin
         psb::PairArgs A{};
         if (int rc = run_on_device(hj, g, a, b, Xs, ldX, &A)) return rc;
-        // Sub-bands alternate between two streams: they touch disjoint rows, so the blocks of sub-band k+1 fill the SMs
-        // that the last, longest blocks of sub-band k leave idle (on one stream every sub-band paid its own drain: 8 x 5
-        // drains per step were most of the 9.5 ms the host calls lost against the resident kernels at lmax 6143).
+        // Sub-bands alternate between two streams: they touch disjoint rows, so the blocks of sub-band k+1 can fill the SMs
+        // that the last blocks of sub-band k leave idle (measured at lmax 6143 on one GPU: no difference, 99.4 vs 99.2 ms
+        // per step -- the drains are short; kept because it costs nothing).
         CUDA_TRY(cudaEventRecord(s.ev_in, s.stream));
         CUDA_TRY(cudaStreamWaitEvent(s.stream2, s.ev_in, 0));
         Trace tr;
