@@ -223,6 +223,30 @@ int psb200_decouple_covmat_dev(int n, double* dY, long ldy, const double* dB1, l
 int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, const double* fields, long ldf,
                      int lmax, double* alm, long lda);
 
+/* ---- W-spectrum production: spin-0 HEALPix transforms ----------------------------------
+ * Replaces, optionally, the Healpix.jl calls behind the window spectra:
+ *   effective_weight_alm!  src/workspace.jl:141-171   map2alm(mask_i .* mask_j [.* sigma^2 .* Omega_pix]; lmax)   (:153-155, :159-163)
+ *   window_function_W!     src/workspace.jl:174-213   alm2cl(w_X, w_Y)[0:lmax]                                      (:202-204)
+ *   map2alm(mask) in front of mcm / master            src/modecoupling.jl:250-256, :328-329
+ * Maps are HEALPix RING-ordered, 12 nside^2 doubles (parent(HealpixMap{Float64,RingOrder})), nside a power of two
+ * <= 2048, lmax <= 4 nside - 1.  alm are complex128 stored as interleaved (re, im) doubles in Healpix.jl's Alm order,
+ * mmax = lmax: index(l, m) = m (2 lmax + 1 - m)/2 + l, (lmax+1)(lmax+2)/2 coefficients.
+ * psb200_map2alm: alm = map2alm(scale * factors[0] .* ... .* factors[nfactors-1]; lmax, niter), 1 <= nfactors <= 3 --
+ *   uniform pixel weights 4 pi/npix and `niter` Jacobi iterations alm += A(map - S alm) (Healpix.jl default niter = 3).
+ * psb200_alm2map: map = alm2map(alm, nside).   psb200_alm2cl: cl[l] = [a_l0 b_l0 + 2 sum_{m>0} Re(a_lm conj b_lm)]/(2l+1),
+ * l = 0..lmax (alm1 == alm2 allowed).  Host forms take host buffers and run on the current device; the _dev forms take
+ * device buffers and are asynchronous on `stream` (dmap is not modified).  No CPU fallback. */
+int psb200_map2alm(int nside, int lmax, int niter, int nfactors, const double* const* factors, double scale, double* alm);
+int psb200_alm2map(int nside, int lmax, const double* alm, double* map);
+int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl);
+int psb200_map2alm_dev(int nside, int lmax, int niter, const void* dmap, void* dalm, void* stream);
+int psb200_alm2map_dev(int nside, int lmax, const void* dalm, void* dmap, void* stream);
+int psb200_alm2cl_dev(int lmax, const void* dalm1, const void* dalm2, void* dcl, void* stream);
+/* Work accounting of ONE Legendre pass (analysis or synthesis; map2alm with niter iterations runs 2 niter + 1) as the
+ * kernel tiles it (host arithmetic): out[0] executed (l, m, ring pair) steps, out[1] steps of the rings the transform
+ * starts, out[2] warps, out[3] ring pairs per lane, out[4] ring-pair chunks.  5 FP64 instructions per step. */
+int psb200_sht_stats(int nside, int lmax, long long* out);
+
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);
 

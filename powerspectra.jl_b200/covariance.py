@@ -1,11 +1,13 @@
 """`coupledcov`, `CovarianceWorkspace` and the covariance inner loops, mirroring
 /root/reference/src/covariance.jl:34-446 and src/workspace.jl:77-213.
 
-The spherical-harmonic work that produces the window spectra W stays on the host and is
-out of scope (north star): a CovarianceWorkspace here is the *cache* of the reference's
-workspace -- the four field names, lmax and the dictionary of W spectra keyed exactly like
-`workspace.W_spectra` (src/workspace.jl:73,83), filled by the caller (or lazily by a
-`provider(X, Y, i, j, alpha, p, q, beta)` callable that runs the host SHT).
+The window spectra W come from spherical-harmonic transforms of mask products
+(`effective_weight_alm!` / `window_function_W!`, src/workspace.jl:141-213).  A CovarianceWorkspace
+here is either built from four `CovField`s like the reference's (`CovarianceWorkspace.from_fields`:
+the transforms then run on the GPU, healpix.py / csrc/psb200_sht.cuh), or is just the *cache* of the
+reference's workspace -- field names, lmax and the dictionary of W spectra keyed exactly like
+`workspace.W_spectra` (src/workspace.jl:73,83), filled by the caller or lazily by a
+`provider(X, Y, i, j, alpha, p, q, beta)` callable.
 """
 from __future__ import annotations
 
@@ -44,6 +46,25 @@ class CovarianceWorkspace:
         self.lmax = int(lmax)
         self.W_spectra = dict(W_spectra or {})
         self.provider = provider
+        self.mask_p = None                 # (name, "TT" | "PP") -> HealpixMap           (src/workspace.jl:80)
+        self.weight_p = None               # (name, "II" | "QQ" | "UU") -> HealpixMap    (:81)
+        self.effective_weights = {}        # (A, i, j, alpha) -> Alm                     (:82)
+
+    @classmethod
+    def from_fields(cls, m_i, m_j, m_p, m_q, lmax: int = 0):
+        """CovarianceWorkspace(m_i, m_j, m_p, m_q; lmax = 0) of the reference (src/workspace.jl:110-135): four
+        CovFields; lmax = 3 nside - 1 when not given (:95, :113)."""
+        from .healpix import nside2lmax
+        fields = (m_i, m_j, m_p, m_q)
+        ws = cls(tuple(f.name for f in fields), lmax if lmax else nside2lmax(m_i.maskT.nside))
+        ws.mask_p, ws.weight_p = {}, {}
+        for f in fields:
+            ws.mask_p[f.name, "TT"] = f.maskT
+            ws.mask_p[f.name, "PP"] = f.maskP
+            ws.weight_p[f.name, "II"] = f.sigma2.i
+            ws.weight_p[f.name, "QQ"] = f.sigma2.q
+            ws.weight_p[f.name, "UU"] = f.sigma2.u
+        return ws
 
 
 def window_function_W(workspace, X, Y, i, j, alpha, p, q, beta):
@@ -51,9 +72,14 @@ def window_function_W(workspace, X, Y, i, j, alpha, p, q, beta):
     key = (X, Y, i, j, alpha, p, q, beta)
     if key in workspace.W_spectra:
         return workspace.W_spectra[key]
+    if workspace.mask_p is not None:
+        from .healpix import window_spectrum
+        w = SpectralVector(window_spectrum(workspace, X, Y, i, j, alpha, p, q, beta))
+        workspace.W_spectra[key] = w
+        return w
     if workspace.provider is None:
         raise KeyError(f"window spectrum {key} not in the workspace and no provider given "
-                       "(the host SHT that produces it is outside this library)")
+                       "(build the workspace with CovarianceWorkspace.from_fields to have it computed)")
     w = workspace.provider(*key)
     if not isinstance(w, SpectralArray):
         w = SpectralVector(w)

@@ -12,6 +12,7 @@
 #include "psb200_lowrows.cuh"
 #include "psb200_quickpol.cuh"
 #include "psb200_zonal.cuh"
+#include "psb200_sht.cuh"
 
 #include <cusolverDn.h>      // types + prototypes only: the library is loaded with dlopen (psb200_solve.inl)
 #include <dlfcn.h>
@@ -983,6 +984,7 @@ int run_quickpol_on_device(const QpHostJob& hj, int g, int a, int b, std::string
 }
 
 #include "psb200_solve.inl"
+#include "psb200_sht.inl"
 
 }  // namespace
 
@@ -1441,6 +1443,8 @@ int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, 
     }
     return OK;
 }
+
+#include "psb200_sht_abi.inl"
 
 double psb200_dfma_peak(int iters)
 {

@@ -1,0 +1,571 @@
+// psb200_sht.cuh -- W-spectrum production: spin-0 HEALPix map2alm / alm2map / alm2cl on the device.
+//
+// What it replaces on the host side of the reference (which stays available):
+//   effective_weight_alm!   /root/reference/src/workspace.jl:141-171   map2alm(mask_i .* mask_j [.* sigma^2 .* Omega_pix]; lmax)
+//   window_function_W!      /root/reference/src/workspace.jl:174-213   mean over (wX, wY) of alm2cl(w_X, w_Y)[0:lmax]
+//   map2alm(mask) feeding mcm   src/modecoupling.jl:250-256, :328-329
+// `map2alm` / `alm2cl` themselves live in Healpix.jl (un-vendored; compat "3, 4"): pixel-weighted analysis on the RING
+// pixelisation followed by `niter` Jacobi iterations a <- a + A(f - S a) (default 3).  This file is a from-scratch
+// B200 design of that transform, not a port of libsharp:
+//
+//   map --(ring kernel: one block per ring, mixed-radix Stockham FFT in shared memory, any ring length 4r)--> Phi[m][ring pair]
+//       --(Legendre kernel: one WARP per (m, chunk of 32 R ring pairs); every lane runs the lambda_lm recurrence of R ring
+//          pairs in registers along l, north/south folded by parity; per 16 l the lanes' partial sums are combined by a
+//          31-shuffle butterfly and written once)--> per-chunk partial alm --(finish: fixed-order sum over chunks)--> alm
+// and the mirror image for synthesis (lanes accumulate F_m(ring) in registers; no reduction at all).  Nothing is
+// atomically accumulated, so results do not depend on scheduling.  The Legendre stage is FP64-pipe bound
+// (5 FP64 instructions per (l, m, ring pair): 3 recurrence + 2 accumulate), the ring stage is shared-memory bound and small.
+//
+// Dynamic range.  lambda_mm ~ sin^m(theta) underflows Float64 long before l reaches the classical region
+// (theta = 1e-3, m = 3000: 1e-9000).  Every ring carries an integer e with lambda = lt * 2^(-800 e), |lt| kept inside
+// [2^-400, 2^487]; the start value comes from log2 lambda_mm = cm[m] + m log2 sin(theta) (cm tabulated on the host in long
+// double); the check runs once per 16 steps (growth per 16 steps < 2^87); a ring contributes only while e = 0 (what it
+// would add before is below 2^-400 of the scale of lambda).  Rings with m > lmax sin(theta) + 16 (lmax/2)^(1/3) are never
+// started (sht_mlim: everything skipped is below 1e-30).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#ifndef PSB_HD
+#if defined(__CUDACC__)
+#define PSB_HD __host__ __device__ __forceinline__
+#else
+#define PSB_HD inline
+#endif
+#endif
+
+namespace psb {
+
+constexpr int SHT_C = 16;                 // l steps between reductions / rescale checks
+constexpr int SHT_WARPS = 4;              // warps per block of the Legendre kernels (independent of each other)
+constexpr double SHT_BIG = 2.58224987808690858965591917200e120;      // 2^400
+constexpr double SHT_DOWN = 1.49969681389882132575131978222e-241;    // 2^-800
+constexpr int SHT_NEVER = 0x7fffffff;
+
+struct ShtDims {
+    int nside, lmax, nrp, nchunks;        // nrp = 2 nside ring pairs (north ring p+1, south ring 4 nside - p - 1; p = nrp-1: the equator alone)
+    long long npix, nalm;                 // 12 nside^2, (lmax+1)(lmax+2)/2
+};
+
+PSB_HD long long sht_alm_base(int lmax, int m) { return (long long)m * (2 * lmax + 1 - m) / 2; }   // index(l, m) = base + l
+
+// ring pair p: pixels per ring, first pixel of the north / south ring, cos and sin of the north colatitude, and
+// whether the first pixel sits at phi = pi/n (caps, belt rings with r - nside even) or at 0
+struct ShtRing { int n; long long startN, startS; double z, s; int shifted; };
+
+PSB_HD ShtRing sht_ring(int nside, int p)
+{
+    ShtRing g;
+    const long long N = nside, r = p + 1, npix = 12 * N * N, ncap = 2 * N * (N - 1);
+    if (r < N) {
+        const double tmp = (double)(r * r) / (3.0 * (double)N * (double)N);
+        g.n = (int)(4 * r);
+        g.startN = 2 * r * (r - 1);
+        g.startS = npix - 2 * r * (r + 1);
+        g.z = 1.0 - tmp;
+        g.s = sqrt(tmp * (2.0 - tmp));
+        g.shifted = 1;
+    } else {
+        g.n = (int)(4 * N);
+        g.startN = ncap + (r - N) * 4 * N;
+        g.startS = ncap + (3 * N - r) * 4 * N;                 // ring 4N - r
+        g.z = (double)(2 * N - r) * 2.0 / (3.0 * (double)N);
+        g.s = sqrt((1.0 + g.z) * (1.0 - g.z));
+        g.shifted = ((r - N) & 1) == 0;
+    }
+    return g;
+}
+
+// rings with m above this are never started.  The margin is 16 turning-point widths (lmax/2)^(1/3): every lambda_lm
+// it skips is below 1e-30 (measured, lmax 191..8191; tests/test_sht.py).  libsharp's `sharp_get_mlim`, which the
+// reference's transform uses, takes lmax sin(theta) + max(100, lmax/100) and drops values up to 1e-9 at lmax 6143.
+PSB_HD double sht_mlim(int lmax, double sth)
+{
+    const double w = 16.0 * cbrt(0.5 * (double)lmax);
+    return lmax * sth + (w < 50.0 ? 50.0 : w);
+}
+
+// recurrence coefficients to advance FROM l:  lambda_{l+1} = c1 (x lambda_l) - c2 lambda_{l-1},
+// c1 = 1/A_{l+1}, c2 = A_l/A_{l+1}, A_l = sqrt((l^2 - m^2)/(4 l^2 - 1))
+PSB_HD void sht_coef(int l, int m, double* c1, double* c2)
+{
+    const double l1 = (double)(l + 1), ld = (double)l, md = (double)m;
+    const double ia2 = (4.0 * l1 * l1 - 1.0) / ((l1 - md) * (l1 + md));
+    const double a2 = ((ld - md) * (ld + md)) / (4.0 * ld * ld - 1.0);
+    *c1 = sqrt(ia2);
+    *c2 = sqrt(a2 * ia2);
+}
+
+// state of one ring's recurrence: lambda_l = lc 2^(-800 e), lambda_{l-1} = lp 2^(-800 e)
+struct ShtLam { double x, lp, lc; int e; };
+
+PSB_HD ShtLam sht_lam_start(int lmax, int m, double cm_m, double z, double sth, bool exists)
+{
+    ShtLam q;
+    q.x = z; q.lp = 0.0; q.lc = 0.0; q.e = SHT_NEVER;
+    if (!exists || (double)m > sht_mlim(lmax, sth)) { q.x = 0.0; return q; }
+    const double L = cm_m + (double)m * log2(sth);
+    int e = 0;
+    if (L < -400.0) e = (int)floor((400.0 - L) / 800.0);
+    q.e = e;
+    const double v = exp2(L + 800.0 * (double)e);
+    q.lc = (m & 1) ? -v : v;
+    return q;
+}
+
+PSB_HD void sht_lam_advance(ShtLam& q, double c1, double c2)
+{
+    const double t = q.x * q.lc;
+    const double u = c2 * q.lp;
+    const double ln = fma(c1, t, -u);
+    q.lp = q.lc;
+    q.lc = ln;
+}
+
+// true when the ring has just become representable (e reached 0)
+PSB_HD bool sht_lam_rescale(ShtLam& q)
+{
+    if (q.e > 0 && q.e != SHT_NEVER && (fabs(q.lc) > SHT_BIG || fabs(q.lp) > SHT_BIG)) {
+        q.lc *= SHT_DOWN;
+        q.lp *= SHT_DOWN;
+        return --q.e == 0;
+    }
+    return false;
+}
+
+PSB_HD void sht_sincospi(double a, double* s, double* c)
+{
+#if defined(__CUDA_ARCH__)
+    sincospi(a, s, c);
+#else
+    // host build (tests/hostcheck): reduce exactly, then libm
+    double r = fmod(a, 2.0);
+    *s = sin(3.14159265358979323846264338327950288 * r);
+    *c = cos(3.14159265358979323846264338327950288 * r);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ring stage.  All functions are written against a context {tid, nthr, sync()} so that tests/hostcheck can run the
+// very same code with one "thread"; on the device the context is the thread block.
+// ------------------------------------------------------------------------------------------------------------------
+
+// radices of h: 4s first, then primes in increasing order (a prime radix p costs p complex MACs per output)
+PSB_HD int sht_factor(int h, int* rad)
+{
+    int n = 0;
+    while (h % 4 == 0) { rad[n++] = 4; h /= 4; }
+    for (int p = 2; p * p <= h; ++p)
+        while (h % p == 0) { rad[n++] = p; h /= p; }
+    if (h > 1) rad[n++] = h;
+    return n;
+}
+
+// T[t] = exp(-2 pi i t / h)
+template <class Ctx> PSB_HD void sht_twiddles(Ctx& cx, double2* T, int h)
+{
+    for (int t = cx.tid; t < h; t += cx.nthr) {
+        double s, c;
+        sht_sincospi(2.0 * (double)t / (double)h, &s, &c);
+        T[t] = make_double2(c, -s);
+    }
+}
+
+// Stockham autosort FFT of the h complex numbers in A (result returned in the buffer the function returns)
+template <class Ctx> PSB_HD double2* sht_fft(Ctx& cx, double2* A, double2* B, const double2* T, int h, const int* rad, int nrad)
+{
+    int Ns = 1;
+    for (int q = 0; q < nrad; ++q) {
+        const int Rr = rad[q], M = Ns * Rr, hR = h / Rr, hM = h / M;
+        for (int o = cx.tid; o < h; o += cx.nthr) {
+            const int k = o % Ns, qq = (o / Ns) % Rr, jhi = o / M;
+            const int j = jhi * Ns + k;
+            int step = k * hM + qq * hR;
+            if (step >= h) step -= h;
+            int idx = 0;
+            double ar = 0.0, ai = 0.0;
+            for (int r = 0; r < Rr; ++r) {
+                const double2 a = A[j + r * hR];
+                const double2 w = T[idx];
+                ar = fma(a.x, w.x, ar); ar = fma(-a.y, w.y, ar);
+                ai = fma(a.x, w.y, ai); ai = fma(a.y, w.x, ai);
+                idx += step;
+                if (idx >= h) idx -= h;
+            }
+            B[o] = make_double2(ar, ai);
+        }
+        cx.sync();
+        double2* t = A; A = B; B = t;
+        Ns = M;
+    }
+    return A;
+}
+
+// Analysis of one ring: f (n reals) -> out[m] = scale * exp(-i m phi0) * sum_k f_k exp(-2 pi i m k / n), m = 0..mmax,
+// written with stride `ostride` (in double2 units).  A, B, T: h = n/2 complex numbers each (shared memory on the device).
+template <class Ctx>
+PSB_HD void sht_ring_analyse(Ctx& cx, const double* f, int n, int shifted, double scale, int mmax,
+                             double2* A, double2* B, double2* T, const int* rad, int nrad, double2* out, long long ostride)
+{
+    const int h = n / 2;
+    sht_twiddles(cx, T, h);
+    for (int k = cx.tid; k < h; k += cx.nthr) A[k] = make_double2(f[2 * k], f[2 * k + 1]);
+    cx.sync();
+    double2* Z = sht_fft(cx, A, B, T, h, rad, nrad);
+    double2* X = (Z == A) ? B : A;                       // X[0..h-1]; X[h] is real and kept apart (no room for h+1 entries)
+    // X[j] = 1/2 [(Z_j + conj Z_{h-j}) - i w_j (Z_j - conj Z_{h-j})],  w_j = exp(-2 pi i j / n)
+    for (int j = cx.tid; j < h; j += cx.nthr) {
+        const double2 a = Z[j], b = Z[j ? h - j : 0];
+        double s, c;
+        sht_sincospi((double)j / (double)h, &s, &c);     // w = c - i s
+        const double er = 0.5 * (a.x + b.x), ei = 0.5 * (a.y - b.y);       // E = (Z_j + conj Z_{h-j})/2
+        const double dr = 0.5 * (a.x - b.x), di = 0.5 * (a.y + b.y);       // D = (Z_j - conj Z_{h-j})/2
+        // -i w D = -i (c - i s)(dr + i di) = (c di - s dr) - i (c dr + s di)
+        X[j] = make_double2(er + (c * di - s * dr), ei - (c * dr + s * di));
+    }
+    cx.sync();
+    const double xh = Z[0].x - Z[0].y;                   // X[h] = Re Z_0 - Im Z_0
+    for (int m = cx.tid; m <= mmax; m += cx.nthr) {
+        int j = m % n;
+        double2 v;
+        if (j < h) v = X[j];
+        else if (j == h) v = make_double2(xh, 0.0);
+        else { v = X[n - j]; v.y = -v.y; }
+        double pr = scale, pi = 0.0;
+        if (shifted) {                                   // exp(-i pi m / n)
+            double s, c;
+            sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c);
+            pr = scale * c; pi = -scale * s;
+        }
+        out[(long long)m * ostride] = make_double2(v.x * pr - v.y * pi, v.x * pi + v.y * pr);
+    }
+    cx.sync();
+}
+
+// Synthesis of one ring: in[m] = F_m (stride istride) -> f_k = Re F_0 + 2 Re sum_{m>0} F_m exp(i m phi_k), n reals.
+// If `ref` is given the ring written is ref - f (the residual of a Jacobi iteration).
+template <class Ctx>
+PSB_HD void sht_ring_synthesise(Ctx& cx, const double2* in, long long istride, int n, int shifted, int mmax,
+                                double2* A, double2* B, double2* T, const int* rad, int nrad, const double* ref, double* f)
+{
+    const int h = n / 2;
+    sht_twiddles(cx, T, h);
+    // S[j], j = 0..h:  sum_{m = j, j+n, ...} P_m  +  sum_{m = n-j, 2n-j, ... > 0} conj P_m,   P_m = F_m exp(i m phi0), P_0 -> Re
+    // kept in B[0..h-1] and (S[h], real) in a register of every thread that needs it -> recomputed below
+    for (int j = cx.tid; j < h; j += cx.nthr) {
+        double sr = 0.0, si = 0.0;
+        for (int m = j; m <= mmax; m += n) {
+            double2 v = in[(long long)m * istride];
+            double pr = 1.0, pi = 0.0;
+            if (shifted) { double s, c; sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c); pr = c; pi = s; }
+            const double xr = v.x * pr - v.y * pi, xi = v.x * pi + v.y * pr;
+            sr += xr;
+            si += (m == 0) ? 0.0 : xi;
+        }
+        for (int m = n - j; m <= mmax; m += n) {
+            double2 v = in[(long long)m * istride];
+            double pr = 1.0, pi = 0.0;
+            if (shifted) { double s, c; sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c); pr = c; pi = s; }
+            const double xr = v.x * pr - v.y * pi, xi = v.x * pi + v.y * pr;
+            sr += xr;
+            si -= xi;
+        }
+        B[j] = make_double2(sr, si);
+    }
+    cx.sync();
+    // S[h] = sum over m = h, h+n, ... of (P_m + conj P_m) = 2 Re P_m
+    double sh = 0.0;
+    for (int m = h; m <= mmax; m += n) {
+        double2 v = in[(long long)m * istride];
+        double pr = 1.0, pi = 0.0;
+        if (shifted) { double s, c; sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c); pr = c; pi = s; }
+        sh += 2.0 * (v.x * pr - v.y * pi);
+    }
+    // conj Z'_j,  Z'_j = (S_j + conj S_{h-j}) + i exp(2 pi i j/n) (S_j - conj S_{h-j})
+    for (int j = cx.tid; j < h; j += cx.nthr) {
+        const double2 a = B[j];
+        double2 b;
+        if (j == 0) b = make_double2(sh, 0.0); else b = B[h - j];
+        double s, c;
+        sht_sincospi((double)j / (double)h, &s, &c);     // exp(+2 pi i j / n) = c + i s
+        const double er = a.x + b.x, ei = a.y - b.y;
+        const double dr = a.x - b.x, di = a.y + b.y;
+        // i (c + i s)(dr + i di) = i (c dr - s di) - (c di + s dr)
+        const double zr = er - (c * di + s * dr), zi = ei + (c * dr - s * di);
+        A[j] = make_double2(zr, -zi);
+    }
+    cx.sync();
+    double2* Z = sht_fft(cx, A, B, T, h, rad, nrad);     // conj of the inverse transform
+    for (int k = cx.tid; k < h; k += cx.nthr) {
+        const double f0 = Z[k].x, f1 = -Z[k].y;
+        if (ref) { f[2 * k] = ref[2 * k] - f0; f[2 * k + 1] = ref[2 * k + 1] - f1; }
+        else { f[2 * k] = f0; f[2 * k + 1] = f1; }
+    }
+    cx.sync();
+}
+
+#if defined(__CUDACC__)
+
+struct ShtBlockCtx {
+    int tid, nthr;
+    __device__ void sync() { __syncthreads(); }
+};
+
+// Phi[(m nrp + p) 2 + hemi] (double2): hemi 0 = north ring p+1, 1 = its southern partner (zero for the equator)
+// grid.x = ring pairs [p_lo, p_lo + gridDim.x), grid.y = 2 hemispheres; dynamic shared memory 3 h_max double2
+__global__ void __launch_bounds__(256) sht_ring_analysis_kernel(ShtDims D, int p_lo, const double* __restrict__ map,
+                                                                double2* __restrict__ Phi)
+{
+    extern __shared__ double2 sht_smem[];
+    __shared__ int rad[16];
+    __shared__ int nrad;
+    const int p = p_lo + blockIdx.x, hemi = blockIdx.y;
+    const ShtRing g = sht_ring(D.nside, p);
+    double2* out = Phi + ((long long)p * 2 + hemi);
+    const long long ostride = (long long)D.nrp * 2;
+    if (hemi == 1 && p == D.nrp - 1) {                 // the equator has no partner
+        for (int m = threadIdx.x; m <= D.lmax; m += blockDim.x) out[(long long)m * ostride] = make_double2(0.0, 0.0);
+        return;
+    }
+    const int h = g.n / 2;
+    if (threadIdx.x == 0) nrad = sht_factor(h, rad);
+    __syncthreads();
+    ShtBlockCtx cx{(int)threadIdx.x, (int)blockDim.x};
+    sht_ring_analyse(cx, map + (hemi ? g.startS : g.startN), g.n, g.shifted, 12.566370614359172953850573533118 / (double)D.npix,
+                     D.lmax, sht_smem, sht_smem + h, sht_smem + 2 * h, rad, nrad, out, ostride);
+}
+
+__global__ void __launch_bounds__(256) sht_ring_synthesis_kernel(ShtDims D, int p_lo, const double2* __restrict__ Phi,
+                                                                 const double* __restrict__ ref, double* __restrict__ map)
+{
+    extern __shared__ double2 sht_smem[];
+    __shared__ int rad[16];
+    __shared__ int nrad;
+    const int p = p_lo + blockIdx.x, hemi = blockIdx.y;
+    if (hemi == 1 && p == D.nrp - 1) return;
+    const ShtRing g = sht_ring(D.nside, p);
+    const int h = g.n / 2;
+    if (threadIdx.x == 0) nrad = sht_factor(h, rad);
+    __syncthreads();
+    ShtBlockCtx cx{(int)threadIdx.x, (int)blockDim.x};
+    const long long st = hemi ? g.startS : g.startN;
+    sht_ring_synthesise(cx, Phi + ((long long)p * 2 + hemi), (long long)D.nrp * 2, g.n, g.shifted, D.lmax,
+                        sht_smem, sht_smem + h, sht_smem + 2 * h, rad, nrad, ref ? ref + st : nullptr, map + st);
+}
+
+// coef[base(m) + l] = (c1, c2) of sht_coef, l = m..lmax
+__global__ void sht_coef_kernel(int lmax, double2* __restrict__ coef)
+{
+    const int m = blockIdx.y;
+    const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > lmax) return;
+    double c1, c2;
+    sht_coef(l, m, &c1, &c2);
+    coef[sht_alm_base(lmax, m) + l] = make_double2(c1, c2);
+}
+
+// cmin[m] = first chunk of ring pairs that holds a ring the transform starts for this m (rings are skipped from the
+// poles inwards: sin(theta) grows with p); chunk c covers ring pairs [c 32 R, (c+1) 32 R)
+__global__ void sht_cmin_kernel(ShtDims D, int R, int* __restrict__ cmin)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > D.lmax) return;
+    int c = 0;
+    for (; c < D.nchunks; ++c) {
+        int plast = (c + 1) * 32 * R - 1;
+        if (plast > D.nrp - 1) plast = D.nrp - 1;
+        if ((double)m <= sht_mlim(D.lmax, sht_ring(D.nside, plast).s)) break;
+    }
+    cmin[m] = c;
+}
+
+// butterfly: every lane holds 32 partial sums v[0..31]; on return lane L holds the warp total of v[L] in v[0].
+// 31 shuffles of 64 bits; the order of the additions is fixed.
+__device__ __forceinline__ void sht_butterfly(double (&v)[32], int lane)
+{
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const double send = up ? v[i] : v[i + w];
+            const double keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+}
+
+// Legendre stage of the analysis: one warp per (m, chunk).  partial[chunk][2 (base(m) + l) + {0 re, 1 im}]
+template <int R>
+__global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDims D, const double4* __restrict__ Phi,
+                                                                         const double2* __restrict__ coef,
+                                                                         const double* __restrict__ cm,
+                                                                         const int* __restrict__ cmin,
+                                                                         double* __restrict__ partial)
+{
+    __shared__ double2 sco[SHT_WARPS][SHT_C];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;
+    const int m = blockIdx.x / bpm;
+    const int chunk = (blockIdx.x % bpm) * SHT_WARPS + wid;
+    if (chunk >= D.nchunks || chunk < cmin[m]) return;
+    const long long base = sht_alm_base(D.lmax, m);
+    const double cm_m = cm[m];
+    ShtLam q[R];
+    double ger[R], gei[R], gor[R], goi[R];
+    const int p0 = (chunk * 32 + lane) * R;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int p = p0 + s;
+        const bool ex = p < D.nrp;
+        const ShtRing g = sht_ring(D.nside, ex ? p : 0);
+        q[s] = sht_lam_start(D.lmax, m, cm_m, g.z, g.s, ex);
+        ger[s] = gei[s] = gor[s] = goi[s] = 0.0;
+        if (q[s].e == 0) {
+            const double4 t = Phi[(long long)m * D.nrp + p];
+            ger[s] = t.x + t.z; gei[s] = t.y + t.w; gor[s] = t.x - t.z; goi[s] = t.y - t.w;
+        }
+    }
+    double* out = partial + (long long)chunk * 2 * D.nalm + 2 * base;
+    for (int l0 = m; l0 <= D.lmax; l0 += SHT_C) {
+        if (lane < SHT_C) {
+            const int l = l0 + lane <= D.lmax ? l0 + lane : D.lmax;
+            sco[wid][lane] = coef[base + l];
+        }
+        __syncwarp();
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < SHT_C; ++j) {
+            const double2 c = sco[wid][j];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if ((j & 1) == 0) { v[2 * j] = fma(q[s].lc, ger[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, gei[s], v[2 * j + 1]); }
+                else              { v[2 * j] = fma(q[s].lc, gor[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, goi[s], v[2 * j + 1]); }
+                sht_lam_advance(q[s], c.x, c.y);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (sht_lam_rescale(q[s])) {
+                const double4 t = Phi[(long long)m * D.nrp + p0 + s];
+                ger[s] = t.x + t.z; gei[s] = t.y + t.w; gor[s] = t.x - t.z; goi[s] = t.y - t.w;
+            }
+        }
+        sht_butterfly(v, lane);
+        const int l = l0 + (lane >> 1);
+        if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0];
+    }
+}
+
+// sum of the per-chunk partial alm in chunk order; accumulate != 0: alm += sum (Jacobi step)
+__global__ void sht_analysis_finish_kernel(ShtDims D, const double* __restrict__ partial, const int* __restrict__ cmin,
+                                           int accumulate, double* __restrict__ alm)
+{
+    const int m = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // double index inside the m column: 2 (l - m) + comp
+    if (i >= 2 * (D.lmax - m + 1)) return;
+    const long long off = 2 * (sht_alm_base(D.lmax, m) + m) + i;
+    double s = 0.0;
+    for (int c = cmin[m]; c < D.nchunks; ++c) s += partial[(long long)c * 2 * D.nalm + off];
+    alm[off] = accumulate ? alm[off] + s : s;
+}
+
+// Legendre stage of the synthesis: one warp per (m, chunk); Phi[m nrp + p] = (F_N re, im, F_S re, im)
+template <int R>
+__global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDims D, const double2* __restrict__ alm,
+                                                                          const double2* __restrict__ coef,
+                                                                          const double* __restrict__ cm,
+                                                                          const int* __restrict__ cmin,
+                                                                          double4* __restrict__ Phi)
+{
+    __shared__ double2 sco[SHT_WARPS][SHT_C];
+    __shared__ double2 sal[SHT_WARPS][SHT_C];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;
+    const int m = blockIdx.x / bpm;
+    const int chunk = (blockIdx.x % bpm) * SHT_WARPS + wid;
+    if (chunk >= D.nchunks) return;
+    const int p0 = (chunk * 32 + lane) * R;
+    if (chunk < cmin[m]) {                                         // nothing starts here: F = 0
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            if (p0 + s < D.nrp) Phi[(long long)m * D.nrp + p0 + s] = make_double4(0.0, 0.0, 0.0, 0.0);
+        return;
+    }
+    const long long base = sht_alm_base(D.lmax, m);
+    const double cm_m = cm[m];
+    ShtLam q[R];
+    double fer[R], fei[R], forr[R], foi[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int p = p0 + s;
+        const bool ex = p < D.nrp;
+        const ShtRing g = sht_ring(D.nside, ex ? p : 0);
+        q[s] = sht_lam_start(D.lmax, m, cm_m, g.z, g.s, ex);
+        fer[s] = fei[s] = forr[s] = foi[s] = 0.0;
+    }
+    for (int l0 = m; l0 <= D.lmax; l0 += SHT_C) {
+        if (lane < SHT_C) {
+            const int l = l0 + lane;
+            sco[wid][lane] = coef[base + (l <= D.lmax ? l : D.lmax)];
+            sal[wid][lane] = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < SHT_C; ++j) {
+            const double2 c = sco[wid][j];
+            const double2 a = sal[wid][j];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if ((j & 1) == 0) { fer[s] = fma(q[s].lc, a.x, fer[s]); fei[s] = fma(q[s].lc, a.y, fei[s]); }
+                else              { forr[s] = fma(q[s].lc, a.x, forr[s]); foi[s] = fma(q[s].lc, a.y, foi[s]); }
+                sht_lam_advance(q[s], c.x, c.y);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            if (sht_lam_rescale(q[s])) fer[s] = fei[s] = forr[s] = foi[s] = 0.0;      // what was summed so far was scaled garbage
+    }
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        if (p0 + s >= D.nrp) continue;
+        double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (q[s].e == 0) t = make_double4(fer[s] + forr[s], fei[s] + foi[s], fer[s] - forr[s], fei[s] - foi[s]);
+        Phi[(long long)m * D.nrp + p0 + s] = t;
+    }
+}
+
+// cl[l] = (Re(a_l0 conj b_l0) + 2 sum_{m=1..l} Re(a_lm conj b_lm))/(2l+1), m ascending (fixed order)
+__global__ void sht_alm2cl_kernel(int lmax, const double2* __restrict__ a, const double2* __restrict__ b, double* __restrict__ cl)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > lmax) return;
+    double s = 0.0;
+    for (int m = 0; m <= l; ++m) {
+        const long long i = sht_alm_base(lmax, m) + l;
+        const double2 x = a[i], y = b[i];
+        const double t = x.x * y.x + x.y * y.y;
+        s += m ? 2.0 * t : t;
+    }
+    cl[l] = s / (2.0 * (double)l + 1.0);
+}
+
+// out = scale * a [* b [* c]]   (effective_weight_alm!: mask_i .* mask_j .* sigma^2 .* Omega_pix)
+__global__ void sht_product_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b,
+                                   const double* __restrict__ c, double scale, double* __restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = a[i];
+        if (b) v *= b[i];
+        if (c) v *= c[i] * scale; else v *= scale;
+        out[i] = v;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace psb

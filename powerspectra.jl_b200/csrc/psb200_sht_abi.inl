@@ -1,0 +1,126 @@
+// psb200_sht_abi.inl -- C entry points of the spin-0 HEALPix transforms (include/psb200.h, "W-spectrum production").
+// Included by psb200.cu inside its extern "C" block.
+
+int psb200_map2alm_dev(int nside, int lmax, int niter, const void* dmap, void* dalm, void* stream)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!dmap || !dalm || niter < 0) return fail(ERR_ARG, "map2alm: bad arguments");
+    int dev = 0;
+    if (int rc = sht_enter(nside, lmax, &dev)) return rc;
+    ShtPlan* P = nullptr;
+    if (int rc = sht_plan(dev, nside, lmax, (cudaStream_t)stream, &P)) return rc;
+    return sht_map2alm(*P, (cudaStream_t)stream, (const double*)dmap, (double*)dalm, niter);
+}
+
+int psb200_alm2map_dev(int nside, int lmax, const void* dalm, void* dmap, void* stream)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!dmap || !dalm) return fail(ERR_ARG, "alm2map: bad arguments");
+    int dev = 0;
+    if (int rc = sht_enter(nside, lmax, &dev)) return rc;
+    ShtPlan* P = nullptr;
+    if (int rc = sht_plan(dev, nside, lmax, (cudaStream_t)stream, &P)) return rc;
+    return sht_synthesis(*P, (cudaStream_t)stream, (const double*)dalm, nullptr, (double*)dmap);
+}
+
+int psb200_alm2cl_dev(int lmax, const void* dalm1, const void* dalm2, void* dcl, void* stream)
+{
+    if (lmax < 0 || !dalm1 || !dalm2 || !dcl) return fail(ERR_ARG, "alm2cl: bad arguments");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    psb::sht_alm2cl_kernel<<<(lmax + 128) / 128, 128, 0, (cudaStream_t)stream>>>(lmax, (const double2*)dalm1, (const double2*)dalm2,
+                                                                              (double*)dcl);
+    CUDA_TRY(cudaGetLastError());
+    return OK;
+}
+
+int psb200_map2alm(int nside, int lmax, int niter, int nfactors, const double* const* factors, double scale, double* alm)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (nfactors < 1 || nfactors > 3 || !factors || !alm || niter < 0) return fail(ERR_ARG, "map2alm: bad arguments");
+    for (int i = 0; i < nfactors; ++i)
+        if (!factors[i]) return fail(ERR_ARG, "map2alm: null map");
+    int dev = 0;
+    if (int rc = sht_enter(nside, lmax, &dev)) return rc;
+    cudaStream_t st = g_scratch[dev].stream;
+    ShtPlan* P = nullptr;
+    if (int rc = sht_plan(dev, nside, lmax, st, &P)) return rc;
+    const size_t nb = (size_t)P->D.npix * sizeof(double);
+    // factors staged in: work (first), resid (second), Phi (third: free until the first analysis)
+    double* slot[3] = {P->work, P->resid, (double*)P->Phi};
+    if (nfactors == 3 && (size_t)(lmax + 1) * P->D.nrp * sizeof(double4) < nb) {
+        if (int rc = scratch_reserve(dev, 0, (size_t)P->D.npix)) return rc;
+        slot[2] = g_scratch[dev].X[0];
+    }
+    for (int i = 0; i < nfactors; ++i) CUDA_TRY(cudaMemcpyAsync(slot[i], factors[i], nb, cudaMemcpyHostToDevice, st));
+    if (nfactors > 1 || scale != 1.0) {
+        psb::sht_product_kernel<<<1184, 256, 0, st>>>(P->D.npix, slot[0], nfactors > 1 ? slot[1] : nullptr,
+                                                     nfactors > 2 ? slot[2] : nullptr, scale, P->work);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (int rc = sht_map2alm(*P, st, P->work, P->alm, niter)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(alm, P->alm, (size_t)2 * P->D.nalm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return OK;
+}
+
+int psb200_alm2map(int nside, int lmax, const double* alm, double* map)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!alm || !map) return fail(ERR_ARG, "alm2map: bad arguments");
+    int dev = 0;
+    if (int rc = sht_enter(nside, lmax, &dev)) return rc;
+    cudaStream_t st = g_scratch[dev].stream;
+    ShtPlan* P = nullptr;
+    if (int rc = sht_plan(dev, nside, lmax, st, &P)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(P->alm, alm, (size_t)2 * P->D.nalm * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int rc = sht_synthesis(*P, st, P->alm, nullptr, P->work)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(map, P->work, (size_t)P->D.npix * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return OK;
+}
+
+int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (lmax < 0 || lmax > 8191 || !alm1 || !alm2 || !cl) return fail(ERR_ARG, "alm2cl: bad arguments");
+    if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    const size_t na = (size_t)(lmax + 1) * (lmax + 2);           // doubles per alm
+    if (int rc = scratch_reserve(dev, 0, 2 * na + (size_t)lmax + 1)) return rc;
+    DeviceScratch& s = g_scratch[dev];
+    double *a = s.X[0], *b = a + na, *c = b + na;
+    CUDA_TRY(cudaMemcpyAsync(a, alm1, na * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    if (alm2 != alm1) CUDA_TRY(cudaMemcpyAsync(b, alm2, na * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    psb::sht_alm2cl_kernel<<<(lmax + 128) / 128, 128, 0, s.stream>>>(lmax, (const double2*)a, (const double2*)(alm2 != alm1 ? b : a), c);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cl, c, ((size_t)lmax + 1) * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return OK;
+}
+
+/* Work accounting of one Legendre pass (analysis or synthesis) as the kernel tiles it; host arithmetic.
+ *   out[0] executed (l, m, ring-pair slot) steps: every started warp x its 16-step passes x 32 R slots
+ *   out[1] steps of rings the transform starts (m <= mlim), l = m..lmax
+ *   out[2] warps started   out[3] R   out[4] chunks */
+int psb200_sht_stats(int nside, int lmax, long long* out)
+{
+    if (nside < 1 || nside > 2048 || (nside & (nside - 1)) || lmax < 0 || lmax > 4 * nside - 1 || !out)
+        return fail(ERR_ARG, "sht_stats: bad arguments");
+    const int R = sht_R(), nrp = 2 * nside, nchunks = (nrp + 32 * R - 1) / (32 * R);
+    std::vector<double> ml(nrp);
+    for (int p = 0; p < nrp; ++p) ml[p] = psb::sht_mlim(lmax, psb::sht_ring(nside, p).s);
+    long long exec = 0, live = 0, warps = 0;
+    for (int m = 0; m <= lmax; ++m) {
+        const long long passes = (lmax - m + psb::SHT_C) / psb::SHT_C;
+        for (int c = 0; c < nchunks; ++c) {
+            const int plast = std::min((c + 1) * 32 * R, nrp) - 1;
+            if ((double)m <= ml[plast]) { exec += passes * psb::SHT_C * 32 * R; ++warps; }
+        }
+        for (int p = 0; p < nrp; ++p)
+            if ((double)m <= ml[p]) live += lmax - m + 1;
+    }
+    out[0] = exec; out[1] = live; out[2] = warps; out[3] = R; out[4] = nchunks;
+    return OK;
+}

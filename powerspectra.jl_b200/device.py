@@ -207,3 +207,42 @@ def dfma_peak(iters: int = 4096) -> float:
     if v < 0:
         _lib.check(2)
     return v
+
+
+# ---- W-spectrum production on device buffers (psb200_sht.cuh) -------------------------------------
+def alm_size(lmax: int) -> int:
+    return (lmax + 1) * (lmax + 2) // 2
+
+
+def map2alm_dev(nside: int, lmax: int, dmap: torch.Tensor, dalm: torch.Tensor, niter: int = 3):
+    """dalm (complex128, Healpix.jl Alm order) = map2alm(dmap; lmax, niter) on the current stream; dmap is not modified."""
+    _require_cuda(dmap)
+    if dalm.dtype != torch.complex128 or not dalm.is_cuda or not dalm.is_contiguous() or dalm.numel() != alm_size(lmax):
+        raise ValueError("dalm must be a contiguous complex128 CUDA tensor of (lmax+1)(lmax+2)/2 entries")
+    if dmap.numel() != 12 * nside * nside:
+        raise ValueError("dmap must hold 12 nside^2 pixels")
+    _lib.check(_lib.lib().psb200_map2alm_dev(nside, lmax, niter, C.c_void_p(dmap.data_ptr()), C.c_void_p(dalm.data_ptr()),
+                                             _stream_ptr()))
+
+
+def alm2map_dev(nside: int, lmax: int, dalm: torch.Tensor, dmap: torch.Tensor):
+    _require_cuda(dmap)
+    if dalm.dtype != torch.complex128 or not dalm.is_cuda or not dalm.is_contiguous() or dalm.numel() != alm_size(lmax):
+        raise ValueError("dalm must be a contiguous complex128 CUDA tensor of (lmax+1)(lmax+2)/2 entries")
+    if dmap.numel() != 12 * nside * nside:
+        raise ValueError("dmap must hold 12 nside^2 pixels")
+    _lib.check(_lib.lib().psb200_alm2map_dev(nside, lmax, C.c_void_p(dalm.data_ptr()), C.c_void_p(dmap.data_ptr()), _stream_ptr()))
+
+
+def alm2cl_dev(lmax: int, a: torch.Tensor, b: torch.Tensor, cl: torch.Tensor):
+    _require_cuda(cl)
+    if cl.numel() < lmax + 1 or a.numel() != alm_size(lmax) or b.numel() != alm_size(lmax):
+        raise ValueError("alm2cl_dev: sizes do not match lmax")
+    _lib.check(_lib.lib().psb200_alm2cl_dev(lmax, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(cl.data_ptr()),
+                                            _stream_ptr()))
+
+
+def sht_stats(nside: int, lmax: int):
+    st = (C.c_longlong * 5)()
+    _lib.check(_lib.lib().psb200_sht_stats(nside, lmax, st))
+    return {"exec_steps": int(st[0]), "live_steps": int(st[1]), "warps": int(st[2]), "R": int(st[3]), "chunks": int(st[4])}
