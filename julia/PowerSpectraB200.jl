@@ -275,4 +275,70 @@ function decouple_covmat_device(Y::SpectralArray{Float64,2}, B1::SpectralArray{F
     return M
 end
 
+"""
+    map2alm_device(maps...; lmax, niter = 3, scale = 1.0) -> Alm
+
+`Healpix.map2alm(scale .* maps[1] .* maps[2] .* ...; lmax, niter)` on the GPU (psb200_map2alm: ring FFTs, Legendre
+recurrences and the Jacobi iterations all on the device; 1 to 3 RING-ordered Float64 maps of one nside).
+"""
+function map2alm_device(maps::PowerSpectra.HealpixMap{Float64,PowerSpectra.RingOrder}...; lmax::Integer, niter::Integer = 3,
+                        scale::Real = 1.0)
+    1 <= length(maps) <= 3 || throw(ArgumentError("one to three maps"))
+    nside = maps[1].resolution.nside
+    all(m -> m.resolution.nside == nside, maps) || throw(ArgumentError("maps of different resolution"))
+    alm = PowerSpectra.Alm(lmax, lmax, zeros(ComplexF64, PowerSpectra.numberOfAlms(lmax, lmax)))
+    pix = [parent(m) for m in maps]
+    ptrs = [pointer(p) for p in pix]
+    GC.@preserve pix ptrs alm begin
+        rc = ccall((:psb200_map2alm, LIB[]), Cint,
+                   (Cint, Cint, Cint, Cint, Ptr{Ptr{Cdouble}}, Cdouble, Ptr{Cdouble}),
+                   nside, lmax, niter, length(pix), ptrs, Float64(scale), alm.alm)      # ComplexF64 = interleaved (re, im)
+    end
+    check(rc)
+    return alm
+end
+
+"""
+    alm2cl_device(a, b) -> Vector{Float64}
+
+`Healpix.alm2cl(a, b)` on the GPU for two full alm (mmax == lmax) of one lmax.
+"""
+function alm2cl_device(a::PowerSpectra.Alm, b::PowerSpectra.Alm)
+    (a.lmax == b.lmax && a.mmax == a.lmax && b.mmax == b.lmax) || throw(ArgumentError("two full alm of one lmax"))
+    cl = Vector{Float64}(undef, a.lmax + 1)
+    GC.@preserve a b cl begin
+        rc = ccall((:psb200_alm2cl, LIB[]), Cint, (Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), a.lmax, a.alm, b.alm, cl)
+    end
+    check(rc)
+    return cl
+end
+
+"""
+    enable_workspace!()
+
+Optional: re-define `effective_weight_alm!` (src/workspace.jl:141-171) so that the mask products and their `map2alm`
+run on the GPU; `window_function_W!` (:174-213) then works unchanged on the alm it caches.  HealpixMap workspaces only.
+"""
+function enable_workspace!()
+    @eval PowerSpectra begin
+        function effective_weight_alm!(workspace::CovarianceWorkspace{Float64,Dict{Tuple{String,Symbol},HealpixMap{Float64,RingOrder,Vector{Float64}}}},
+                                       A, i, j, α)
+            haskey(workspace.effective_weights, (A, i, j, α)) && return workspace.effective_weights[(A, i, j, α)]
+            X, Y = split_maptype(α)
+            lmax = workspace.lmax
+            m_iX, m_jY = workspace.mask_p[i, X], workspace.mask_p[j, Y]
+            if A == :∅∅
+                w = $(map2alm_device)(m_iX, m_jY; lmax = lmax)
+            elseif (A in (:II, :QQ, :UU)) && i == j
+                w = $(map2alm_device)(m_iX, m_jY, workspace.weight_p[i, A]; lmax = lmax, scale = pixsize(m_iX))
+            else
+                return Alm(lmax, lmax, zeros(ComplexF64, numberOfAlms(lmax, lmax)))
+            end
+            workspace.effective_weights[A, i, j, α] = w
+            return w
+        end
+    end
+    return nothing
+end
+
 end # module

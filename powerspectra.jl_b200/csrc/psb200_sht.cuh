@@ -36,7 +36,7 @@
 
 namespace psb {
 
-constexpr int SHT_C = 16;                 // l steps between reductions / rescale checks
+constexpr int SHT_C = 16;                 // largest number of l steps between reductions / rescale checks (kernels: 8 or 16)
 constexpr int SHT_WARPS = 4;              // warps per block of the Legendre kernels (independent of each other)
 constexpr double SHT_BIG = 2.58224987808690858965591917200e120;      // 2^400
 constexpr double SHT_DOWN = 1.49969681389882132575131978222e-241;    // 2^-800
@@ -171,28 +171,56 @@ template <class Ctx> PSB_HD void sht_twiddles(Ctx& cx, double2* T, int h)
     }
 }
 
-// Stockham autosort FFT of the h complex numbers in A (result returned in the buffer the function returns)
+// Stockham autosort FFT of the h complex numbers in A (result returned in the buffer the function returns).
+// Radix 4 and 2: one thread per butterfly, inputs read once (4 + 3 shared loads for 4 outputs); any other radix p: one
+// thread per output, p complex MACs against the table (a prime ring length costs O(h p), the HEALPix caps have them all).
 template <class Ctx> PSB_HD double2* sht_fft(Ctx& cx, double2* A, double2* B, const double2* T, int h, const int* rad, int nrad)
 {
     int Ns = 1;
     for (int q = 0; q < nrad; ++q) {
         const int Rr = rad[q], M = Ns * Rr, hR = h / Rr, hM = h / M;
-        for (int o = cx.tid; o < h; o += cx.nthr) {
-            const int k = o % Ns, qq = (o / Ns) % Rr, jhi = o / M;
-            const int j = jhi * Ns + k;
-            int step = k * hM + qq * hR;
-            if (step >= h) step -= h;
-            int idx = 0;
-            double ar = 0.0, ai = 0.0;
-            for (int r = 0; r < Rr; ++r) {
-                const double2 a = A[j + r * hR];
-                const double2 w = T[idx];
-                ar = fma(a.x, w.x, ar); ar = fma(-a.y, w.y, ar);
-                ai = fma(a.x, w.y, ai); ai = fma(a.y, w.x, ai);
-                idx += step;
-                if (idx >= h) idx -= h;
+        if (Rr == 4) {
+            for (int j = cx.tid; j < hR; j += cx.nthr) {
+                const int k = j % Ns, j0 = (j / Ns) * M + k;
+                const double2 a0 = A[j], a1 = A[j + hR], a2 = A[j + 2 * hR], a3 = A[j + 3 * hR];
+                const double2 w1 = T[k * hM], w2 = T[2 * k * hM], w3 = T[3 * k * hM];          // 3 k hM < 3 h / 4
+                const double b1r = a1.x * w1.x - a1.y * w1.y, b1i = a1.x * w1.y + a1.y * w1.x;
+                const double b2r = a2.x * w2.x - a2.y * w2.y, b2i = a2.x * w2.y + a2.y * w2.x;
+                const double b3r = a3.x * w3.x - a3.y * w3.y, b3i = a3.x * w3.y + a3.y * w3.x;
+                const double s0r = a0.x + b2r, s0i = a0.y + b2i, d0r = a0.x - b2r, d0i = a0.y - b2i;
+                const double s1r = b1r + b3r, s1i = b1i + b3i, d1r = b1r - b3r, d1i = b1i - b3i;
+                B[j0] = make_double2(s0r + s1r, s0i + s1i);
+                B[j0 + Ns] = make_double2(d0r + d1i, d0i - d1r);              // a0 - i b1 - b2 + i b3
+                B[j0 + 2 * Ns] = make_double2(s0r - s1r, s0i - s1i);
+                B[j0 + 3 * Ns] = make_double2(d0r - d1i, d0i + d1r);          // a0 + i b1 - b2 - i b3
             }
-            B[o] = make_double2(ar, ai);
+        } else if (Rr == 2) {
+            for (int j = cx.tid; j < hR; j += cx.nthr) {
+                const int k = j % Ns, j0 = (j / Ns) * M + k;
+                const double2 a0 = A[j], a1 = A[j + hR];
+                const double2 w1 = T[k * hM];
+                const double b1r = a1.x * w1.x - a1.y * w1.y, b1i = a1.x * w1.y + a1.y * w1.x;
+                B[j0] = make_double2(a0.x + b1r, a0.y + b1i);
+                B[j0 + Ns] = make_double2(a0.x - b1r, a0.y - b1i);
+            }
+        } else {
+            for (int o = cx.tid; o < h; o += cx.nthr) {
+                const int k = o % Ns, qq = (o / Ns) % Rr, jhi = o / M;
+                const int j = jhi * Ns + k;
+                int step = k * hM + qq * hR;
+                if (step >= h) step -= h;
+                int idx = 0;
+                double ar = 0.0, ai = 0.0;
+                for (int r = 0; r < Rr; ++r) {
+                    const double2 a = A[j + r * hR];
+                    const double2 w = T[idx];
+                    ar = fma(a.x, w.x, ar); ar = fma(-a.y, w.y, ar);
+                    ai = fma(a.x, w.y, ai); ai = fma(a.y, w.x, ai);
+                    idx += step;
+                    if (idx >= h) idx -= h;
+                }
+                B[o] = make_double2(ar, ai);
+            }
         }
         cx.sync();
         double2* t = A; A = B; B = t;
@@ -379,31 +407,40 @@ __global__ void sht_cmin_kernel(ShtDims D, int R, int* __restrict__ cmin)
     cmin[m] = c;
 }
 
-// butterfly: every lane holds 32 partial sums v[0..31]; on return lane L holds the warp total of v[L] in v[0].
-// 31 shuffles of 64 bits; the order of the additions is fixed.
-__device__ __forceinline__ void sht_butterfly(double (&v)[32], int lane)
+// butterfly: every lane holds NV (32 or 16) partial sums v[0..NV-1]; on return v[0] of lane L is the warp total of
+// v[L] (NV = 32) or of v[L >> 1] (NV = 16, held by both lanes of a pair).  NV - 1 (+1) shuffles of 64 bits; the order of
+// the additions is fixed.
+template <int NV> __device__ __forceinline__ void sht_butterfly(double (&v)[NV], int lane)
 {
 #pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const bool up = (lane & w) != 0;
+    for (int t = 0; t < 5; ++t) {
+        const int d = 16 >> t;
+        const int half = NV >> (t + 1);              // compile-time once unrolled: v stays in registers
+        if (half >= 1) {
+            const bool up = (lane & d) != 0;
 #pragma unroll
-        for (int i = 0; i < w; ++i) {
-            const double send = up ? v[i] : v[i + w];
-            const double keep = up ? v[i + w] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            for (int i = 0; i < half; ++i) {
+                const double send = up ? v[i] : v[i + half];
+                const double keep = up ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
         }
     }
 }
 
 // Legendre stage of the analysis: one warp per (m, chunk).  partial[chunk][2 (base(m) + l) + {0 re, 1 im}]
-template <int R>
+// R ring pairs per lane, C l steps between reductions; the coefficients of the next C steps are in flight while the
+// current ones are used; while no ring of the warp is representable yet the warp only advances the recurrences.
+template <int R, int C>
 __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDims D, const double4* __restrict__ Phi,
                                                                          const double2* __restrict__ coef,
                                                                          const double* __restrict__ cm,
                                                                          const int* __restrict__ cmin,
                                                                          double* __restrict__ partial)
 {
-    __shared__ double2 sco[SHT_WARPS][SHT_C];
+    __shared__ double2 sco[SHT_WARPS][C];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;
     const int m = blockIdx.x / bpm;
@@ -414,6 +451,7 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
     ShtLam q[R];
     double ger[R], gei[R], gor[R], goi[R];
     const int p0 = (chunk * 32 + lane) * R;
+    bool alive = false;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
         const int p = p0 + s;
@@ -424,27 +462,46 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
         if (q[s].e == 0) {
             const double4 t = Phi[(long long)m * D.nrp + p];
             ger[s] = t.x + t.z; gei[s] = t.y + t.w; gor[s] = t.x - t.z; goi[s] = t.y - t.w;
+            alive = true;
         }
     }
     double* out = partial + (long long)chunk * 2 * D.nalm + 2 * base;
-    for (int l0 = m; l0 <= D.lmax; l0 += SHT_C) {
-        if (lane < SHT_C) {
-            const int l = l0 + lane <= D.lmax ? l0 + lane : D.lmax;
-            sco[wid][lane] = coef[base + l];
-        }
+    double2 cnext = make_double2(0.0, 0.0);
+    if (lane < C) cnext = coef[base + (m + lane <= D.lmax ? m + lane : D.lmax)];
+    for (int l0 = m; l0 <= D.lmax; l0 += C) {
+        if (lane < C) sco[wid][lane] = cnext;
         __syncwarp();
-        double v[32];
+        if (lane < C && l0 + C <= D.lmax) cnext = coef[base + (l0 + C + lane <= D.lmax ? l0 + C + lane : D.lmax)];
+        if (__any_sync(0xffffffffu, alive)) {
+            double v[2 * C];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+            for (int i = 0; i < 2 * C; ++i) v[i] = 0.0;
 #pragma unroll
-        for (int j = 0; j < SHT_C; ++j) {
-            const double2 c = sco[wid][j];
+            for (int j = 0; j < C; ++j) {
+                const double2 c = sco[wid][j];
 #pragma unroll
-            for (int s = 0; s < R; ++s) {
-                if ((j & 1) == 0) { v[2 * j] = fma(q[s].lc, ger[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, gei[s], v[2 * j + 1]); }
-                else              { v[2 * j] = fma(q[s].lc, gor[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, goi[s], v[2 * j + 1]); }
-                sht_lam_advance(q[s], c.x, c.y);
+                for (int s = 0; s < R; ++s) {
+                    if ((j & 1) == 0) { v[2 * j] = fma(q[s].lc, ger[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, gei[s], v[2 * j + 1]); }
+                    else              { v[2 * j] = fma(q[s].lc, gor[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, goi[s], v[2 * j + 1]); }
+                    sht_lam_advance(q[s], c.x, c.y);
+                }
             }
+            sht_butterfly<2 * C>(v, lane);
+            if (C == 16) {
+                const int l = l0 + (lane >> 1);
+                if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0];
+            } else {
+                const int l = l0 + (lane >> 2);
+                if (l <= D.lmax && (lane & 1) == 0) out[2 * (long long)l + ((lane >> 1) & 1)] = v[0];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const double2 c = sco[wid][j];
+#pragma unroll
+                for (int s = 0; s < R; ++s) sht_lam_advance(q[s], c.x, c.y);
+            }
+            if (lane < 2 * C && l0 + (lane >> 1) <= D.lmax) out[2 * (long long)l0 + lane] = 0.0;
         }
         __syncwarp();
 #pragma unroll
@@ -452,11 +509,9 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
             if (sht_lam_rescale(q[s])) {
                 const double4 t = Phi[(long long)m * D.nrp + p0 + s];
                 ger[s] = t.x + t.z; gei[s] = t.y + t.w; gor[s] = t.x - t.z; goi[s] = t.y - t.w;
+                alive = true;
             }
         }
-        sht_butterfly(v, lane);
-        const int l = l0 + (lane >> 1);
-        if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0];
     }
 }
 
@@ -474,15 +529,14 @@ __global__ void sht_analysis_finish_kernel(ShtDims D, const double* __restrict__
 }
 
 // Legendre stage of the synthesis: one warp per (m, chunk); Phi[m nrp + p] = (F_N re, im, F_S re, im)
-template <int R>
+template <int R, int C>
 __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDims D, const double2* __restrict__ alm,
                                                                           const double2* __restrict__ coef,
                                                                           const double* __restrict__ cm,
                                                                           const int* __restrict__ cmin,
                                                                           double4* __restrict__ Phi)
 {
-    __shared__ double2 sco[SHT_WARPS][SHT_C];
-    __shared__ double2 sal[SHT_WARPS][SHT_C];
+    __shared__ double4 sca[SHT_WARPS][C];          // (c1, c2, a re, a im) of one l
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;
     const int m = blockIdx.x / bpm;
@@ -499,6 +553,7 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
     const double cm_m = cm[m];
     ShtLam q[R];
     double fer[R], fei[R], forr[R], foi[R];
+    bool alive = false;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
         const int p = p0 + s;
@@ -506,29 +561,47 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
         const ShtRing g = sht_ring(D.nside, ex ? p : 0);
         q[s] = sht_lam_start(D.lmax, m, cm_m, g.z, g.s, ex);
         fer[s] = fei[s] = forr[s] = foi[s] = 0.0;
+        alive |= q[s].e == 0;
     }
-    for (int l0 = m; l0 <= D.lmax; l0 += SHT_C) {
-        if (lane < SHT_C) {
-            const int l = l0 + lane;
-            sco[wid][lane] = coef[base + (l <= D.lmax ? l : D.lmax)];
-            sal[wid][lane] = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
-        }
+    double4 nxt = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (lane < C) {
+        const int l = m + lane;
+        const double2 c = coef[base + (l <= D.lmax ? l : D.lmax)];
+        const double2 a = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
+        nxt = make_double4(c.x, c.y, a.x, a.y);
+    }
+    for (int l0 = m; l0 <= D.lmax; l0 += C) {
+        if (lane < C) sca[wid][lane] = nxt;
         __syncwarp();
+        if (lane < C && l0 + C <= D.lmax) {
+            const int l = l0 + C + lane;
+            const double2 c = coef[base + (l <= D.lmax ? l : D.lmax)];
+            const double2 a = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
+            nxt = make_double4(c.x, c.y, a.x, a.y);
+        }
+        if (__any_sync(0xffffffffu, alive)) {
 #pragma unroll
-        for (int j = 0; j < SHT_C; ++j) {
-            const double2 c = sco[wid][j];
-            const double2 a = sal[wid][j];
+            for (int j = 0; j < C; ++j) {
+                const double4 c = sca[wid][j];
 #pragma unroll
-            for (int s = 0; s < R; ++s) {
-                if ((j & 1) == 0) { fer[s] = fma(q[s].lc, a.x, fer[s]); fei[s] = fma(q[s].lc, a.y, fei[s]); }
-                else              { forr[s] = fma(q[s].lc, a.x, forr[s]); foi[s] = fma(q[s].lc, a.y, foi[s]); }
-                sht_lam_advance(q[s], c.x, c.y);
+                for (int s = 0; s < R; ++s) {
+                    if ((j & 1) == 0) { fer[s] = fma(q[s].lc, c.z, fer[s]); fei[s] = fma(q[s].lc, c.w, fei[s]); }
+                    else              { forr[s] = fma(q[s].lc, c.z, forr[s]); foi[s] = fma(q[s].lc, c.w, foi[s]); }
+                    sht_lam_advance(q[s], c.x, c.y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const double4 c = sca[wid][j];
+#pragma unroll
+                for (int s = 0; s < R; ++s) sht_lam_advance(q[s], c.x, c.y);
             }
         }
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < R; ++s)
-            if (sht_lam_rescale(q[s])) fer[s] = fei[s] = forr[s] = foi[s] = 0.0;      // what was summed so far was scaled garbage
+            if (sht_lam_rescale(q[s])) { fer[s] = fei[s] = forr[s] = foi[s] = 0.0; alive = true; }    // what was summed so far was scaled garbage
     }
 #pragma unroll
     for (int s = 0; s < R; ++s) {

@@ -2,7 +2,7 @@
 // Included by psb200.cu inside its anonymous namespace.
 
 struct ShtPlan {                      // per device and (nside, lmax): tables + work buffers, kept between calls
-    int nside = 0, lmax = 0, R = 0;
+    int nside = 0, lmax = 0, R = 0, C = 0;
     psb::ShtDims D{};
     double2* coef = nullptr;          // recurrence coefficients, alm layout
     double* cm = nullptr;             // log2 |lambda_mm| prefactors
@@ -31,6 +31,13 @@ int sht_R()
     return (r == 2 || r == 4 || r == 8) ? r : 4;
 }
 
+int sht_C()
+{
+    const char* e = getenv("PSB200_SHT_C");
+    const int c = e ? atoi(e) : 16;
+    return c == 8 ? 8 : 16;
+}
+
 int sht_check(int nside, int lmax)
 {
     if (nside < 1 || nside > 2048 || (nside & (nside - 1)))
@@ -44,7 +51,7 @@ int sht_plan(int dev, int nside, int lmax, cudaStream_t st, ShtPlan** out)
 {
     ShtPlan& P = g_sht[dev];
     const int R = sht_R();
-    if (P.nside == nside && P.lmax == lmax && P.R == R) { *out = &P; return OK; }
+    if (P.nside == nside && P.lmax == lmax && P.R == R) { P.C = sht_C(); *out = &P; return OK; }
     CUDA_TRY(cudaDeviceSynchronize());
     sht_free(P);
     psb::ShtDims D;
@@ -80,7 +87,7 @@ int sht_plan(int dev, int nside, int lmax, cudaStream_t st, ShtPlan** out)
         CUDA_TRY(cudaFuncSetAttribute(psb::sht_ring_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_TRY(cudaFuncSetAttribute(psb::sht_ring_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    P.nside = nside; P.lmax = lmax; P.R = R; P.D = D;
+    P.nside = nside; P.lmax = lmax; P.R = R; P.C = sht_C(); P.D = D;
     *out = &P;
     return OK;
 }
@@ -110,11 +117,16 @@ int sht_analysis(ShtPlan& P, cudaStream_t st, const double* dmap, double* dalm, 
         })) return rc;
     const int bpm = (D.nchunks + psb::SHT_WARPS - 1) / psb::SHT_WARPS;
     const unsigned grid = (unsigned)((D.lmax + 1) * bpm);
-    switch (P.R) {
-        case 2: psb::sht_leg_analysis_kernel<2><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial); break;
-        case 8: psb::sht_leg_analysis_kernel<8><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial); break;
-        default: psb::sht_leg_analysis_kernel<4><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial);
+#define PSB_SHT_ANA(RR, CC) psb::sht_leg_analysis_kernel<RR, CC><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial)
+    switch (P.R * 100 + P.C) {
+        case 208: PSB_SHT_ANA(2, 8); break;
+        case 216: PSB_SHT_ANA(2, 16); break;
+        case 408: PSB_SHT_ANA(4, 8); break;
+        case 808: PSB_SHT_ANA(8, 8); break;
+        case 816: PSB_SHT_ANA(8, 16); break;
+        default: PSB_SHT_ANA(4, 16);
     }
+#undef PSB_SHT_ANA
     CUDA_TRY(cudaGetLastError());
     psb::sht_analysis_finish_kernel<<<dim3((unsigned)((2 * (D.lmax + 1) + 127) / 128), (unsigned)(D.lmax + 1)), 128, 0, st>>>(
         D, P.partial, P.cmin, accumulate, dalm);
@@ -128,11 +140,16 @@ int sht_synthesis(ShtPlan& P, cudaStream_t st, const double* dalm, const double*
     const psb::ShtDims D = P.D;
     const int bpm = (D.nchunks + psb::SHT_WARPS - 1) / psb::SHT_WARPS;
     const unsigned grid = (unsigned)((D.lmax + 1) * bpm);
-    switch (P.R) {
-        case 2: psb::sht_leg_synthesis_kernel<2><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, (const double2*)dalm, P.coef, P.cm, P.cmin, P.Phi); break;
-        case 8: psb::sht_leg_synthesis_kernel<8><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, (const double2*)dalm, P.coef, P.cm, P.cmin, P.Phi); break;
-        default: psb::sht_leg_synthesis_kernel<4><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, (const double2*)dalm, P.coef, P.cm, P.cmin, P.Phi);
+#define PSB_SHT_SYN(RR, CC) psb::sht_leg_synthesis_kernel<RR, CC><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, (const double2*)dalm, P.coef, P.cm, P.cmin, P.Phi)
+    switch (P.R * 100 + P.C) {
+        case 208: PSB_SHT_SYN(2, 8); break;
+        case 216: PSB_SHT_SYN(2, 16); break;
+        case 408: PSB_SHT_SYN(4, 8); break;
+        case 808: PSB_SHT_SYN(8, 8); break;
+        case 816: PSB_SHT_SYN(8, 16); break;
+        default: PSB_SHT_SYN(4, 16);
     }
+#undef PSB_SHT_SYN
     CUDA_TRY(cudaGetLastError());
     return sht_ring_launches(P, [&](int lo, int cnt, int threads, size_t smem) {
         psb::sht_ring_synthesis_kernel<<<dim3((unsigned)cnt, 2), threads, smem, st>>>(D, lo, (const double2*)P.Phi, ref, dmap);

@@ -103,24 +103,24 @@ int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
 /* Work accounting of one Legendre pass (analysis or synthesis) as the kernel tiles it; host arithmetic.
  *   out[0] executed (l, m, ring-pair slot) steps: every started warp x its 16-step passes x 32 R slots
  *   out[1] steps of rings the transform starts (m <= mlim), l = m..lmax
- *   out[2] warps started   out[3] R   out[4] chunks */
+ *   out[2] warps started   out[3] R   out[4] chunks   out[5] l steps per pass */
 int psb200_sht_stats(int nside, int lmax, long long* out)
 {
     if (nside < 1 || nside > 2048 || (nside & (nside - 1)) || lmax < 0 || lmax > 4 * nside - 1 || !out)
         return fail(ERR_ARG, "sht_stats: bad arguments");
-    const int R = sht_R(), nrp = 2 * nside, nchunks = (nrp + 32 * R - 1) / (32 * R);
+    const int R = sht_R(), C = sht_C(), nrp = 2 * nside, nchunks = (nrp + 32 * R - 1) / (32 * R);
     std::vector<double> ml(nrp);
     for (int p = 0; p < nrp; ++p) ml[p] = psb::sht_mlim(lmax, psb::sht_ring(nside, p).s);
     long long exec = 0, live = 0, warps = 0;
     for (int m = 0; m <= lmax; ++m) {
-        const long long passes = (lmax - m + psb::SHT_C) / psb::SHT_C;
+        const long long passes = (lmax - m + C) / C;
         for (int c = 0; c < nchunks; ++c) {
             const int plast = std::min((c + 1) * 32 * R, nrp) - 1;
-            if ((double)m <= ml[plast]) { exec += passes * psb::SHT_C * 32 * R; ++warps; }
+            if ((double)m <= ml[plast]) { exec += passes * C * 32 * R; ++warps; }
         }
         for (int p = 0; p < nrp; ++p)
             if ((double)m <= ml[p]) live += lmax - m + 1;
     }
-    out[0] = exec; out[1] = live; out[2] = warps; out[3] = R; out[4] = nchunks;
+    out[0] = exec; out[1] = live; out[2] = warps; out[3] = R; out[4] = nchunks; out[5] = C;
     return OK;
 }

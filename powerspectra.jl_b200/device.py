@@ -243,6 +243,7 @@ def alm2cl_dev(lmax: int, a: torch.Tensor, b: torch.Tensor, cl: torch.Tensor):
 
 
 def sht_stats(nside: int, lmax: int):
-    st = (C.c_longlong * 5)()
+    st = (C.c_longlong * 6)()
     _lib.check(_lib.lib().psb200_sht_stats(nside, lmax, st))
-    return {"exec_steps": int(st[0]), "live_steps": int(st[1]), "warps": int(st[2]), "R": int(st[3]), "chunks": int(st[4])}
+    return {"exec_steps": int(st[0]), "live_steps": int(st[1]), "warps": int(st[2]), "R": int(st[3]), "chunks": int(st[4]),
+            "C": int(st[5])}

@@ -206,11 +206,11 @@ def test_host_transforms_vs_oracle(hc, nside, lmax):
 def test_sht_stats_accounting():
     import ctypes as C
     import powerspectra_jl_b200 as ps
-    out = (C.c_longlong * 5)()
+    out = (C.c_longlong * 6)()
     assert ps.lib().psb200_sht_stats(64, 191, out) == 0
-    exec_, live, warps, R, chunks = list(out)
+    exec_, live, warps, R, chunks, steps = list(out)
     naive = sum((191 - m + 1) for m in range(192)) * 128
-    assert R == 4 and chunks == 1 and warps == 192 and live <= naive and exec_ >= live
+    assert R == 4 and steps == 16 and chunks == 1 and warps == 192 and live <= naive and exec_ >= live
     assert ps.lib().psb200_sht_stats(2048, 6143, out) == 0
     assert 0.55 < out[1] / (sum(6144 - m for m in range(6144)) * 4096) < 0.9       # rings skipped near the poles
     assert out[1] / out[0] > 0.7
@@ -263,8 +263,9 @@ def test_gpu_vs_host_build_medium(ps, hc, nside, lmax):
 @pytest.mark.parametrize("nside", [1024, 2048])
 def test_gpu_full_size_properties(ps, nside):
     """BASELINE-size maps (nside 2048 <-> lmax 6143): a constant map is Y_00 alone; a band-limited field (lmax = 1.5 nside)
-    synthesised on the device is recovered by map2alm with 3 iterations; Parseval ties alm2cl to the pixel variance;
-    two runs are bit-identical (nothing is accumulated atomically)."""
+    synthesised on the device is recovered by map2alm as the Jacobi iterations proceed (the HEALPix quadrature is not
+    exact: 1e-3 without iterations, ~1e-7 after the default 3, below 1e-9 after 8); Parseval ties alm2cl to the pixel
+    variance; two runs are bit-identical (nothing is accumulated atomically)."""
     lmax = 3 * nside // 2
     one = ps.map2alm(ps.HealpixMap(np.ones(12 * nside * nside)), lmax=lmax, niter=0).alm
     assert abs(one[0] - np.sqrt(4 * np.pi)) < 1e-13
@@ -275,10 +276,14 @@ def test_gpu_full_size_properties(ps, nside):
     a[:lmax + 1] = a[:lmax + 1].real
     a *= np.exp(-0.5 * (np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)]) / (0.4 * lmax)) ** 2)
     f = ps.alm2map(ps.Alm(lmax, lmax, a), nside)
+    e0 = rel(ps.map2alm(f, lmax=lmax, niter=0).alm, a)
     back = ps.map2alm(f, lmax=lmax, niter=3)
-    assert rel(back.alm, a) < 1e-9
+    e3 = rel(back.alm, a)
+    assert 1e-5 < e0 < 1e-2 and e3 < 1e-3 * e0 and e3 < 1e-6
     again = ps.map2alm(f, lmax=lmax, niter=3)
     assert np.array_equal(back.alm, again.alm)
+    back = ps.map2alm(f, lmax=lmax, niter=8)
+    assert rel(back.alm, a) < 1e-9
     cl = ps.alm2cl_device(back)
     parseval = float(np.sum((2 * np.arange(lmax + 1) + 1) * cl) / (4 * np.pi))
     assert abs(parseval - float(np.mean(f.pixels ** 2))) < 1e-6 * parseval

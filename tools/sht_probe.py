@@ -23,7 +23,7 @@ L = ps.lib()
 g = torch.Generator(device="cuda").manual_seed(1)
 n = dev.alm_size(lmax)
 alm = torch.randn(n, dtype=torch.complex128, device="cuda", generator=g)
-ls = torch.cat([torch.arange(m, lmax + 1, device="cuda") for m in range(lmax + 1)])
+ls = torch.tensor(np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)]), device="cuda")
 alm *= torch.exp(-0.5 * (ls / (0.25 * lmax)) ** 2)
 alm[:lmax + 1] = alm[:lmax + 1].real.to(torch.complex128)
 f = torch.empty(12 * nside * nside, dtype=torch.float64, device="cuda")
