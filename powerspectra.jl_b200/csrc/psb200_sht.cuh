@@ -36,7 +36,7 @@
 
 namespace psb {
 
-constexpr int SHT_C = 16;                 // largest number of l steps between reductions / rescale checks (kernels: 8 or 16)
+constexpr int SHT_C = 16;                 // l steps between reductions / rescale checks (8: same time per step, measured)
 constexpr int SHT_WARPS = 4;              // warps per block of the Legendre kernels (independent of each other)
 constexpr double SHT_BIG = 2.58224987808690858965591917200e120;      // 2^400
 constexpr double SHT_DOWN = 1.49969681389882132575131978222e-241;    // 2^-800
@@ -150,7 +150,8 @@ PSB_HD void sht_sincospi(double a, double* s, double* c)
 // very same code with one "thread"; on the device the context is the thread block.
 // ------------------------------------------------------------------------------------------------------------------
 
-// radices of h: 4s first, then primes in increasing order (a prime radix p costs p complex MACs per output)
+// radices of h: the largest odd prime first (the first stage has no stage twiddles, which lets sht_fft evaluate its
+// outputs q and p - q from one pass over the inputs), then 4s, a 2, and the remaining primes in increasing order
 PSB_HD int sht_factor(int h, int* rad)
 {
     int n = 0;
@@ -158,6 +159,11 @@ PSB_HD int sht_factor(int h, int* rad)
     for (int p = 2; p * p <= h; ++p)
         while (h % p == 0) { rad[n++] = p; h /= p; }
     if (h > 1) rad[n++] = h;
+    if (n > 1 && (rad[n - 1] & 1)) {
+        const int big = rad[n - 1];
+        for (int i = n - 1; i > 0; --i) rad[i] = rad[i - 1];
+        rad[0] = big;
+    }
     return n;
 }
 
@@ -172,14 +178,36 @@ template <class Ctx> PSB_HD void sht_twiddles(Ctx& cx, double2* T, int h)
 }
 
 // Stockham autosort FFT of the h complex numbers in A (result returned in the buffer the function returns).
-// Radix 4 and 2: one thread per butterfly, inputs read once (4 + 3 shared loads for 4 outputs); any other radix p: one
-// thread per output, p complex MACs against the table (a prime ring length costs O(h p), the HEALPix caps have them all).
+// Radix 4 and 2: one thread per butterfly, inputs read once (4 + 3 shared loads for 4 outputs); the largest odd prime p
+// goes first and costs h (p+1)/2 half-price complex MACs (a prime ring length is O(h p): the HEALPix caps have them all);
+// any other odd radix: one thread per output, p complex MACs against the table.
 template <class Ctx> PSB_HD double2* sht_fft(Ctx& cx, double2* A, double2* B, const double2* T, int h, const int* rad, int nrad)
 {
     int Ns = 1;
     for (int q = 0; q < nrad; ++q) {
         const int Rr = rad[q], M = Ns * Rr, hR = h / Rr, hM = h / M;
-        if (Rr == 4) {
+        if (q == 0 && (Rr & 1)) {
+            // first stage, odd radix p (Ns = 1): out[j p + q] = sum_r A[j + r h/p] w^(q r), w = exp(-2 pi i / p); outputs q and
+            // p - q share every load and half the products (w^((p-q) r) = conj w^(q r)); consecutive threads take consecutive
+            // j, so the table load is a warp-wide broadcast
+            const int hq = (Rr + 1) / 2;
+            for (int it = cx.tid; it < hR * hq; it += cx.nthr) {
+                const int j = it % hR, qi = it / hR;
+                const int step = qi * hR;
+                int idx = 0;
+                double P = 0.0, Q = 0.0, U = 0.0, V = 0.0;
+                for (int r = 0; r < Rr; ++r) {
+                    const double2 a = A[j + r * hR];
+                    const double2 w = T[idx];
+                    P = fma(a.x, w.x, P); Q = fma(a.y, w.y, Q);
+                    U = fma(a.x, w.y, U); V = fma(a.y, w.x, V);
+                    idx += step;
+                    if (idx >= h) idx -= h;
+                }
+                B[j * Rr + qi] = make_double2(P - Q, U + V);
+                if (qi) B[j * Rr + Rr - qi] = make_double2(P + Q, V - U);
+            }
+        } else if (Rr == 4) {
             for (int j = cx.tid; j < hR; j += cx.nthr) {
                 const int k = j % Ns, j0 = (j / Ns) * M + k;
                 const double2 a0 = A[j], a1 = A[j + hR], a2 = A[j + 2 * hR], a3 = A[j + 3 * hR];
@@ -341,7 +369,7 @@ struct ShtBlockCtx {
 
 // Phi[(m nrp + p) 2 + hemi] (double2): hemi 0 = north ring p+1, 1 = its southern partner (zero for the equator)
 // grid.x = ring pairs [p_lo, p_lo + gridDim.x), grid.y = 2 hemispheres; dynamic shared memory 3 h_max double2
-__global__ void __launch_bounds__(256) sht_ring_analysis_kernel(ShtDims D, int p_lo, const double* __restrict__ map,
+__global__ void __launch_bounds__(512) sht_ring_analysis_kernel(ShtDims D, int p_lo, const double* __restrict__ map,
                                                                 double2* __restrict__ Phi)
 {
     extern __shared__ double2 sht_smem[];
@@ -363,7 +391,7 @@ __global__ void __launch_bounds__(256) sht_ring_analysis_kernel(ShtDims D, int p
                      D.lmax, sht_smem, sht_smem + h, sht_smem + 2 * h, rad, nrad, out, ostride);
 }
 
-__global__ void __launch_bounds__(256) sht_ring_synthesis_kernel(ShtDims D, int p_lo, const double2* __restrict__ Phi,
+__global__ void __launch_bounds__(512) sht_ring_synthesis_kernel(ShtDims D, int p_lo, const double2* __restrict__ Phi,
                                                                  const double* __restrict__ ref, double* __restrict__ map)
 {
     extern __shared__ double2 sht_smem[];
@@ -407,41 +435,42 @@ __global__ void sht_cmin_kernel(ShtDims D, int R, int* __restrict__ cmin)
     cmin[m] = c;
 }
 
-// butterfly: every lane holds NV (32 or 16) partial sums v[0..NV-1]; on return v[0] of lane L is the warp total of
-// v[L] (NV = 32) or of v[L >> 1] (NV = 16, held by both lanes of a pair).  NV - 1 (+1) shuffles of 64 bits; the order of
-// the additions is fixed.
-template <int NV> __device__ __forceinline__ void sht_butterfly(double (&v)[NV], int lane)
+// butterfly of the analysis: every lane holds the partial sums of 16 l steps, v[2j] and v[2j+1]; EVEN lanes hold
+// (re, im) there and ODD lanes (im, re) -- they swap their G registers when they load them -- so the first exchange,
+// between the lanes of a pair, needs no selects: afterwards even lanes own the 16 real parts and odd lanes the 16
+// imaginary parts.  Four select-and-exchange stages (xor 16, 8, 4, 2) then halve 16 -> 1: on return v[0] of lane L is
+// the warp total of step L >> 1, component L & 1.  31 shuffles of 64 bits; the order of the additions is fixed.
+__device__ __forceinline__ void sht_butterfly(double (&v)[32], int lane)
 {
 #pragma unroll
-    for (int t = 0; t < 5; ++t) {
-        const int d = 16 >> t;
-        const int half = NV >> (t + 1);              // compile-time once unrolled: v stays in registers
-        if (half >= 1) {
-            const bool up = (lane & d) != 0;
+    for (int j = 0; j < 16; ++j) v[j] = v[2 * j] + __shfl_xor_sync(0xffffffffu, v[2 * j + 1], 1);
 #pragma unroll
-            for (int i = 0; i < half; ++i) {
-                const double send = up ? v[i] : v[i + half];
-                const double keep = up ? v[i + half] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
-            }
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+    for (int t = 0; t < 4; ++t) {
+        const int d = 16 >> t, half = 8 >> t;          // compile-time once unrolled: v stays in registers
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
         }
     }
 }
 
 // Legendre stage of the analysis: one warp per (m, chunk).  partial[chunk][2 (base(m) + l) + {0 re, 1 im}]
-// R ring pairs per lane, C l steps between reductions; the coefficients of the next C steps are in flight while the
+// R ring pairs per lane, C = 16 l steps between reductions; the coefficients of the next C steps are in flight while the
 // current ones are used; while no ring of the warp is representable yet the warp only advances the recurrences.
-template <int R, int C>
+template <int R>
 __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDims D, const double4* __restrict__ Phi,
                                                                          const double2* __restrict__ coef,
                                                                          const double* __restrict__ cm,
                                                                          const int* __restrict__ cmin,
                                                                          double* __restrict__ partial)
 {
+    constexpr int C = SHT_C;
     __shared__ double2 sco[SHT_WARPS][C];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool odd = (lane & 1) != 0;                  // odd lanes keep (im, re) where even lanes keep (re, im): sht_butterfly
     const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;
     const int m = blockIdx.x / bpm;
     const int chunk = (blockIdx.x % bpm) * SHT_WARPS + wid;
@@ -461,7 +490,8 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
         ger[s] = gei[s] = gor[s] = goi[s] = 0.0;
         if (q[s].e == 0) {
             const double4 t = Phi[(long long)m * D.nrp + p];
-            ger[s] = t.x + t.z; gei[s] = t.y + t.w; gor[s] = t.x - t.z; goi[s] = t.y - t.w;
+            ger[s] = odd ? t.y + t.w : t.x + t.z; gei[s] = odd ? t.x + t.z : t.y + t.w;
+            gor[s] = odd ? t.y - t.w : t.x - t.z; goi[s] = odd ? t.x - t.z : t.y - t.w;
             alive = true;
         }
     }
@@ -486,14 +516,9 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
                     sht_lam_advance(q[s], c.x, c.y);
                 }
             }
-            sht_butterfly<2 * C>(v, lane);
-            if (C == 16) {
-                const int l = l0 + (lane >> 1);
-                if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0];
-            } else {
-                const int l = l0 + (lane >> 2);
-                if (l <= D.lmax && (lane & 1) == 0) out[2 * (long long)l + ((lane >> 1) & 1)] = v[0];
-            }
+            sht_butterfly(v, lane);
+            const int l = l0 + (lane >> 1);
+            if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0];
         } else {
 #pragma unroll
             for (int j = 0; j < C; ++j) {
@@ -508,7 +533,8 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
         for (int s = 0; s < R; ++s) {
             if (sht_lam_rescale(q[s])) {
                 const double4 t = Phi[(long long)m * D.nrp + p0 + s];
-                ger[s] = t.x + t.z; gei[s] = t.y + t.w; gor[s] = t.x - t.z; goi[s] = t.y - t.w;
+                ger[s] = odd ? t.y + t.w : t.x + t.z; gei[s] = odd ? t.x + t.z : t.y + t.w;
+                gor[s] = odd ? t.y - t.w : t.x - t.z; goi[s] = odd ? t.x - t.z : t.y - t.w;
                 alive = true;
             }
         }
@@ -529,13 +555,14 @@ __global__ void sht_analysis_finish_kernel(ShtDims D, const double* __restrict__
 }
 
 // Legendre stage of the synthesis: one warp per (m, chunk); Phi[m nrp + p] = (F_N re, im, F_S re, im)
-template <int R, int C>
+template <int R>
 __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDims D, const double2* __restrict__ alm,
                                                                           const double2* __restrict__ coef,
                                                                           const double* __restrict__ cm,
                                                                           const int* __restrict__ cmin,
                                                                           double4* __restrict__ Phi)
 {
+    constexpr int C = SHT_C;
     __shared__ double4 sca[SHT_WARPS][C];          // (c1, c2, a re, a im) of one l
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;

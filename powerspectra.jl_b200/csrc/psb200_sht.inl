@@ -31,12 +31,7 @@ int sht_R()
     return (r == 2 || r == 4 || r == 8) ? r : 4;
 }
 
-int sht_C()
-{
-    const char* e = getenv("PSB200_SHT_C");
-    const int c = e ? atoi(e) : 16;
-    return c == 8 ? 8 : 16;
-}
+int sht_C() { return psb::SHT_C; }
 
 int sht_check(int nside, int lmax)
 {
@@ -101,7 +96,7 @@ template <class F> int sht_ring_launches(const ShtPlan& P, F launch)
         const int lo = edges[c], hi = edges[c + 1];
         if (hi <= lo) continue;
         const int hmax = 2 * std::min(hi, N);
-        const int threads = hmax >= 512 ? 256 : 64;
+        const int threads = hmax >= 2048 ? 512 : hmax >= 512 ? 256 : 64;
         if (int rc = launch(lo, hi - lo, threads, (size_t)3 * hmax * sizeof(double2))) return rc;
     }
     return OK;
@@ -117,14 +112,11 @@ int sht_analysis(ShtPlan& P, cudaStream_t st, const double* dmap, double* dalm, 
         })) return rc;
     const int bpm = (D.nchunks + psb::SHT_WARPS - 1) / psb::SHT_WARPS;
     const unsigned grid = (unsigned)((D.lmax + 1) * bpm);
-#define PSB_SHT_ANA(RR, CC) psb::sht_leg_analysis_kernel<RR, CC><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial)
-    switch (P.R * 100 + P.C) {
-        case 208: PSB_SHT_ANA(2, 8); break;
-        case 216: PSB_SHT_ANA(2, 16); break;
-        case 408: PSB_SHT_ANA(4, 8); break;
-        case 808: PSB_SHT_ANA(8, 8); break;
-        case 816: PSB_SHT_ANA(8, 16); break;
-        default: PSB_SHT_ANA(4, 16);
+#define PSB_SHT_ANA(RR) psb::sht_leg_analysis_kernel<RR><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial)
+    switch (P.R) {
+        case 2: PSB_SHT_ANA(2); break;
+        case 8: PSB_SHT_ANA(8); break;
+        default: PSB_SHT_ANA(4);
     }
 #undef PSB_SHT_ANA
     CUDA_TRY(cudaGetLastError());
@@ -140,14 +132,11 @@ int sht_synthesis(ShtPlan& P, cudaStream_t st, const double* dalm, const double*
     const psb::ShtDims D = P.D;
     const int bpm = (D.nchunks + psb::SHT_WARPS - 1) / psb::SHT_WARPS;
     const unsigned grid = (unsigned)((D.lmax + 1) * bpm);
-#define PSB_SHT_SYN(RR, CC) psb::sht_leg_synthesis_kernel<RR, CC><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, (const double2*)dalm, P.coef, P.cm, P.cmin, P.Phi)
-    switch (P.R * 100 + P.C) {
-        case 208: PSB_SHT_SYN(2, 8); break;
-        case 216: PSB_SHT_SYN(2, 16); break;
-        case 408: PSB_SHT_SYN(4, 8); break;
-        case 808: PSB_SHT_SYN(8, 8); break;
-        case 816: PSB_SHT_SYN(8, 16); break;
-        default: PSB_SHT_SYN(4, 16);
+#define PSB_SHT_SYN(RR) psb::sht_leg_synthesis_kernel<RR><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, (const double2*)dalm, P.coef, P.cm, P.cmin, P.Phi)
+    switch (P.R) {
+        case 2: PSB_SHT_SYN(2); break;
+        case 8: PSB_SHT_SYN(8); break;
+        default: PSB_SHT_SYN(4);
     }
 #undef PSB_SHT_SYN
     CUDA_TRY(cudaGetLastError());
