@@ -302,46 +302,48 @@ PSB_HD void sht_ring_analyse(Ctx& cx, const double* f, int n, int shifted, doubl
 // If `ref` is given the ring written is ref - f (the residual of a Jacobi iteration).
 template <class Ctx>
 PSB_HD void sht_ring_synthesise(Ctx& cx, const double2* in, long long istride, int n, int shifted, int mmax,
-                                double2* A, double2* B, double2* T, const int* rad, int nrad, const double* ref, double* f)
+                                double2* A, double2* B, double2* T, double2* W, const int* rad, int nrad, const double* ref,
+                                double* f)
 {
     const int h = n / 2;
     sht_twiddles(cx, T, h);
-    // S[j], j = 0..h:  sum_{m = j, j+n, ...} P_m  +  sum_{m = n-j, 2n-j, ... > 0} conj P_m,   P_m = F_m exp(i m phi0), P_0 -> Re
-    // kept in B[0..h-1] and (S[h], real) in a register of every thread that needs it -> recomputed below
-    for (int j = cx.tid; j < h; j += cx.nthr) {
+    // S[j], j = 0..h (B holds h+1 entries):  sum_{m = j, j+n, ...} P_m  +  sum_{m = n-j, 2n-j, ... > 0} conj P_m,
+    // P_m = F_m exp(i m phi0), P_0 -> Re.  Short rings fold mmax/n terms per entry: the terms of an entry are dealt to
+    // G = nthr/(h+1) threads whose partial sums (W, nthr entries) are added in a fixed order.
+    const int G = cx.nthr / (h + 1) > 1 ? cx.nthr / (h + 1) : 1;
+    for (int it = cx.tid; it < (h + 1) * G; it += cx.nthr) {
+        const int j = it % (h + 1), g = it / (h + 1);
         double sr = 0.0, si = 0.0;
-        for (int m = j; m <= mmax; m += n) {
+        for (int m = j + g * n; m <= mmax; m += G * n) {
             double2 v = in[(long long)m * istride];
             double pr = 1.0, pi = 0.0;
             if (shifted) { double s, c; sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c); pr = c; pi = s; }
-            const double xr = v.x * pr - v.y * pi, xi = v.x * pi + v.y * pr;
-            sr += xr;
-            si += (m == 0) ? 0.0 : xi;
+            sr += v.x * pr - v.y * pi;
+            si += v.x * pi + v.y * pr;
         }
-        for (int m = n - j; m <= mmax; m += n) {
+        for (int m = n - j + g * n; m <= mmax; m += G * n) {
             double2 v = in[(long long)m * istride];
             double pr = 1.0, pi = 0.0;
             if (shifted) { double s, c; sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c); pr = c; pi = s; }
-            const double xr = v.x * pr - v.y * pi, xi = v.x * pi + v.y * pr;
-            sr += xr;
-            si -= xi;
+            sr += v.x * pr - v.y * pi;
+            si -= v.x * pi + v.y * pr;
         }
-        B[j] = make_double2(sr, si);
+        if (G > 1) W[g * (h + 1) + j] = make_double2(sr, si);
+        else B[j] = make_double2(sr, (j == 0 || j == h) ? 0.0 : si);          // S_0 and S_h are real
     }
     cx.sync();
-    // S[h] = sum over m = h, h+n, ... of (P_m + conj P_m) = 2 Re P_m
-    double sh = 0.0;
-    for (int m = h; m <= mmax; m += n) {
-        double2 v = in[(long long)m * istride];
-        double pr = 1.0, pi = 0.0;
-        if (shifted) { double s, c; sht_sincospi((double)(m % (2 * n)) / (double)n, &s, &c); pr = c; pi = s; }
-        sh += 2.0 * (v.x * pr - v.y * pi);
+    if (G > 1) {
+        for (int j = cx.tid; j <= h; j += cx.nthr) {
+            double sr = 0.0, si = 0.0;
+            for (int g = 0; g < G; ++g) { sr += W[g * (h + 1) + j].x; si += W[g * (h + 1) + j].y; }
+            B[j] = make_double2(sr, (j == 0 || j == h) ? 0.0 : si);
+        }
+        cx.sync();
     }
     // conj Z'_j,  Z'_j = (S_j + conj S_{h-j}) + i exp(2 pi i j/n) (S_j - conj S_{h-j})
     for (int j = cx.tid; j < h; j += cx.nthr) {
         const double2 a = B[j];
-        double2 b;
-        if (j == 0) b = make_double2(sh, 0.0); else b = B[h - j];
+        const double2 b = B[h - j];
         double s, c;
         sht_sincospi((double)j / (double)h, &s, &c);     // exp(+2 pi i j / n) = c + i s
         const double er = a.x + b.x, ei = a.y - b.y;
@@ -368,7 +370,7 @@ struct ShtBlockCtx {
 };
 
 // Phi[(m nrp + p) 2 + hemi] (double2): hemi 0 = north ring p+1, 1 = its southern partner (zero for the equator)
-// grid.x = ring pairs [p_lo, p_lo + gridDim.x), grid.y = 2 hemispheres; dynamic shared memory 3 h_max double2
+// grid.x = ring pairs [p_lo, p_lo + gridDim.x), grid.y = 2 hemispheres; dynamic shared memory (3 h_max + 1 + blockDim.x) double2
 __global__ void __launch_bounds__(512) sht_ring_analysis_kernel(ShtDims D, int p_lo, const double* __restrict__ map,
                                                                 double2* __restrict__ Phi)
 {
@@ -406,7 +408,8 @@ __global__ void __launch_bounds__(512) sht_ring_synthesis_kernel(ShtDims D, int 
     ShtBlockCtx cx{(int)threadIdx.x, (int)blockDim.x};
     const long long st = hemi ? g.startS : g.startN;
     sht_ring_synthesise(cx, Phi + ((long long)p * 2 + hemi), (long long)D.nrp * 2, g.n, g.shifted, D.lmax,
-                        sht_smem, sht_smem + h, sht_smem + 2 * h, rad, nrad, ref ? ref + st : nullptr, map + st);
+                        sht_smem, sht_smem + h, sht_smem + 2 * h + 1, sht_smem + 3 * h + 1, rad, nrad, ref ? ref + st : nullptr,
+                        map + st);
 }
 
 // coef[base(m) + l] = (c1, c2) of sht_coef, l = m..lmax

@@ -77,7 +77,7 @@ int sht_plan(int dev, int nside, int lmax, cudaStream_t st, ShtPlan** out)
     psb::sht_cmin_kernel<<<(lmax + 128) / 128, 128, 0, st>>>(D, R, P.cmin);
     CUDA_TRY(cudaGetLastError());
     const int hmax = 2 * nside;
-    const int smem = 3 * hmax * (int)sizeof(double2);
+    const int smem = (3 * hmax + 1 + 512) * (int)sizeof(double2);
     if (smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(psb::sht_ring_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_TRY(cudaFuncSetAttribute(psb::sht_ring_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -97,7 +97,7 @@ template <class F> int sht_ring_launches(const ShtPlan& P, F launch)
         if (hi <= lo) continue;
         const int hmax = 2 * std::min(hi, N);
         const int threads = hmax >= 2048 ? 512 : hmax >= 512 ? 256 : 64;
-        if (int rc = launch(lo, hi - lo, threads, (size_t)3 * hmax * sizeof(double2))) return rc;
+        if (int rc = launch(lo, hi - lo, threads, (size_t)(3 * hmax + 1 + threads) * sizeof(double2))) return rc;
     }
     return OK;
 }

@@ -60,7 +60,7 @@ void ring_stage_synthesis(const Dims& D, const std::vector<double2>& Phi, const 
     for (int p = 0; p < D.nrp; ++p) {
         const psb::ShtRing g = psb::sht_ring(D.nside, p);
         const int h = g.n / 2;
-        std::vector<double2> A(h), B(h), T(h);
+        std::vector<double2> A(h), B(h + 1), T(h);
         int rad[16];
         const int nrad = psb::sht_factor(h, rad);
         for (int hemi = 0; hemi < 2; ++hemi) {
@@ -68,7 +68,7 @@ void ring_stage_synthesis(const Dims& D, const std::vector<double2>& Phi, const 
             HostCtx cx;
             const long long st = hemi ? g.startS : g.startN;
             psb::sht_ring_synthesise(cx, Phi.data() + ((size_t)p * 2 + hemi), (long long)D.nrp * 2, g.n, g.shifted, D.lmax,
-                                     A.data(), B.data(), T.data(), rad, nrad, ref ? ref + st : nullptr, map + st);
+                                     A.data(), B.data(), T.data(), T.data(), rad, nrad, ref ? ref + st : nullptr, map + st);
         }
     }
 }
@@ -210,11 +210,12 @@ extern "C" int sht_host_ring_analyse(const double* f, int n, int shifted, double
 extern "C" int sht_host_ring_synthesise(const double* in, int n, int shifted, int mmax, double* f)
 {
     const int h = n / 2;
-    std::vector<double2> A(h), B(h), T(h);
+    std::vector<double2> A(h), B(h + 1), T(h);
     int rad[16];
     const int nrad = psb::sht_factor(h, rad);
     HostCtx cx;
-    psb::sht_ring_synthesise(cx, (const double2*)in, 1, n, shifted, mmax, A.data(), B.data(), T.data(), rad, nrad, nullptr, f);
+    psb::sht_ring_synthesise(cx, (const double2*)in, 1, n, shifted, mmax, A.data(), B.data(), T.data(), T.data(), rad, nrad,
+                             nullptr, f);
     return nrad;
 }
 
