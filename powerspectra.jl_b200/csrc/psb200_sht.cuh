@@ -642,18 +642,31 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
     }
 }
 
-// cl[l] = (Re(a_l0 conj b_l0) + 2 sum_{m=1..l} Re(a_lm conj b_lm))/(2l+1), m ascending (fixed order)
-__global__ void sht_alm2cl_kernel(int lmax, const double2* __restrict__ a, const double2* __restrict__ b, double* __restrict__ cl)
+// cl[l] = (Re(a_l0 conj b_l0) + 2 sum_{m=1..l} Re(a_lm conj b_lm))/(2l+1).  Two stages so that the m sum is not one
+// serial chain per l: blockIdx.y = segment of SHT_CL_SEG consecutive m, partial[seg][l]; then the segments in order.
+constexpr int SHT_CL_SEG = 64;
+__global__ void sht_alm2cl_partial_kernel(int lmax, const double2* __restrict__ a, const double2* __restrict__ b,
+                                          double* __restrict__ partial)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l > lmax) return;
+    const int m0 = blockIdx.y * SHT_CL_SEG;
     double s = 0.0;
-    for (int m = 0; m <= l; ++m) {
+    for (int m = m0; m < m0 + SHT_CL_SEG && m <= l; ++m) {
         const long long i = sht_alm_base(lmax, m) + l;
         const double2 x = a[i], y = b[i];
         const double t = x.x * y.x + x.y * y.y;
         s += m ? 2.0 * t : t;
     }
+    partial[(long long)blockIdx.y * (lmax + 1) + l] = s;
+}
+
+__global__ void sht_alm2cl_finish_kernel(int lmax, int nseg, const double* __restrict__ partial, double* __restrict__ cl)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > lmax) return;
+    double s = 0.0;
+    for (int g = 0; g < nseg && g * SHT_CL_SEG <= l; ++g) s += partial[(long long)g * (lmax + 1) + l];
     cl[l] = s / (2.0 * (double)l + 1.0);
 }
 

@@ -158,6 +158,32 @@ int sht_map2alm(ShtPlan& P, cudaStream_t st, const double* dmap, double* dalm, i
     return OK;
 }
 
+struct ClScratch { double* p = nullptr; size_t cap = 0; };
+ClScratch g_cl[16];                   // per-device partial sums of psb200_alm2cl_dev (its own buffer: the call is asynchronous)
+
+int cl_scratch(int dev, size_t n, double** out)
+{
+    ClScratch& c = g_cl[dev];
+    if (c.cap < n) {
+        if (c.p) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(c.p); c.p = nullptr; c.cap = 0; }
+        CUDA_TRY(cudaMalloc(&c.p, n * sizeof(double)));
+        c.cap = n;
+    }
+    *out = c.p;
+    return OK;
+}
+
+// alm2cl on device buffers; scratch: ceil((lmax+1)/SHT_CL_SEG) x (lmax+1) doubles
+int sht_alm2cl(int lmax, const double2* a, const double2* b, double* scratch, double* cl, cudaStream_t st)
+{
+    const int nseg = (lmax + psb::SHT_CL_SEG) / psb::SHT_CL_SEG;
+    psb::sht_alm2cl_partial_kernel<<<dim3((unsigned)((lmax + 128) / 128), (unsigned)nseg), 128, 0, st>>>(lmax, a, b, scratch);
+    CUDA_TRY(cudaGetLastError());
+    psb::sht_alm2cl_finish_kernel<<<(lmax + 128) / 128, 128, 0, st>>>(lmax, nseg, scratch, cl);
+    CUDA_TRY(cudaGetLastError());
+    return OK;
+}
+
 int sht_enter(int nside, int lmax, int* dev)
 {
     if (int rc = sht_check(nside, lmax)) return rc;

@@ -25,12 +25,16 @@ int psb200_alm2map_dev(int nside, int lmax, const void* dalm, void* dmap, void* 
 
 int psb200_alm2cl_dev(int lmax, const void* dalm1, const void* dalm2, void* dcl, void* stream)
 {
-    if (lmax < 0 || !dalm1 || !dalm2 || !dcl) return fail(ERR_ARG, "alm2cl: bad arguments");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (lmax < 0 || lmax > 8191 || !dalm1 || !dalm2 || !dcl) return fail(ERR_ARG, "alm2cl: bad arguments");
     if (device_count() <= 0) return fail(ERR_NODEVICE, "no CUDA device visible: libpsb200 has no CPU fallback");
-    psb::sht_alm2cl_kernel<<<(lmax + 128) / 128, 128, 0, (cudaStream_t)stream>>>(lmax, (const double2*)dalm1, (const double2*)dalm2,
-                                                                              (double*)dcl);
-    CUDA_TRY(cudaGetLastError());
-    return OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
+    const size_t nseg = (size_t)(lmax + psb::SHT_CL_SEG) / psb::SHT_CL_SEG;
+    double* part = nullptr;
+    if (int rc = cl_scratch(dev, nseg * ((size_t)lmax + 1), &part)) return rc;       // calls on one device must be stream-ordered by the caller
+    return sht_alm2cl(lmax, (const double2*)dalm1, (const double2*)dalm2, part, (double*)dcl, (cudaStream_t)stream);
 }
 
 int psb200_map2alm(int nside, int lmax, int niter, int nfactors, const double* const* factors, double scale, double* alm)
@@ -88,13 +92,13 @@ int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 16) return fail(ERR_ARG, "device index %d above the supported 15", dev);
     const size_t na = (size_t)(lmax + 1) * (lmax + 2);           // doubles per alm
-    if (int rc = scratch_reserve(dev, 0, 2 * na + (size_t)lmax + 1)) return rc;
+    const size_t nseg = (size_t)(lmax + psb::SHT_CL_SEG) / psb::SHT_CL_SEG;
+    if (int rc = scratch_reserve(dev, 0, 2 * na + (nseg + 1) * ((size_t)lmax + 1))) return rc;
     DeviceScratch& s = g_scratch[dev];
-    double *a = s.X[0], *b = a + na, *c = b + na;
+    double *a = s.X[0], *b = a + na, *c = b + na, *part = c + lmax + 1;
     CUDA_TRY(cudaMemcpyAsync(a, alm1, na * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     if (alm2 != alm1) CUDA_TRY(cudaMemcpyAsync(b, alm2, na * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    psb::sht_alm2cl_kernel<<<(lmax + 128) / 128, 128, 0, s.stream>>>(lmax, (const double2*)a, (const double2*)(alm2 != alm1 ? b : a), c);
-    CUDA_TRY(cudaGetLastError());
+    if (int rc = sht_alm2cl(lmax, (const double2*)a, (const double2*)(alm2 != alm1 ? b : a), part, c, s.stream)) return rc;
     CUDA_TRY(cudaMemcpyAsync(cl, c, ((size_t)lmax + 1) * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     return OK;
