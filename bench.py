@@ -832,10 +832,27 @@ def extras(args, ps, dev, L, world, torch, cpu):
         "fp64_frac_map2alm": 7 * 5.0 * st["exec_steps"] / (t_m2a * 1e-3) / peak,
         "what": "psb200_map2alm_dev / psb200_alm2map_dev / psb200_alm2cl_dev device-resident on one GPU; e2e = psb200_map2alm "
                 "with three pageable host maps (mask_i, mask_j, sigma^2) in and the alm out; fractions = executed "
-                "(l, m, ring pair) steps x 5 FP64 instructions / time of the whole pass (ring FFT stage included) / DFMA peak. "
-                "No CPU arm: the reference's transform is libsharp behind Healpix.jl, neither is in this image, and the "
-                "oracle is a direct O(npix lmax^2) sum"}
+                "(l, m, ring pair) steps x 5 FP64 instructions / time of the whole pass (ring FFT stage included) / DFMA peak"}
     del dalm, dmap, dback
+    if cpu:
+        # CPU arm in the reference's shape (oracle/shtcpu.c: per-ring FFTs + scaled lambda_lm recurrences, plain C + OpenMP,
+        # -O3 -march=native; NOT libsharp, which Healpix.jl calls and which is not in this image), at nside 512 where it
+        # takes seconds; the GPU is timed at the same size beside it
+        from oracle import shtoracle as so
+        ns_c, lm_c = 512, 1535
+        fc = np.random.default_rng(22).normal(size=12 * ns_c * ns_c)
+        so.fast_lib(native=True).shtcpu_threads(cores)
+        t0 = time.perf_counter()
+        a_cpu = so.fast_map2alm(fc, ns_c, lm_c, 3, native=True)
+        dt = time.perf_counter() - t0
+        dfc = torch.tensor(fc, device="cuda")
+        dac = torch.empty(dev.alm_size(lm_c), dtype=torch.complex128, device="cuda")
+        t_g = dtime(lambda: dev.map2alm_dev(ns_c, lm_c, dfc, dac, 3), reps=3)
+        out["w_production"]["cpu_baseline"] = {
+            "value": 1.0 / dt, "unit": "map2alm(niter=3)/s at nside 512, lmax 1535", "cores": cores, "kind": "port",
+            "sample": f"one whole transform at nside {ns_c} ({dt:.2f} s); ring-based C/OpenMP restatement, not libsharp"}
+        out["w_production"]["gpu_same_size"] = {"ms": t_g, "value": 1e3 / t_g, "speedup_vs_cpu": dt * 1e3 / t_g,
+                                                "max_rel_diff_vs_cpu": float(np.max(np.abs(dac.cpu().numpy() - a_cpu)) / np.max(np.abs(a_cpu)))}
     return out
 
 

@@ -192,3 +192,51 @@ def effective_weight_alm(nside, lmax, mask_i, mask_j, sigma2=None, niter: int = 
         f = f * (4 * LD(np.pi) / npix(nside))          # parent(map_buffer) .*= parent(weight) .* Omega_p  (:161-162)
         f = f * np.asarray(sigma2, dtype=LD)
     return map2alm(f, nside, lmax, niter)
+
+
+# ---- ring-based CPU restatement (oracle/shtcpu.c: C + OpenMP, the shape of the reference's libsharp path) ---------
+_fast = None
+_fast_native = False
+
+
+def fast_lib(native: bool = False):
+    """libshtcpu.so (portable build, tests) or, with native=True, the -O3 -march=native build made on this machine
+    (bench.py's timed CPU arm)."""
+    global _fast, _fast_native
+    import ctypes as C
+    import os
+    import subprocess
+    if _fast is None or native != _fast_native:
+        here = os.path.dirname(os.path.abspath(__file__))
+        subprocess.run(["make", "-C", here] + (["native"] if native else []), check=True, capture_output=True)
+        L = C.CDLL(os.path.join(here, "_build", "libshtcpu_native.so" if native else "libshtcpu.so"))
+        dp = C.POINTER(C.c_double)
+        L.shtcpu_map2alm.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp]
+        L.shtcpu_alm2map.argtypes = [C.c_int, C.c_int, dp, dp]
+        L.shtcpu_threads.argtypes = [C.c_int]
+        _fast, _fast_native = L, native
+    return _fast
+
+
+def fast_map2alm(f, nside: int, lmax: int, niter: int = 3, native: bool = False, threads: int = 0):
+    import ctypes as C
+    L = fast_lib(native)
+    if threads:
+        L.shtcpu_threads(threads)
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    alm = np.zeros(alm_size(lmax), dtype=np.complex128)
+    dp = C.POINTER(C.c_double)
+    if L.shtcpu_map2alm(nside, lmax, niter, f.ctypes.data_as(dp), alm.ctypes.data_as(dp)):
+        raise MemoryError("shtcpu_map2alm")
+    return alm
+
+
+def fast_alm2map(alm, nside: int, lmax: int, native: bool = False):
+    import ctypes as C
+    L = fast_lib(native)
+    alm = np.ascontiguousarray(alm, dtype=np.complex128)
+    f = np.zeros(npix(nside))
+    dp = C.POINTER(C.c_double)
+    if L.shtcpu_alm2map(nside, lmax, alm.ctypes.data_as(dp), f.ctypes.data_as(dp)):
+        raise MemoryError("shtcpu_alm2map")
+    return f
