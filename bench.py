@@ -827,12 +827,12 @@ def extras(args, ps, dev, L, world, torch, cpu):
         "map2alm_e2e_ms": t_e, "e2e_h2d_bytes": 3 * npix * 8, "e2e_d2h_bytes": int(halm.nbytes),
         "roundtrip_rel_err_niter3": err3,
         "legendre_steps_per_pass": st["exec_steps"], "live_over_executed": st["live_steps"] / st["exec_steps"],
-        "fp64_frac_analysis": 5.0 * st["exec_steps"] / (t_ana * 1e-3) / peak,
-        "fp64_frac_synthesis": 5.0 * st["exec_steps"] / (t_syn * 1e-3) / peak,
-        "fp64_frac_map2alm": 7 * 5.0 * st["exec_steps"] / (t_m2a * 1e-3) / peak,
+        "fp64_frac_analysis": 4.0 * st["exec_steps"] / (t_ana * 1e-3) / peak,
+        "fp64_frac_synthesis": 4.0 * st["exec_steps"] / (t_syn * 1e-3) / peak,
+        "fp64_frac_map2alm": 7 * 4.0 * st["exec_steps"] / (t_m2a * 1e-3) / peak,
         "what": "psb200_map2alm_dev / psb200_alm2map_dev / psb200_alm2cl_dev device-resident on one GPU; e2e = psb200_map2alm "
                 "with three pageable host maps (mask_i, mask_j, sigma^2) in and the alm out; fractions = executed "
-                "(l, m, ring pair) steps x 5 FP64 instructions / time of the whole pass (ring FFT stage included) / DFMA peak"}
+                "(l, m, ring pair) steps x 4 FP64 instructions / time of the whole pass (ring FFT stage included) / DFMA peak"}
     del dalm, dmap, dback
     if cpu:
         # CPU arm in the reference's shape (oracle/shtcpu.c: per-ring FFTs + scaled lambda_lm recurrences, plain C + OpenMP,

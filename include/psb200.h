@@ -245,7 +245,7 @@ int psb200_alm2cl_dev(int lmax, const void* dalm1, const void* dalm2, void* dcl,
 /* Work accounting of ONE Legendre pass (analysis or synthesis; map2alm with niter iterations runs 2 niter + 1) as the
  * kernel tiles it (host arithmetic): out[0] executed (l, m, ring pair) steps, out[1] steps of the rings the transform
  * starts, out[2] warps, out[3] ring pairs per lane, out[4] ring-pair chunks, out[5] l steps per pass (out: 6 entries).
- * 5 FP64 instructions per step. */
+ * 4 FP64 instructions per step (2 of the un-normalised recurrence + 2 accumulate). */
 int psb200_sht_stats(int nside, int lmax, long long* out);
 
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */

@@ -14,7 +14,8 @@
 //          31-shuffle butterfly and written once)--> per-chunk partial alm --(finish: fixed-order sum over chunks)--> alm
 // and the mirror image for synthesis (lanes accumulate F_m(ring) in registers; no reduction at all).  Nothing is
 // atomically accumulated, so results do not depend on scheduling.  The Legendre stage is FP64-pipe bound
-// (5 FP64 instructions per (l, m, ring pair): 3 recurrence + 2 accumulate), the ring stage is shared-memory bound and small.
+// (4 FP64 instructions per (l, m, ring pair): 2 of the un-normalised recurrence + 2 accumulate), the ring stage is
+// shared-memory bound and small.
 //
 // Dynamic range.  lambda_mm ~ sin^m(theta) underflows Float64 long before l reaches the classical region
 // (theta = 1e-3, m = 3000: 1e-9000).  Every ring carries an integer e with lambda = lt * 2^(-800 e), |lt| kept inside
@@ -85,15 +86,27 @@ PSB_HD double sht_mlim(int lmax, double sth)
     return lmax * sth + (w < 50.0 ? 50.0 : w);
 }
 
-// recurrence coefficients to advance FROM l:  lambda_{l+1} = c1 (x lambda_l) - c2 lambda_{l-1},
-// c1 = 1/A_{l+1}, c2 = A_l/A_{l+1}, A_l = sqrt((l^2 - m^2)/(4 l^2 - 1))
-PSB_HD void sht_coef(int l, int m, double* c1, double* c2)
+// Recurrence inside a pass of SHT_C steps starting at l0 (l0 - m a multiple of SHT_C).  With A_l^2 = (l^2 - m^2)/(4 l^2 - 1)
+// the normalised functions obey lambda_{l+1} = (x lambda_l - A_l lambda_{l-1})/A_{l+1}; the kernels step the UN-normalised
+// mu_j = lambda_{l0+j}/Q_j, Q_0 = 1, Q_{j+1} = Q_j/A_{l0+j+1}, which obeys
+//     mu_{j+1} = x mu_j - d_j mu_{j-1},   d_0 = A_{l0} (mu_{-1} = lambda_{l0-1}),  d_j = A_{l0+j}^2 (j >= 1)
+// -- one multiply and one FMA per step instead of two multiplies and one FMA, no square root in d_j.  Q_j only depends on
+// (l, m): the analysis multiplies the REDUCED sum of step j by it, the synthesis folds it into a_lm when it stages them,
+// and the pass ends with lambda_{l0+16} = Q_16 mu_16, lambda_{l0+15} = Q_15 mu_15.  Q_16 < 2^90 (first pass, m ~ lmax).
+// Table entry of step j: (d_j, Q_{j+1}); column m holds the entries of l = m .. lmax + SHT_C - 1 (whole passes).
+PSB_HD long long sht_coef_base(int lmax, int m) { return sht_alm_base(lmax, m) + (long long)(SHT_C - 1) * m; }   // index = base + l
+PSB_HD long long sht_coef_size(int lmax) { return sht_alm_base(lmax, lmax) + lmax + (long long)(SHT_C - 1) * lmax + SHT_C; }
+
+PSB_HD void sht_coef_pass(int l0, int m, double2* out)      // out[0..SHT_C-1]
 {
-    const double l1 = (double)(l + 1), ld = (double)l, md = (double)m;
-    const double ia2 = (4.0 * l1 * l1 - 1.0) / ((l1 - md) * (l1 + md));
-    const double a2 = ((ld - md) * (ld + md)) / (4.0 * ld * ld - 1.0);
-    *c1 = sqrt(ia2);
-    *c2 = sqrt(a2 * ia2);
+    double Q = 1.0;
+    for (int j = 0; j < SHT_C; ++j) {
+        const double l = (double)(l0 + j), l1 = l + 1.0, md = (double)m;
+        const double a2 = ((l - md) * (l + md)) / (4.0 * l * l - 1.0);                 // A_l^2 (0 at l = m; l = m = 0: -0/-1)
+        const double ia2 = (4.0 * l1 * l1 - 1.0) / ((l1 - md) * (l1 + md));            // 1/A_{l+1}^2
+        Q *= sqrt(ia2);
+        out[j] = make_double2(j ? a2 : sqrt(fabs(a2)), Q);
+    }
 }
 
 // state of one ring's recurrence: lambda_l = lc 2^(-800 e), lambda_{l-1} = lp 2^(-800 e)
@@ -113,13 +126,20 @@ PSB_HD ShtLam sht_lam_start(int lmax, int m, double cm_m, double z, double sth, 
     return q;
 }
 
-PSB_HD void sht_lam_advance(ShtLam& q, double c1, double c2)
+// one step of the un-normalised recurrence on (lp, lc) = (mu_{j-1}, mu_j)
+PSB_HD void sht_mu_advance(ShtLam& q, double d)
 {
-    const double t = q.x * q.lc;
-    const double u = c2 * q.lp;
-    const double ln = fma(c1, t, -u);
+    const double t = d * q.lp;
+    const double n = fma(q.x, q.lc, -t);
     q.lp = q.lc;
-    q.lc = ln;
+    q.lc = n;
+}
+
+// end of a pass: back to lambda.  q15 = Q_15 (1 when SHT_C == 1), q16 = Q_16
+PSB_HD void sht_mu_close(ShtLam& q, double q15, double q16)
+{
+    q.lp *= q15;
+    q.lc *= q16;
 }
 
 // true when the ring has just become representable (e reached 0)
@@ -412,15 +432,17 @@ __global__ void __launch_bounds__(512) sht_ring_synthesis_kernel(ShtDims D, int 
                         map + st);
 }
 
-// coef[base(m) + l] = (c1, c2) of sht_coef, l = m..lmax
+// coef[sht_coef_base(m) + l] = (d_j, Q_{j+1}) of sht_coef_pass: one thread per (m, pass)
 __global__ void sht_coef_kernel(int lmax, double2* __restrict__ coef)
 {
     const int m = blockIdx.y;
-    const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
-    if (l > lmax) return;
-    double c1, c2;
-    sht_coef(l, m, &c1, &c2);
-    coef[sht_alm_base(lmax, m) + l] = make_double2(c1, c2);
+    const int l0 = m + (blockIdx.x * blockDim.x + threadIdx.x) * SHT_C;
+    if (l0 > lmax) return;
+    double2 e[SHT_C];
+    sht_coef_pass(l0, m, e);
+    double2* out = coef + sht_coef_base(lmax, m) + l0;
+#pragma unroll
+    for (int j = 0; j < SHT_C; ++j) out[j] = e[j];
 }
 
 // cmin[m] = first chunk of ring pairs that holds a ring the transform starts for this m (rings are skipped from the
@@ -479,6 +501,7 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
     const int chunk = (blockIdx.x % bpm) * SHT_WARPS + wid;
     if (chunk >= D.nchunks || chunk < cmin[m]) return;
     const long long base = sht_alm_base(D.lmax, m);
+    const double2* cf = coef + sht_coef_base(D.lmax, m);
     const double cm_m = cm[m];
     ShtLam q[R];
     double ger[R], gei[R], gor[R], goi[R];
@@ -500,11 +523,11 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
     }
     double* out = partial + (long long)chunk * 2 * D.nalm + 2 * base;
     double2 cnext = make_double2(0.0, 0.0);
-    if (lane < C) cnext = coef[base + (m + lane <= D.lmax ? m + lane : D.lmax)];
+    if (lane < C) cnext = cf[m + lane];
     for (int l0 = m; l0 <= D.lmax; l0 += C) {
         if (lane < C) sco[wid][lane] = cnext;
         __syncwarp();
-        if (lane < C && l0 + C <= D.lmax) cnext = coef[base + (l0 + C + lane <= D.lmax ? l0 + C + lane : D.lmax)];
+        if (lane < C && l0 + C <= D.lmax) cnext = cf[l0 + C + lane];
         if (__any_sync(0xffffffffu, alive)) {
             double v[2 * C];
 #pragma unroll
@@ -516,20 +539,26 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
                 for (int s = 0; s < R; ++s) {
                     if ((j & 1) == 0) { v[2 * j] = fma(q[s].lc, ger[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, gei[s], v[2 * j + 1]); }
                     else              { v[2 * j] = fma(q[s].lc, gor[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, goi[s], v[2 * j + 1]); }
-                    sht_lam_advance(q[s], c.x, c.y);
+                    sht_mu_advance(q[s], c.x);
                 }
             }
             sht_butterfly(v, lane);
-            const int l = l0 + (lane >> 1);
-            if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0];
+            const int jl = lane >> 1, l = l0 + jl;                  // the sums were of mu_j: times Q_j
+            const double Qj = jl ? sco[wid][jl - 1].y : 1.0;
+            if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0] * Qj;
         } else {
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                const double2 c = sco[wid][j];
+                const double d = sco[wid][j].x;
 #pragma unroll
-                for (int s = 0; s < R; ++s) sht_lam_advance(q[s], c.x, c.y);
+                for (int s = 0; s < R; ++s) sht_mu_advance(q[s], d);
             }
             if (lane < 2 * C && l0 + (lane >> 1) <= D.lmax) out[2 * (long long)l0 + lane] = 0.0;
+        }
+        {
+            const double q15 = sco[wid][C - 2].y, q16 = sco[wid][C - 1].y;
+#pragma unroll
+            for (int s = 0; s < R; ++s) sht_mu_close(q[s], q15, q16);
         }
         __syncwarp();
 #pragma unroll
@@ -566,7 +595,7 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
                                                                           double4* __restrict__ Phi)
 {
     constexpr int C = SHT_C;
-    __shared__ double4 sca[SHT_WARPS][C];          // (c1, c2, a re, a im) of one l
+    __shared__ double4 sca[SHT_WARPS][C];          // (d_j, Q_{j+1}, Q_j a re, Q_j a im) of one l
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bpm = (D.nchunks + SHT_WARPS - 1) / SHT_WARPS;
     const int m = blockIdx.x / bpm;
@@ -580,6 +609,7 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
         return;
     }
     const long long base = sht_alm_base(D.lmax, m);
+    const double2* cf = coef + sht_coef_base(D.lmax, m);
     const double cm_m = cm[m];
     ShtLam q[R];
     double fer[R], fei[R], forr[R], foi[R];
@@ -596,18 +626,20 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
     double4 nxt = make_double4(0.0, 0.0, 0.0, 0.0);
     if (lane < C) {
         const int l = m + lane;
-        const double2 c = coef[base + (l <= D.lmax ? l : D.lmax)];
+        const double2 c = cf[l];
+        const double Qj = lane ? cf[l - 1].y : 1.0;
         const double2 a = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
-        nxt = make_double4(c.x, c.y, a.x, a.y);
+        nxt = make_double4(c.x, c.y, Qj * a.x, Qj * a.y);
     }
     for (int l0 = m; l0 <= D.lmax; l0 += C) {
         if (lane < C) sca[wid][lane] = nxt;
         __syncwarp();
         if (lane < C && l0 + C <= D.lmax) {
             const int l = l0 + C + lane;
-            const double2 c = coef[base + (l <= D.lmax ? l : D.lmax)];
+            const double2 c = cf[l];
+            const double Qj = lane ? cf[l - 1].y : 1.0;
             const double2 a = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
-            nxt = make_double4(c.x, c.y, a.x, a.y);
+            nxt = make_double4(c.x, c.y, Qj * a.x, Qj * a.y);
         }
         if (__any_sync(0xffffffffu, alive)) {
 #pragma unroll
@@ -617,16 +649,21 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
                 for (int s = 0; s < R; ++s) {
                     if ((j & 1) == 0) { fer[s] = fma(q[s].lc, c.z, fer[s]); fei[s] = fma(q[s].lc, c.w, fei[s]); }
                     else              { forr[s] = fma(q[s].lc, c.z, forr[s]); foi[s] = fma(q[s].lc, c.w, foi[s]); }
-                    sht_lam_advance(q[s], c.x, c.y);
+                    sht_mu_advance(q[s], c.x);
                 }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                const double4 c = sca[wid][j];
+                const double d = sca[wid][j].x;
 #pragma unroll
-                for (int s = 0; s < R; ++s) sht_lam_advance(q[s], c.x, c.y);
+                for (int s = 0; s < R; ++s) sht_mu_advance(q[s], d);
             }
+        }
+        {
+            const double q15 = sca[wid][C - 2].y, q16 = sca[wid][C - 1].y;
+#pragma unroll
+            for (int s = 0; s < R; ++s) sht_mu_close(q[s], q15, q16);
         }
         __syncwarp();
 #pragma unroll

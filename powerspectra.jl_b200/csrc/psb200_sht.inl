@@ -4,7 +4,7 @@
 struct ShtPlan {                      // per device and (nside, lmax): tables + work buffers, kept between calls
     int nside = 0, lmax = 0, R = 0, C = 0;
     psb::ShtDims D{};
-    double2* coef = nullptr;          // recurrence coefficients, alm layout
+    double2* coef = nullptr;          // recurrence coefficients (d_j, Q_{j+1}), sht_coef_base layout
     double* cm = nullptr;             // log2 |lambda_mm| prefactors
     int* cmin = nullptr;              // first active chunk per m
     double4* Phi = nullptr;           // ring-pair phases, (lmax+1) x nrp x 32 B
@@ -54,7 +54,7 @@ int sht_plan(int dev, int nside, int lmax, cudaStream_t st, ShtPlan** out)
     D.nchunks = (D.nrp + 32 * R - 1) / (32 * R);
     D.npix = 12LL * nside * nside;
     D.nalm = (long long)(lmax + 1) * (lmax + 2) / 2;
-    CUDA_TRY(cudaMalloc(&P.coef, D.nalm * sizeof(double2)));
+    CUDA_TRY(cudaMalloc(&P.coef, (size_t)psb::sht_coef_size(lmax) * sizeof(double2)));
     CUDA_TRY(cudaMalloc(&P.cm, (size_t)(lmax + 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc(&P.cmin, (size_t)(lmax + 1) * sizeof(int)));
     CUDA_TRY(cudaMalloc(&P.Phi, (size_t)(lmax + 1) * D.nrp * sizeof(double4)));
@@ -72,7 +72,7 @@ int sht_plan(int dev, int nside, int lmax, cudaStream_t st, ShtPlan** out)
     }
     CUDA_TRY(cudaMemcpyAsync(P.cm, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));           // cm is a local
-    psb::sht_coef_kernel<<<dim3((unsigned)((lmax + 128) / 128), (unsigned)(lmax + 1)), 128, 0, st>>>(lmax, P.coef);
+    psb::sht_coef_kernel<<<dim3((unsigned)((lmax / psb::SHT_C + 64) / 64), (unsigned)(lmax + 1)), 64, 0, st>>>(lmax, P.coef);
     CUDA_TRY(cudaGetLastError());
     psb::sht_cmin_kernel<<<(lmax + 128) / 128, 128, 0, st>>>(D, R, P.cmin);
     CUDA_TRY(cudaGetLastError());

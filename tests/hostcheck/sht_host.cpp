@@ -91,16 +91,18 @@ void leg_analysis(const Dims& D, const std::vector<double2>& Phi, const std::vec
             };
             if (q.e == 0) load();
             for (int l0 = m; l0 <= D.lmax; l0 += psb::SHT_C) {
+                double2 cf[psb::SHT_C];
+                psb::sht_coef_pass(l0, m, cf);
                 for (int j = 0; j < psb::SHT_C; ++j) {
                     const int l = l0 + j;
+                    const double Qj = j ? cf[j - 1].y : 1.0;
                     if (l <= D.lmax) {
-                        sre[l] += q.lc * ((j & 1) ? gor : ger);
-                        sim[l] += q.lc * ((j & 1) ? goi : gei);
+                        sre[l] += Qj * (q.lc * ((j & 1) ? gor : ger));
+                        sim[l] += Qj * (q.lc * ((j & 1) ? goi : gei));
                     }
-                    double c1, c2;
-                    psb::sht_coef(l <= D.lmax ? l : D.lmax, m, &c1, &c2);
-                    psb::sht_lam_advance(q, c1, c2);
+                    psb::sht_mu_advance(q, cf[j].x);
                 }
+                psb::sht_mu_close(q, cf[psb::SHT_C - 2].y, cf[psb::SHT_C - 1].y);
                 if (psb::sht_lam_rescale(q)) load();
             }
         }
@@ -124,15 +126,17 @@ void leg_synthesis(const Dims& D, const double* alm, const std::vector<double>& 
             if (q.e == psb::SHT_NEVER) continue;
             double fer = 0, fei = 0, forr = 0, foi = 0;
             for (int l0 = m; l0 <= D.lmax; l0 += psb::SHT_C) {
+                double2 cf[psb::SHT_C];
+                psb::sht_coef_pass(l0, m, cf);
                 for (int j = 0; j < psb::SHT_C; ++j) {
                     const int l = l0 + j;
-                    const double ar = l <= D.lmax ? alm[2 * (base + l)] : 0.0, ai = l <= D.lmax ? alm[2 * (base + l) + 1] : 0.0;
+                    const double Qj = j ? cf[j - 1].y : 1.0;
+                    const double ar = l <= D.lmax ? Qj * alm[2 * (base + l)] : 0.0, ai = l <= D.lmax ? Qj * alm[2 * (base + l) + 1] : 0.0;
                     if (j & 1) { forr = fma(q.lc, ar, forr); foi = fma(q.lc, ai, foi); }
                     else { fer = fma(q.lc, ar, fer); fei = fma(q.lc, ai, fei); }
-                    double c1, c2;
-                    psb::sht_coef(l <= D.lmax ? l : D.lmax, m, &c1, &c2);
-                    psb::sht_lam_advance(q, c1, c2);
+                    psb::sht_mu_advance(q, cf[j].x);
                 }
+                psb::sht_mu_close(q, cf[psb::SHT_C - 2].y, cf[psb::SHT_C - 1].y);
                 if (psb::sht_lam_rescale(q)) fer = fei = forr = foi = 0.0;
             }
             if (q.e == 0) {
@@ -183,13 +187,14 @@ extern "C" int sht_host_lambda(int nside, int lmax, int m, int p, double* lam)
     if (q.e == psb::SHT_NEVER) return -1;
     int alive = q.e == 0 ? m : lmax + 1;
     for (int l0 = m; l0 <= lmax; l0 += psb::SHT_C) {
+        double2 cf[psb::SHT_C];
+        psb::sht_coef_pass(l0, m, cf);
         for (int j = 0; j < psb::SHT_C; ++j) {
             const int l = l0 + j;
-            if (l <= lmax && q.e == 0) lam[l - m] = q.lc;
-            double c1, c2;
-            psb::sht_coef(l <= lmax ? l : lmax, m, &c1, &c2);
-            psb::sht_lam_advance(q, c1, c2);
+            if (l <= lmax && q.e == 0) lam[l - m] = q.lc * (j ? cf[j - 1].y : 1.0);
+            psb::sht_mu_advance(q, cf[j].x);
         }
+        psb::sht_mu_close(q, cf[psb::SHT_C - 2].y, cf[psb::SHT_C - 1].y);
         if (psb::sht_lam_rescale(q)) alive = l0 + psb::SHT_C;
     }
     return alive;

@@ -55,8 +55,8 @@ rec = {"nside": nside, "lmax": lmax, "R": st["R"], "ms_alm2map": t_syn, "ms_anal
 if not once:
     peak = L.psb200_dfma_peak(20000) / 2.0           # FP64 lane-instructions / s
     rec["dfma_peak_tflops"] = 2 * peak / 1e12
-    rec["frac_synthesis_pass"] = 5.0 * st["exec_steps"] / (t_syn * 1e-3) / peak          # includes the ring stage in the time
-    rec["frac_analysis_pass"] = 5.0 * st["exec_steps"] / (t_ana * 1e-3) / peak
-    rec["frac_map2alm"] = 7 * 5.0 * st["exec_steps"] / (t_m2a * 1e-3) / peak
+    rec["frac_synthesis_pass"] = 4.0 * st["exec_steps"] / (t_syn * 1e-3) / peak          # includes the ring stage in the time
+    rec["frac_analysis_pass"] = 4.0 * st["exec_steps"] / (t_ana * 1e-3) / peak
+    rec["frac_map2alm"] = 7 * 4.0 * st["exec_steps"] / (t_m2a * 1e-3) / peak
     rec["useful_over_exec"] = st["live_steps"] / st["exec_steps"]
 print(json.dumps(rec))
