@@ -588,7 +588,7 @@ __global__ void sht_analysis_finish_kernel(ShtDims D, const double* __restrict__
 
 // Legendre stage of the synthesis: one warp per (m, chunk); Phi[m nrp + p] = (F_N re, im, F_S re, im)
 template <int R>
-__global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDims D, const double2* __restrict__ alm,
+__global__ void __launch_bounds__(32 * SHT_WARPS, R <= 4 ? 5 : 1) sht_leg_synthesis_kernel(ShtDims D, const double2* __restrict__ alm,
                                                                           const double2* __restrict__ coef,
                                                                           const double* __restrict__ cm,
                                                                           const int* __restrict__ cmin,
@@ -623,23 +623,24 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_synthesis_kernel(ShtDi
         fer[s] = fei[s] = forr[s] = foi[s] = 0.0;
         alive |= q[s].e == 0;
     }
-    double4 nxt = make_double4(0.0, 0.0, 0.0, 0.0);
+    // raw loads of the next pass are kept in registers and only combined when they are stored to shared memory, one
+    // pass later: nothing depends on them while they are in flight
+    double2 nc = make_double2(0.0, 0.0), na = make_double2(0.0, 0.0);
+    double nq = 1.0;
     if (lane < C) {
         const int l = m + lane;
-        const double2 c = cf[l];
-        const double Qj = lane ? cf[l - 1].y : 1.0;
-        const double2 a = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
-        nxt = make_double4(c.x, c.y, Qj * a.x, Qj * a.y);
+        nc = cf[l];
+        if (lane) nq = cf[l - 1].y;
+        if (l <= D.lmax) na = alm[base + l];
     }
     for (int l0 = m; l0 <= D.lmax; l0 += C) {
-        if (lane < C) sca[wid][lane] = nxt;
+        if (lane < C) sca[wid][lane] = make_double4(nc.x, nc.y, nq * na.x, nq * na.y);
         __syncwarp();
         if (lane < C && l0 + C <= D.lmax) {
             const int l = l0 + C + lane;
-            const double2 c = cf[l];
-            const double Qj = lane ? cf[l - 1].y : 1.0;
-            const double2 a = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
-            nxt = make_double4(c.x, c.y, Qj * a.x, Qj * a.y);
+            nc = cf[l];
+            if (lane) nq = cf[l - 1].y;
+            na = l <= D.lmax ? alm[base + l] : make_double2(0.0, 0.0);
         }
         if (__any_sync(0xffffffffu, alive)) {
 #pragma unroll
