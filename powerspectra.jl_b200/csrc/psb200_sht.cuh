@@ -482,11 +482,32 @@ __device__ __forceinline__ void sht_butterfly(double (&v)[32], int lane)
     }
 }
 
+// the same for 8 l steps (v[0..15]): three select-and-exchange stages (xor 16, 8, 4), then the lanes L and L ^ 2 hold two
+// halves of the same sum: v[0] of lane L is the warp total of step L >> 2, component L & 1 (in both lanes of such a pair)
+__device__ __forceinline__ void sht_butterfly8(double (&v)[16], int lane)
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[2 * j] + __shfl_xor_sync(0xffffffffu, v[2 * j + 1], 1);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int d = 16 >> t, half = 4 >> t;
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+}
+
 // Legendre stage of the analysis: one warp per (m, chunk).  partial[chunk][2 (base(m) + l) + {0 re, 1 im}]
 // R ring pairs per lane, C = 16 l steps between reductions; the coefficients of the next C steps are in flight while the
 // current ones are used; while no ring of the warp is representable yet the warp only advances the recurrences.
-template <int R>
-__global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDims D, const double4* __restrict__ Phi,
+// V = l steps per reduction (16: one butterfly per pass; 8: two, with 32 registers less)
+template <int R, int V>
+__global__ void __launch_bounds__(32 * SHT_WARPS, (R <= 4 && V == 8) ? 5 : 1) sht_leg_analysis_kernel(ShtDims D, const double4* __restrict__ Phi,
                                                                          const double2* __restrict__ coef,
                                                                          const double* __restrict__ cm,
                                                                          const int* __restrict__ cmin,
@@ -529,23 +550,35 @@ __global__ void __launch_bounds__(32 * SHT_WARPS) sht_leg_analysis_kernel(ShtDim
         __syncwarp();
         if (lane < C && l0 + C <= D.lmax) cnext = cf[l0 + C + lane];
         if (__any_sync(0xffffffffu, alive)) {
-            double v[2 * C];
 #pragma unroll
-            for (int i = 0; i < 2 * C; ++i) v[i] = 0.0;
+            for (int hh = 0; hh < C / V; ++hh) {
+                double v[2 * V];
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                const double2 c = sco[wid][j];
+                for (int i = 0; i < 2 * V; ++i) v[i] = 0.0;
 #pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    if ((j & 1) == 0) { v[2 * j] = fma(q[s].lc, ger[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, gei[s], v[2 * j + 1]); }
-                    else              { v[2 * j] = fma(q[s].lc, gor[s], v[2 * j]); v[2 * j + 1] = fma(q[s].lc, goi[s], v[2 * j + 1]); }
-                    sht_mu_advance(q[s], c.x);
+                for (int jj = 0; jj < V; ++jj) {
+                    const int j = hh * V + jj;
+                    const double2 c = sco[wid][j];
+#pragma unroll
+                    for (int s = 0; s < R; ++s) {
+                        if ((j & 1) == 0) { v[2 * jj] = fma(q[s].lc, ger[s], v[2 * jj]); v[2 * jj + 1] = fma(q[s].lc, gei[s], v[2 * jj + 1]); }
+                        else              { v[2 * jj] = fma(q[s].lc, gor[s], v[2 * jj]); v[2 * jj + 1] = fma(q[s].lc, goi[s], v[2 * jj + 1]); }
+                        sht_mu_advance(q[s], c.x);
+                    }
+                }
+                // the sums were of mu_j: times Q_j
+                if constexpr (V == 16) {
+                    sht_butterfly(v, lane);
+                    const int jl = lane >> 1, l = l0 + jl;
+                    const double Qj = jl ? sco[wid][jl - 1].y : 1.0;
+                    if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0] * Qj;
+                } else {
+                    sht_butterfly8(v, lane);
+                    const int jl = hh * V + (lane >> 2), l = l0 + jl;
+                    const double Qj = jl ? sco[wid][jl - 1].y : 1.0;
+                    if (l <= D.lmax && (lane & 2) == 0) out[2 * (long long)l + (lane & 1)] = v[0] * Qj;
                 }
             }
-            sht_butterfly(v, lane);
-            const int jl = lane >> 1, l = l0 + jl;                  // the sums were of mu_j: times Q_j
-            const double Qj = jl ? sco[wid][jl - 1].y : 1.0;
-            if (l <= D.lmax) out[2 * (long long)l + (lane & 1)] = v[0] * Qj;
         } else {
 #pragma unroll
             for (int j = 0; j < C; ++j) {

@@ -33,6 +33,12 @@ int sht_R()
 
 int sht_C() { return psb::SHT_C; }
 
+int sht_V()                           // l steps per reduction of the analysis kernel
+{
+    const char* e = getenv("PSB200_SHT_V");
+    return (e && atoi(e) == 16) ? 16 : 8;
+}
+
 int sht_check(int nside, int lmax)
 {
     if (nside < 1 || nside > 2048 || (nside & (nside - 1)))
@@ -112,11 +118,14 @@ int sht_analysis(ShtPlan& P, cudaStream_t st, const double* dmap, double* dalm, 
         })) return rc;
     const int bpm = (D.nchunks + psb::SHT_WARPS - 1) / psb::SHT_WARPS;
     const unsigned grid = (unsigned)((D.lmax + 1) * bpm);
-#define PSB_SHT_ANA(RR) psb::sht_leg_analysis_kernel<RR><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial)
-    switch (P.R) {
-        case 2: PSB_SHT_ANA(2); break;
-        case 8: PSB_SHT_ANA(8); break;
-        default: PSB_SHT_ANA(4);
+#define PSB_SHT_ANA(RR, VV) psb::sht_leg_analysis_kernel<RR, VV><<<grid, 32 * psb::SHT_WARPS, 0, st>>>(D, P.Phi, P.coef, P.cm, P.cmin, P.partial)
+    switch (P.R * 100 + sht_V()) {
+        case 208: PSB_SHT_ANA(2, 8); break;
+        case 216: PSB_SHT_ANA(2, 16); break;
+        case 416: PSB_SHT_ANA(4, 16); break;
+        case 808: PSB_SHT_ANA(8, 8); break;
+        case 816: PSB_SHT_ANA(8, 16); break;
+        default: PSB_SHT_ANA(4, 8);
     }
 #undef PSB_SHT_ANA
     CUDA_TRY(cudaGetLastError());
