@@ -33,10 +33,12 @@ int sht_R()
 
 int sht_C() { return psb::SHT_C; }
 
-int sht_V()                           // l steps per reduction of the analysis kernel
+// l steps per reduction of the analysis kernel: 16 (default), or 8 = two reductions per pass with 32 registers less and a
+// fifth block per SM -- measured 30.5 vs 29.8 ms per analysis pass at nside 2048: the extra warps buy nothing
+int sht_V()
 {
     const char* e = getenv("PSB200_SHT_V");
-    return (e && atoi(e) == 16) ? 16 : 8;
+    return (e && atoi(e) == 8) ? 8 : 16;
 }
 
 int sht_check(int nside, int lmax)
@@ -122,10 +124,10 @@ int sht_analysis(ShtPlan& P, cudaStream_t st, const double* dmap, double* dalm, 
     switch (P.R * 100 + sht_V()) {
         case 208: PSB_SHT_ANA(2, 8); break;
         case 216: PSB_SHT_ANA(2, 16); break;
-        case 416: PSB_SHT_ANA(4, 16); break;
+        case 408: PSB_SHT_ANA(4, 8); break;
         case 808: PSB_SHT_ANA(8, 8); break;
         case 816: PSB_SHT_ANA(8, 16); break;
-        default: PSB_SHT_ANA(4, 8);
+        default: PSB_SHT_ANA(4, 16);
     }
 #undef PSB_SHT_ANA
     CUDA_TRY(cudaGetLastError());
