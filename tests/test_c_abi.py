@@ -19,6 +19,7 @@ C_SRC = textwrap.dedent(r"""
     typedef long long (*terms_t)(int, int, int, int);
     typedef const char* (*str_t)(void);
     typedef int (*cnt_t)(void);
+    typedef int (*m2a_t)(int, int, int, int, const double* const*, double, double*);
 
     int main(int argc, char** argv)
     {
@@ -30,7 +31,8 @@ C_SRC = textwrap.dedent(r"""
         str_t version = (str_t)dlsym(h, "psb200_version");
         str_t last_error = (str_t)dlsym(h, "psb200_last_error");
         cnt_t ndev = (cnt_t)dlsym(h, "psb200_device_count");
-        if (!mcm || !edges || !terms || !version || !last_error || !ndev) { printf("missing symbol\n"); return 3; }
+        m2a_t map2alm = (m2a_t)dlsym(h, "psb200_map2alm");
+        if (!mcm || !edges || !terms || !version || !last_error || !ndev || !map2alm) { printf("missing symbol\n"); return 3; }
         printf("version=%s devices=%d\n", version(), ndev());
         int e[5];
         if (edges(0, 767, 768, 4, e) != 0 || e[0] != 0 || e[4] != 768) { printf("band_edges wrong\n"); return 4; }
@@ -43,6 +45,17 @@ C_SRC = textwrap.dedent(r"""
         if (ndev() == 0) {
             if (rc != 5 || !strstr(last_error(), "no CPU fallback")) { printf("expected code 5, got %d (%s)\n", rc, last_error()); return 7; }
         } else if (rc != 0) { printf("compute failed: %d %s\n", rc, last_error()); return 8; }
+        /* W-spectrum production: map2alm of 2 x (0.5 everywhere) at nside 2 is sqrt(4 pi) Y_00 */
+        double map[48], alm[2 * 10];
+        for (int i = 0; i < 48; ++i) map[i] = 0.5;
+        const double* maps[1] = {map};
+        int rs = map2alm(2, 3, 3, 1, maps, 2.0, alm);
+        if (ndev() == 0) {
+            if (rs != 5) { printf("map2alm: expected code 5, got %d\n", rs); return 11; }
+        } else if (rs != 0 || !(alm[0] > 3.5449077018110 && alm[0] < 3.5449077018111) || alm[1] != 0.0) {
+            printf("map2alm failed: %d a00 = %.17g (%s)\n", rs, alm[0], last_error()); return 12;
+        }
+        if (map2alm(3, 3, 3, 1, maps, 1.0, alm) != 1) { printf("map2alm: nside 3 must be a bad argument\n"); return 13; }
         if (argc > 2 && !strcmp(argv[2], "--require-gpu")) {
             /* V == 1 and l1 + l2 <= 7 = nV-1: the l3 sum is complete, Xi = 1/4pi, M[l1,l2] = (2 l2+1)/4pi */
             if (rc != 0) { printf("a device is required here (rc=%d)\n", rc); return 9; }
