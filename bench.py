@@ -834,6 +834,7 @@ def extras(args, ps, dev, L, world, torch, cpu):
                 "with three pageable host maps (mask_i, mask_j, sigma^2) in and the alm out; fractions = executed "
                 "(l, m, ring pair) steps x 4 FP64 instructions / time of the whole pass (ring FFT stage included) / DFMA peak"}
     del dalm, dmap, dback
+    L.psb200_sht_release()
     if cpu:
         # CPU arm in the reference's shape (oracle/shtcpu.c: per-ring FFTs + scaled lambda_lm recurrences, plain C + OpenMP,
         # -O3 -march=native; NOT libsharp, which Healpix.jl calls and which is not in this image), at nside 512 where it

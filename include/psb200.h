@@ -247,6 +247,9 @@ int psb200_alm2cl_dev(int lmax, const void* dalm1, const void* dalm2, void* dcl,
  * starts, out[2] warps, out[3] ring pairs per lane, out[4] ring-pair chunks, out[5] l steps per pass (out: 6 entries).
  * 4 FP64 instructions per step (2 of the un-normalised recurrence + 2 accumulate). */
 int psb200_sht_stats(int nside, int lmax, long long* out);
+/* The transforms keep their tables and work buffers per device between calls (one (nside, lmax) at a time; 12 GB at
+ * nside 2048, lmax 6143); this frees them on every device. */
+int psb200_sht_release(void);
 
 /* 3j terms (full families, as the reference evaluates them) of one call on rows [row_lo,row_hi). */
 long long psb200_terms(int families, int lmax, int row_lo, int row_hi);

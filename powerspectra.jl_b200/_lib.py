@@ -60,6 +60,7 @@ PROTOTYPES = {
     "psb200_alm2map_dev": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psb200_alm2cl_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psb200_sht_stats": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "psb200_sht_release": (C.c_int, []),
 }
 
 

@@ -104,6 +104,26 @@ int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
     return OK;
 }
 
+/* Frees the tables and work buffers the transforms keep per device between calls (12 GB at nside 2048, lmax 6143). */
+int psb200_sht_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    const int n = device_count();
+    if (n <= 0) return OK;
+    int cur = 0;
+    CUDA_TRY(cudaGetDevice(&cur));
+    for (int d = 0; d < n && d < 16; ++d) {
+        if (!g_sht[d].nside && !g_cl[d].p) continue;
+        CUDA_TRY(cudaSetDevice(d));
+        CUDA_TRY(cudaDeviceSynchronize());
+        sht_free(g_sht[d]);
+        cudaFree(g_cl[d].p);
+        g_cl[d] = ClScratch{};
+    }
+    CUDA_TRY(cudaSetDevice(cur));
+    return OK;
+}
+
 /* Work accounting of one Legendre pass (analysis or synthesis) as the kernel tiles it; host arithmetic.
  *   out[0] executed (l, m, ring-pair slot) steps: every started warp x its 16-step passes x 32 R slots
  *   out[1] steps of rings the transform starts (m <= mlim), l = m..lmax

@@ -93,6 +93,11 @@ def alm2cl_device(a: Alm, b: Alm | None = None) -> np.ndarray:
     return cl
 
 
+def release_transform_buffers():
+    """Free the per-device tables and work buffers the transforms keep between calls (psb200_sht_release)."""
+    _lib.check(_lib.lib().psb200_sht_release())
+
+
 class CovField:
     """src/workspace.jl:20-60: name, temperature and polarisation masks, pixel variances (i, q, u)."""
 
