@@ -833,7 +833,20 @@ def extras(args, ps, dev, L, world, torch, cpu):
         "what": "psb200_map2alm_dev / psb200_alm2map_dev / psb200_alm2cl_dev device-resident on one GPU; e2e = psb200_map2alm "
                 "with three pageable host maps (mask_i, mask_j, sigma^2) in and the alm out; fractions = executed "
                 "(l, m, ring pair) steps x 4 FP64 instructions / time of the whole pass (ring FFT stage included) / DFMA peak"}
-    del dalm, dmap, dback
+    # the same through the batched call: four products of the three maps, every map uploaded once, products dealt to `world` GPUs
+    prods = [[0, 1, -1], [0, 2, -1], [1, 2, -1], [0, 1, 2]]
+    outs = [np.zeros(dev.alm_size(lm), dtype=np.complex128) for _ in prods]
+    idx = (C.c_int * (3 * len(prods)))(*[v for p_ in prods for v in p_])
+    sc = np.full(len(prods), 4.0 * np.pi / npix)
+    op = (DP * len(prods))(*[o.ctypes.data_as(DP) for o in outs])
+
+    def many():
+        ps._lib.check(L.psb200_map2alm_many(nside, lm, 3, 3, ptrs, len(prods), idx, sc.ctypes.data_as(DP), op, world))
+    t_b = wtime(many, reps=1)
+    out["w_production"]["batched"] = {"products": len(prods), "unique_maps": 3, "ngpus": world, "ms_per_product": t_b / len(prods),
+                                      "equals_single_call": bool(np.array_equal(outs[3], halm)),
+                                      "what": "psb200_map2alm_many: maps uploaded once per device, alm downloads overlapped with the next product"}
+    del dalm, dmap, dback, outs
     L.psb200_sht_release()
     if cpu:
         # CPU arm in the reference's shape (oracle/shtcpu.c: per-ring FFTs + scaled lambda_lm recurrences, plain C + OpenMP,

@@ -237,6 +237,12 @@ int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, 
  * l = 0..lmax (alm1 == alm2 allowed).  Host forms take host buffers and run on the current device; the _dev forms take
  * device buffers and are asynchronous on `stream` (dmap is not modified).  No CPU fallback. */
 int psb200_map2alm(int nside, int lmax, int niter, int nfactors, const double* const* factors, double scale, double* alm);
+/* Every effective weight of a workspace in one call: alm[k] = map2alm(scale[k] * maps[idx[3k]] .* maps[idx[3k+1]] .* maps[idx[3k+2]])
+ * for k < nprod (idx entries -1 = no factor; the first must be given).  The nmaps unique host maps are uploaded ONCE per
+ * device instead of once per product; ngpus > 1 deals the products round-robin to that many devices (the transforms of
+ * different products are independent: no exchange), 0 = all visible, 1 = the current device. */
+int psb200_map2alm_many(int nside, int lmax, int niter, int nmaps, const double* const* maps, int nprod, const int* idx,
+                        const double* scale, double* const* alm, int ngpus);
 int psb200_alm2map(int nside, int lmax, const double* alm, double* map);
 int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl);
 int psb200_map2alm_dev(int nside, int lmax, int niter, const void* dmap, void* dalm, void* stream);

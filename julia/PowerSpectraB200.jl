@@ -299,6 +299,36 @@ function map2alm_device(maps::PowerSpectra.HealpixMap{Float64,PowerSpectra.RingO
 end
 
 """
+    map2alm_many(maps, products; lmax, niter = 3, scales = ones(length(products)), ngpus = NGPUS[]) -> Vector{Alm}
+
+`[map2alm(scales[k] .* prod(maps[i] for i in products[k]); lmax, niter) for k in eachindex(products)]` in one library call
+(psb200_map2alm_many): every distinct map crosses PCIe once per GPU instead of once per product, and the products are dealt
+to `ngpus` devices.  `products[k]` holds one to three 1-based indices into `maps`.  What a workspace needs: all the
+`effective_weight_alm!` products of its masks and variance maps (src/workspace.jl:141-171).
+"""
+function map2alm_many(maps::Vector{<:PowerSpectra.HealpixMap{Float64,PowerSpectra.RingOrder}}, products::Vector{<:AbstractVector{<:Integer}};
+                      lmax::Integer, niter::Integer = 3, scales::Vector{Float64} = ones(length(products)), ngpus::Integer = NGPUS[])
+    nside = maps[1].resolution.nside
+    all(m -> m.resolution.nside == nside, maps) || throw(ArgumentError("maps of different resolution"))
+    all(p -> 1 <= length(p) <= 3, products) || throw(ArgumentError("one to three factors per product"))
+    idx = fill(Cint(-1), 3 * length(products))
+    for (k, p) in enumerate(products), (f, i) in enumerate(p)
+        idx[3 * (k - 1) + f] = Cint(i - 1)
+    end
+    out = [PowerSpectra.Alm(lmax, lmax, zeros(ComplexF64, PowerSpectra.numberOfAlms(lmax, lmax))) for _ in products]
+    pix = [parent(m) for m in maps]
+    mp = [pointer(p) for p in pix]
+    op = [Ptr{Cdouble}(pointer(a.alm)) for a in out]
+    GC.@preserve pix mp out op idx scales begin
+        rc = ccall((:psb200_map2alm_many, LIB[]), Cint,
+                   (Cint, Cint, Cint, Cint, Ptr{Ptr{Cdouble}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Ptr{Cdouble}}, Cint),
+                   nside, lmax, niter, length(pix), mp, length(products), idx, scales, op, ngpus)
+    end
+    check(rc)
+    return out
+end
+
+"""
     alm2cl_device(a, b) -> Vector{Float64}
 
 `Healpix.alm2cl(a, b)` on the GPU for two full alm (mmax == lmax) of one lmax.

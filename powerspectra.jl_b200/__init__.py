@@ -14,7 +14,7 @@ from .covariance import (ConstantDict, CovarianceWorkspace, coupledcov, coupledc
                          loop_covTEEE, loop_covTEEE_planck, loop_covTETE, loop_covTTEE, loop_covTTTE,
                          loop_covTTTT, window_function_W)
 from .healpix import (CovField, HealpixMap, PolarizedHealpixMap, alm2cl_device, alm2map, effective_weight_alm, map2alm,
-                      nside2lmax, nside2npix)
+                      nside2lmax, nside2npix, precompute_effective_weights, weights_needed)
 from .modecoupling import (Alm, alm2cl, inner_mcm00, inner_mcm02, inner_mcmmm, inner_mcmpp,
                            inner_mcmpp_mcmmm, maskedalm2spectra, maskedalm2spectra_device, mcm,
                            mcm_master, mcm_solve)
@@ -26,5 +26,5 @@ __all__ = [
     "mcm", "mcm_master", "mcm_solve", "maskedalm2spectra", "maskedalm2spectra_device", "decouple_covmat_device", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
     "SpectralArray", "SpectralVector", "BlockSpectralMatrix", "spectralzeros", "spectralones",
     "decouple_covmat", "BandedSpectralMatrix", "quickpolXi", "quickpolW", "k_u", "Alm", "alm2cl", "HealpixMap", "PolarizedHealpixMap", "CovField", "map2alm", "alm2map", "alm2cl_device",
-    "effective_weight_alm", "nside2lmax", "nside2npix", "lib", "LIB_PATH", "PSB200Error",
+    "effective_weight_alm", "precompute_effective_weights", "weights_needed", "nside2lmax", "nside2npix", "lib", "LIB_PATH", "PSB200Error",
 ]

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "psb200_zonal_alm": (C.c_int, [C.c_int, C.c_int, DP, DP, DP, C.c_long, C.c_int, DP, C.c_long]),
     "psb200_quickpol_edges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "psb200_map2alm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, DPP, C.c_double, DP]),
+    "psb200_map2alm_many": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, DPP, C.c_int, C.POINTER(C.c_int), DP, DPP, C.c_int]),
     "psb200_alm2map": (C.c_int, [C.c_int, C.c_int, DP, DP]),
     "psb200_alm2cl": (C.c_int, [C.c_int, DP, DP, DP]),
     "psb200_map2alm_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

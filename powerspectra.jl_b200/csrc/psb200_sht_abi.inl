@@ -104,6 +104,94 @@ int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
     return OK;
 }
 
+// products dealt to device `dev`: k = first, first + stride, ...; every unique map the device needs is uploaded once
+static int map2alm_many_on_device(int dev, int first, int stride, int nside, int lmax, int niter, int nmaps,
+                                  const double* const* maps, int nprod, const int* idx, const double* scale,
+                                  double* const* alm, std::string* err)
+{
+    auto run = [&]() -> int {
+        CUDA_TRY(cudaSetDevice(dev));
+        if (int rc = scratch_reserve(dev, 5, 16)) return rc;
+        cudaStream_t st = g_scratch[dev].stream;
+        ShtPlan* P = nullptr;
+        if (int rc = sht_plan(dev, nside, lmax, st, &P)) return rc;
+        const size_t nb = (size_t)P->D.npix * sizeof(double);
+        std::vector<double*> dmap(nmaps, nullptr);
+        int rc = OK;
+        for (int k = first; k < nprod && rc == OK; k += stride)
+            for (int f = 0; f < 3 && rc == OK; ++f) {
+                const int i = idx[3 * k + f];
+                if (i < 0 || dmap[i]) continue;
+                const cudaError_t e = cudaMalloc(&dmap[i], nb);
+                if (e != cudaSuccess) { dmap[i] = nullptr; rc = fail(ERR_OOM, "map2alm_many: device copy of map %d: %s", i, cudaGetErrorString(e)); break; }
+                if (cudaMemcpyAsync(dmap[i], maps[i], nb, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = fail(ERR_CUDA, "map2alm_many: upload of map %d failed", i);
+            }
+        // the alm of product n goes to the host on the copy stream while product n + 1 is computed (two staging buffers)
+        cudaStream_t cs = g_scratch[dev].copy_stream;
+        cudaEvent_t* ev = g_scratch[dev].ev;                 // ev[b]: alm in buffer b computed; ev[2 + b]: buffer b copied out
+        int n = 0;
+        for (int k = first; k < nprod && rc == OK; k += stride, ++n) {
+            const int* ix = idx + 3 * k;
+            const int b = n & 1;
+            double* dalm = b ? P->alm2 : P->alm;
+            if (n >= 2 && cudaStreamWaitEvent(st, ev[2 + b], 0) != cudaSuccess) { rc = fail(ERR_CUDA, "map2alm_many: event wait"); break; }
+            psb::sht_product_kernel<<<1184, 256, 0, st>>>(P->D.npix, dmap[ix[0]], ix[1] >= 0 ? dmap[ix[1]] : nullptr,
+                                                         ix[2] >= 0 ? dmap[ix[2]] : nullptr, scale[k], P->work);
+            if (cudaGetLastError() != cudaSuccess) { rc = fail(ERR_CUDA, "map2alm_many: product kernel"); break; }
+            rc = sht_map2alm(*P, st, P->work, dalm, niter);
+            if (rc != OK) break;
+            if (cudaEventRecord(ev[b], st) != cudaSuccess || cudaStreamWaitEvent(cs, ev[b], 0) != cudaSuccess ||
+                cudaMemcpyAsync(alm[k], dalm, (size_t)2 * P->D.nalm * sizeof(double), cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+                cudaEventRecord(ev[2 + b], cs) != cudaSuccess)
+                rc = fail(ERR_CUDA, "map2alm_many: download of alm %d failed", k);
+        }
+        const cudaError_t es = cudaStreamSynchronize(st), ec = cudaStreamSynchronize(cs);
+        if (rc == OK && (es != cudaSuccess || ec != cudaSuccess)) rc = fail(ERR_CUDA, "map2alm_many: %s", cudaGetErrorString(es != cudaSuccess ? es : ec));
+        for (double* p : dmap) cudaFree(p);
+        return rc;
+    };
+    const int rc = run();
+    if (rc != OK && err) *err = g_err;
+    return rc;
+}
+
+int psb200_map2alm_many(int nside, int lmax, int niter, int nmaps, const double* const* maps, int nprod, const int* idx,
+                        const double* scale, double* const* alm, int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (nmaps < 1 || nprod < 1 || !maps || !idx || !scale || !alm || niter < 0) return fail(ERR_ARG, "map2alm_many: bad arguments");
+    for (int i = 0; i < nmaps; ++i)
+        if (!maps[i]) return fail(ERR_ARG, "map2alm_many: null map %d", i);
+    for (int k = 0; k < nprod; ++k) {
+        if (!alm[k]) return fail(ERR_ARG, "map2alm_many: null output %d", k);
+        if (idx[3 * k] < 0 || idx[3 * k] >= nmaps) return fail(ERR_ARG, "map2alm_many: product %d has no first factor", k);
+        for (int f = 1; f < 3; ++f)
+            if (idx[3 * k + f] >= nmaps || idx[3 * k + f] < -1) return fail(ERR_ARG, "map2alm_many: product %d names map %d", k, idx[3 * k + f]);
+        if (idx[3 * k + 1] < 0 && idx[3 * k + 2] >= 0) return fail(ERR_ARG, "map2alm_many: product %d skips its second factor", k);
+    }
+    if (int rc = sht_check(nside, lmax)) return rc;
+    int ng = 0;
+    if (int rc = resolve_ngpus(ngpus, &ng)) return rc;
+    if (ng > nprod) ng = nprod;
+    int cur = 0;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (ng == 1) {                                            // the caller's current device
+        if (cur >= 16) return fail(ERR_ARG, "device index %d above the supported 15", cur);
+        return map2alm_many_on_device(cur, 0, 1, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, nullptr);
+    }
+    std::vector<int> rcs(ng, OK);
+    std::vector<std::string> errs(ng);
+    std::vector<std::thread> th;
+    for (int g = 1; g < ng; ++g)
+        th.emplace_back([&, g] { rcs[g] = map2alm_many_on_device(g, g, ng, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, &errs[g]); });
+    rcs[0] = map2alm_many_on_device(0, 0, ng, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, &errs[0]);
+    for (auto& t : th) t.join();
+    cudaSetDevice(cur);
+    for (int g = 0; g < ng; ++g)
+        if (rcs[g] != OK) { g_err = "device " + std::to_string(g) + ": " + errs[g]; return rcs[g]; }
+    return OK;
+}
+
 /* Frees the tables and work buffers the transforms keep per device between calls (12 GB at nside 2048, lmax 6143). */
 int psb200_sht_release(void)
 {

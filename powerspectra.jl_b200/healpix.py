@@ -138,10 +138,63 @@ def effective_weight_alm(workspace, A, i, j, alpha, *, niter: int = 3) -> Alm:
     return w
 
 
+def _weight_terms(X):
+    return ("II",) if X == "TT" else ("QQ", "UU") if X == "PP" else (X,)
+
+
+def weights_needed(W_keys):
+    """The (A, i, j, alpha) effective weights behind a list of window-spectrum keys (X, Y, i, j, alpha, p, q, beta)."""
+    out = []
+    for X, Y, i, j, alpha, p, q, beta in W_keys:
+        for wx in _weight_terms(X):
+            out.append((wx, i, j, alpha))
+        for wy in _weight_terms(Y):
+            out.append((wy, p, q, beta))
+    return list(dict.fromkeys(out))
+
+
+def precompute_effective_weights(workspace, keys, *, niter: int = 3, ngpus: int = 1):
+    """All the effective weights `keys` = [(A, i, j, alpha), ...] not yet in the workspace's cache from ONE library call
+    (psb200_map2alm_many): every mask / variance map goes to the device once instead of once per product, and with
+    ngpus > 1 the products are dealt to several GPUs.  Same results as effective_weight_alm, which then finds them cached."""
+    from .covariance import NULL
+    lmax = workspace.lmax
+    todo, maps, index = [], [], {}
+
+    def slot(m):
+        if id(m) not in index:
+            index[id(m)] = len(maps)
+            maps.append(m.pixels)
+        return index[id(m)]
+
+    for key in dict.fromkeys(keys):
+        A, i, j, alpha = key
+        if key in workspace.effective_weights:
+            continue
+        X, Y = split_maptype(alpha)
+        m_iX, m_jY = workspace.mask_p[i, X], workspace.mask_p[j, Y]
+        if A == NULL:
+            todo.append((key, [slot(m_iX), slot(m_jY), -1], 1.0))
+        elif A in ("II", "QQ", "UU") and i == j:
+            todo.append((key, [slot(m_iX), slot(m_jY), slot(workspace.weight_p[i, A])], 4.0 * np.pi / len(m_iX)))
+    if not todo:
+        return 0
+    nside = HealpixMap(maps[0]).nside
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    out = [np.zeros(nalm, dtype=np.complex128) for _ in todo]
+    idx = (C.c_int * (3 * len(todo)))(*[v for _, ix, _ in todo for v in ix])
+    scale = np.array([sc for _, _, sc in todo], dtype=np.float64)
+    mp = (_lib.DP * len(maps))(*[_dp(m) for m in maps])
+    op = (_lib.DP * len(out))(*[o.ctypes.data_as(_lib.DP) for o in out])
+    _lib.check(_lib.lib().psb200_map2alm_many(nside, lmax, int(niter), len(maps), mp, len(todo), idx, _dp(scale), op, int(ngpus)))
+    for (key, _, _), o in zip(todo, out):
+        workspace.effective_weights[key] = Alm(lmax, lmax, o)
+    return len(todo)
+
+
 def window_spectrum(workspace, X, Y, i, j, alpha, p, q, beta, *, niter: int = 3) -> np.ndarray:
     """The arithmetic of window_function_W! (src/workspace.jl:181-208): TT -> (II,), PP -> (QQ, UU), mean of alm2cl."""
-    tx = ("II",) if X == "TT" else ("QQ", "UU") if X == "PP" else (X,)
-    ty = ("II",) if Y == "TT" else ("QQ", "UU") if Y == "PP" else (Y,)
+    tx, ty = _weight_terms(X), _weight_terms(Y)
     out = np.zeros(workspace.lmax + 1)
     for wx in tx:
         for wy in ty:

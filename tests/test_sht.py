@@ -167,6 +167,25 @@ def test_host_ring_transforms_any_length(hc, n, shifted):
     assert np.max(np.abs(hc.sht_ring_synthesise(F, n, shifted) - fr.astype(float))) < 5e-14 * np.sqrt(mmax)
 
 
+def test_host_ring_transforms_property(hc):
+    """Random ring lengths 4r (r up to 2048: every mix of radices the HEALPix caps produce): synthesis of a band-limited
+    spectrum followed by analysis returns it (mmax < n/2: no aliasing), for shifted and unshifted rings."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(st.integers(min_value=1, max_value=2048), st.booleans(), st.integers(min_value=0, max_value=2 ** 31 - 1))
+    def run(r, shifted, seed):
+        n = 4 * r
+        mmax = n // 2 - 1
+        rng = np.random.default_rng(seed)
+        F = rng.normal(size=mmax + 1) + 1j * rng.normal(size=mmax + 1)
+        F[0] = F[0].real
+        f = hc.sht_ring_synthesise(F, n, shifted)
+        back = hc.sht_ring_analyse(f, shifted, 1.0 / n, mmax)
+        assert np.max(np.abs(back - F)) < 1e-12 * np.sqrt(n)
+    run()
+
+
 @pytest.mark.parametrize("nside", [1, 2, 8, 64, 2048])
 def test_host_ring_geometry(hc, nside):
     nphi, start, z, phi0 = so.ring_table(nside)
@@ -354,6 +373,53 @@ def test_gpu_workspace_window_spectra_vs_oracle(ps):
     assert np.all(np.isfinite(C_.parent)) and np.allclose(C_.parent, C_.parent.T)
 
 
+def _two_field_workspace(ps, nside, lmax, seed=5):
+    rng = np.random.default_rng(seed)
+    th, ph = so.pix2ang_ring(nside)
+    th, ph = th.astype(float), ph.astype(float)
+    mask = lambda k: 0.5 * (1 + np.tanh(4 * (np.sin(th) * np.cos(ph - k) + 0.3 * np.cos(2 * th) + 0.2)))
+    var = lambda k: 1.0 + 0.5 * np.cos(th + k) ** 2 + 0.1 * rng.random(th.size)
+    F = [ps.CovField(name, mask(k), mask(k + 0.5), ps.PolarizedHealpixMap(var(k), var(k + 1), var(k + 2)))
+         for k, name in enumerate("AB")]
+    return ps.CovarianceWorkspace.from_fields(F[0], F[1], F[0], F[1], lmax=lmax)
+
+
+def _batched_weights_case(ps, ngpus):
+    """psb200_map2alm_many (unique maps uploaded once, products dealt to `ngpus` devices) against the one-at-a-time path:
+    every effective weight the TTTT and EEEE window spectra of a two-field workspace need, bit for bit."""
+    nside, lmax = 32, 80
+    N_ = ps.covariance.NULL
+    W_keys = [(N_, N_, "A", "A", "TT", "B", "B", "TT"), (N_, "TT", "A", "B", "TT", "A", "B", "TT"),
+              ("TT", "TT", "A", "A", "TT", "B", "B", "TT"), ("PP", "PP", "A", "A", "PP", "B", "B", "PP"),
+              (N_, "PP", "B", "B", "PP", "A", "A", "PP"), ("TT", "PP", "A", "A", "TP", "B", "B", "PT")]
+    keys = ps.weights_needed(W_keys)
+    assert ("QQ", "A", "A", "PP") in keys and ("II", "A", "B", "TT") in keys
+    one = _two_field_workspace(ps, nside, lmax)
+    many = _two_field_workspace(ps, nside, lmax)
+    n = ps.precompute_effective_weights(many, keys, ngpus=ngpus)
+    assert n == len([k for k in keys if k[0] == N_ or k[1] == k[2]])            # i != j noise weights are zero: not computed
+    assert ps.precompute_effective_weights(many, keys, ngpus=ngpus) == 0       # all cached now
+    for k in keys:
+        a = ps.effective_weight_alm(one, *k)
+        b = ps.effective_weight_alm(many, *k)
+        assert np.array_equal(a.alm, b.alm), k
+    for wk in W_keys:
+        assert np.array_equal(ps.window_function_W(one, *wk).parent, ps.window_function_W(many, *wk).parent)
+
+
+@pytest.mark.gpu
+def test_gpu_batched_effective_weights(ps):
+    _batched_weights_case(ps, 1)
+
+
+@pytest.mark.gpu
+def test_gpu_batched_effective_weights_across_gpus(ps):
+    if ps.lib().psb200_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _batched_weights_case(ps, 2)
+    _batched_weights_case(ps, 0)
+
+
 @pytest.mark.gpu
 def test_gpu_sht_argument_errors(ps):
     with pytest.raises(ValueError):
@@ -363,6 +429,15 @@ def test_gpu_sht_argument_errors(ps):
         ps.map2alm(f, lmax=8)                                            # lmax > 4 nside - 1
     with pytest.raises(ValueError):
         ps.map2alm(f, lmax=3, niter=-1)
+    import ctypes as C
+    DP = ps._lib.DP
+    m = np.ones(48)
+    out = np.zeros(10, dtype=np.complex128)
+    mp, op = (DP * 1)(m.ctypes.data_as(DP)), (DP * 1)(out.ctypes.data_as(DP))
+    sc = np.ones(1)
+    call = lambda ix, ng=1: ps.lib().psb200_map2alm_many(2, 3, 0, 1, mp, 1, (C.c_int * 3)(*ix), sc.ctypes.data_as(DP), op, ng)
+    assert call([0, -1, -1]) == 0 and abs(out[0] - np.sqrt(4 * np.pi)) < 1e-14
+    assert call([-1, 0, -1]) == 1 and call([0, 1, -1]) == 1 and call([0, -1, 0]) == 1 and call([0, -1, -1], 99) == 1
     assert ps.map2alm(f, lmax=0, niter=0).alm.size == 1
     from powerspectra_jl_b200 import healpix
     healpix.release_transform_buffers()                                  # and the next call rebuilds its plan
