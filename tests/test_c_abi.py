@@ -45,11 +45,11 @@ C_SRC = textwrap.dedent(r"""
         if (ndev() == 0) {
             if (rc != 5 || !strstr(last_error(), "no CPU fallback")) { printf("expected code 5, got %d (%s)\n", rc, last_error()); return 7; }
         } else if (rc != 0) { printf("compute failed: %d %s\n", rc, last_error()); return 8; }
-        /* W-spectrum production: map2alm of 2 x (0.5 everywhere) at nside 2 is sqrt(4 pi) Y_00 */
+        /* W-spectrum production: the pixel-weighted analysis (niter 0) of 2 x (0.5 everywhere) at nside 2 gives a_00 = sqrt(4 pi) */
         double map[48], alm[2 * 10];
         for (int i = 0; i < 48; ++i) map[i] = 0.5;
         const double* maps[1] = {map};
-        int rs = map2alm(2, 3, 3, 1, maps, 2.0, alm);
+        int rs = map2alm(2, 3, 0, 1, maps, 2.0, alm);
         if (ndev() == 0) {
             if (rs != 5) { printf("map2alm: expected code 5, got %d\n", rs); return 11; }
         } else if (rs != 0 || !(alm[0] > 3.5449077018110 && alm[0] < 3.5449077018111) || alm[1] != 0.0) {
