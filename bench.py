@@ -459,6 +459,64 @@ def run_gpu(args, lmax):
         for _ in range(e2e_steps):
             host_calls(host_out, world)              # blocking host calls: wall clock brackets them
         wall_e2e = (time.perf_counter() - t0) * 1e3
+        e2e_alloc = {"used": "one-node page-locked arrays (torch pin_memory)", "numa_nodes": int(L.psb200_host_numa_nodes())}
+        # Several GPUs on a multi-socket host: the same calls into result arrays whose 2 MB pieces alternate between the
+        # NUMA nodes (psb200_host_alloc policy 1) -- every GPU then writes half of its region to its own socket.  Both
+        # allocations are timed in every such run and both numbers are reported; e2e is the faster one.
+        if world > 1 and e2e_alloc["numa_nodes"] > 1 and not os.environ.get("PSB200_BENCH_NO_INTERLEAVE"):
+            import ctypes
+            blocks, host_il = [], {}
+            for name, v in outs.items():
+                host_il[name] = []
+                for _ in v:
+                    p = L.psb200_host_alloc(N * N * 8, 1)
+                    if not p:
+                        raise SystemExit("psb200_host_alloc: " + L.psb200_last_error().decode())
+                    blocks.append(p)
+                    host_il[name].append(np.ctypeslib.as_array(ctypes.cast(p, DP), shape=(N, N)))
+            cnt = (ctypes.c_int * 8)()
+            seen = L.psb200_host_placement(blocks[0], cnt, 8)
+            host_calls(host_il, world)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_calls(host_il, world)
+            wall_il = (time.perf_counter() - t0) * 1e3
+            same = all(np.array_equal(a, b) for name in host_out for a, b in zip(host_out[name], host_il[name]))
+            e2e_alloc.update({"one_node_ms_per_step": wall_e2e / e2e_steps, "interleaved_ms_per_step": wall_il / e2e_steps,
+                              "interleaved_placement_sample": list(cnt)[:e2e_alloc["numa_nodes"]] if seen > 0 else None,
+                              "interleaved_equals_one_node": bool(same)})
+            if not same:
+                raise SystemExit("bench: results in the interleaved arrays differ from the one-node arrays")
+            if wall_il < wall_e2e:
+                wall_e2e = wall_il
+                e2e_alloc["used"] = "page-locked arrays interleaved over the NUMA nodes (psb200_host_alloc policy 1)"
+            del host_il
+            for p in blocks:
+                L.psb200_host_free(p)
+
+        # ---- the same calls into PAGEABLE result arrays, which is what the reference allocates (spectralzeros): the
+        # library's staged delivery (page-locked ring + scatter threads) beside the CUDA runtime's own bounce copies ----
+        pageable = None
+        if not os.environ.get("PSB200_BENCH_NO_PAGEABLE"):
+            host_pg = {name: [np.zeros((N, N)) + 0.0 for _ in v] for name, v in outs.items()}      # touched pages, like Julia's zeros
+            pageable = {}
+            saved = os.environ.get("PSB200_STAGED")
+            for key, val in (("staged_ms_per_step", "1"), ("runtime_bounce_ms_per_step", "0")):
+                os.environ["PSB200_STAGED"] = val
+                host_calls(host_pg, world)
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    host_calls(host_pg, world)
+                pageable[key] = (time.perf_counter() - t0) * 1e3 / e2e_steps
+                pageable[key.replace("_ms_per_step", "_equals_page_locked")] = bool(
+                    all(np.array_equal(a, b) for name in host_out for a, b in zip(host_out[name], host_pg[name])))
+            if saved is None:
+                del os.environ["PSB200_STAGED"]
+            else:
+                os.environ["PSB200_STAGED"] = saved
+            del host_pg
+            if not (pageable["staged_equals_page_locked"] and pageable["runtime_bounce_equals_page_locked"]):
+                raise SystemExit(f"bench: results in pageable arrays differ from the page-locked ones: {pageable}")
 
         # ---- the outputs themselves: N-GPU host call == 1-GPU host call == NCCL-gather driver, bit for bit ----
         # (every (l1,l2) pair is computed independently of the banding, src/modecoupling.jl:84-92, so any difference
@@ -546,6 +604,7 @@ def run_gpu(args, lmax):
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / e2e_steps,
                     "path": f"psb200_mcm / psb200_cov C-ABI host calls with ngpus={world} (pageable inputs, pinned "
                             "host outputs; every GPU copies its own band of the result to the host)",
+                    "host_arrays": e2e_alloc, "pageable_outputs": pageable,
                     "per_rank_driver": None if ms_driver is None else {
                         "ms_per_step": ms_driver, "value": terms_step / (ms_driver * 1e-3),
                         "path": "pinned host -> H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0"}},

@@ -38,6 +38,7 @@
  */
 #ifndef PSB200_H
 #define PSB200_H
+#include <stddef.h>   /* size_t */
 
 #ifdef __cplusplus
 extern "C" {
@@ -273,6 +274,33 @@ int psb200_job_stats(int api, int code, int lmax, int lenW, int row_lo, int row_
 /* FP64 pipe microbenchmark: dependent-free DFMA streams on every SM for `iters` iterations;
  * returns achieved FLOP/s (2 per DFMA) on the current device, <0 on error. */
 double psb200_dfma_peak(int iters);
+
+/* ---- host result buffers -------------------------------------------------------------------------------
+ * The reference allocates its result arrays itself (spectralzeros, src/modecoupling.jl:199 etc. -- pageable memory, which
+ * the host calls accept as they are).  A caller that owns the allocation gets the full PCIe rate from a page-locked
+ * array, and on a multi-socket box with several GPUs from one whose pages are spread over the sockets: every GPU writes
+ * its own region of the result by DMA, and an array that lives on one socket makes half the GPUs write across the
+ * socket link.
+ * psb200_host_alloc: page-locked (cudaHostRegister, portable), zero-filled, 2 MB aligned.  policy 0 = pages on the NUMA
+ *   node of the calling thread; policy 1 = 2 MB pieces alternating between the NUMA nodes the process may run on
+ *   (mbind(MPOL_INTERLEAVE), or first touch by node-bound threads where the container filters mbind; same as 0 on a
+ *   one-node host).  NULL on failure (psb200_last_error).  On a host without a CUDA device the memory is returned
+ *   unregistered (placement stays testable); the compute calls still fail with code 5 there.
+ * psb200_host_free: releases such a block (0, or 1 for a pointer that is not one).
+ * psb200_host_placement: counts[k] = sampled pieces of the block found on node k < maxnodes; returns the number of
+ *   samples, 0 when the kernel does not tell (get_mempolicy filtered), -1 for a bad pointer.
+ * psb200_host_numa_nodes: nodes policy 1 would use. */
+void* psb200_host_alloc(size_t bytes, int policy);
+/* PAGEABLE result arrays -- what the reference itself allocates -- are served by a staged delivery inside the host
+ * calls: the regions of the result are DMA'd into a ring of page-locked chunks of the library and scattered into the
+ * caller's array by a few host threads, instead of the CUDA runtime's one-thread bounce copy.  Environment:
+ * PSB200_STAGED=0 turns it off, PSB200_STAGE_THREADS (default min(8, cores / (2 ngpus))) and PSB200_STAGE_CHUNK_MB
+ * (default 8) tune it.  psb200_selftest_delivery is its test hook: host memory only, no device (csrc/psb200.cu). */
+int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int staged, int chunk_kb, int nch,
+                             int nthreads, double* const* out, long ldo);
+int psb200_host_free(void* p);
+int psb200_host_placement(const void* p, int* counts, int maxnodes);
+int psb200_host_numa_nodes(void);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,27 @@ function quickpol_call!(𝚵::SpectralArray{Float64,2}, ν₁, ν₂, s₁, s₂
 end
 
 """
+    pinned_spectralzeros(lmin:lmax; interleave = false) -> SpectralArray{Float64,2}
+
+A zero N x N `SpectralArray` over `lmin:lmax` in page-locked memory of the library (psb200_host_alloc): the result of a
+host call lands in it at the full PCIe rate (about 55 GB/s against 20 GB/s into a pageable `spectralzeros`).  With
+`interleave = true` the 2 MB pieces of the array alternate between the NUMA nodes of the host, which is what a call on
+several GPUs of a two-socket box wants.  Pass it to the in-place methods (`PowerSpectra.inner_mcm⁰⁰!(𝐌, V)` and the
+`loop_cov*!` family); release it with `free_pinned!(𝐌)` when done (the memory is not garbage collected).
+"""
+function pinned_spectralzeros(r::AbstractUnitRange; interleave::Bool = false)
+    n = length(r)
+    p = ccall((:psb200_host_alloc, LIB[]), Ptr{Cdouble}, (Csize_t, Cint), n * n * sizeof(Float64), interleave ? 1 : 0)
+    p == C_NULL && error("libpsb200: " * unsafe_string(ccall((:psb200_last_error, LIB[]), Cstring, ())))
+    A = unsafe_wrap(Array, p, (n, n); own = false)            # zero-filled by the library
+    return SpectralArray(A, (first(r) - 1, first(r) - 1))
+end
+
+"Release an array made by `pinned_spectralzeros`; it must not be touched afterwards."
+free_pinned!(𝐌::SpectralArray{Float64,2}) =
+    (ccall((:psb200_host_free, LIB[]), Cint, (Ptr{Cvoid},), pointer(parent(𝐌))) == 0 || throw(ArgumentError("not a pinned_spectralzeros array")); nothing)
+
+"""
     enable!(libpath = "libpsb200.so"; ngpus = 1)
 
 Re-define the inner loops of PowerSpectra to call the B200 library.  `ngpus = 0` uses every

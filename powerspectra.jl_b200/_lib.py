@@ -62,6 +62,11 @@ PROTOTYPES = {
     "psb200_alm2cl_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "psb200_sht_stats": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "psb200_sht_release": (C.c_int, []),
+    "psb200_host_alloc": (C.c_void_p, [C.c_size_t, C.c_int]),
+    "psb200_host_free": (C.c_int, [C.c_void_p]),
+    "psb200_host_placement": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
+    "psb200_host_numa_nodes": (C.c_int, []),
+    "psb200_selftest_delivery": (C.c_int, [C.c_int] * 10 + [DPP, C.c_long]),
 }
 
 
@@ -105,3 +110,36 @@ def check(rc: int):
         import numpy as np
         raise np.linalg.LinAlgError(msg)       # Julia: LinearAlgebra.SingularException
     raise PSB200Error(rc, msg)
+
+
+class HostMatrix:
+    """An N x N Float64 result array in page-locked host memory of the library (psb200_host_alloc), column-major like
+    parent(SpectralArray).  `interleave=True` spreads its 2 MB pieces over the NUMA nodes of the host, which is what
+    a several-GPU host call wants (every GPU writes its own region by DMA).  `.array` is the numpy view; the memory is
+    released by `.free()` or when the object dies -- views taken from `.array` must not outlive it."""
+
+    def __init__(self, n: int, interleave: bool = False):
+        import numpy as np
+        L = lib()
+        self._p = L.psb200_host_alloc(int(n) * int(n) * 8, 1 if interleave else 0)
+        if not self._p:
+            raise PSB200Error(4, L.psb200_last_error().decode("utf-8", "replace"))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, DP), shape=(n, n)).T      # Fortran order over the block
+
+    def placement(self, maxnodes: int = 8):
+        """Sampled 2 MB pieces per NUMA node, or None where the kernel does not tell."""
+        cnt = (C.c_int * maxnodes)()
+        seen = lib().psb200_host_placement(self._p, cnt, maxnodes)
+        return list(cnt) if seen > 0 else None
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().psb200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

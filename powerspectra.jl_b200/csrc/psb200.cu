@@ -16,8 +16,10 @@
 
 #include <cusolverDn.h>      // types + prototypes only: the library is loaded with dlopen (psb200_solve.inl)
 #include <dlfcn.h>
+#include <emmintrin.h>       // SSE2 streaming stores of the staged delivery (host side)
 
 #include <algorithm>
+#include <condition_variable>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -529,6 +531,9 @@ struct DeviceScratch {
     cudaStream_t copy_stream = nullptr;     // D2H of finished column bands, overlapped with compute
     cudaEvent_t ev_in = nullptr;            // inputs of the call are on the device
     cudaEvent_t ev[32] = {};
+    char* ring = nullptr;                   // page-locked staging chunks of the pageable-destination delivery
+    size_t ring_bytes = 0;
+    cudaEvent_t ring_ev[32] = {};           // blocking-sync events, one per chunk
 };
 DeviceScratch g_scratch[16];
 
@@ -683,7 +688,201 @@ static std::vector<int> split_rows(int a, int b, int lmax, int lenW, int nsub)
     return e;
 }
 
-int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
+// ---------------------------------------------------------------------------------------
+// Delivery of a band's result to the caller's host array.
+//
+// A band hands over a list of 2-D copies (block columns straight from the slab, block rows from their transposed
+// copies), each tied to the sub-band whose kernels produce it.  Into PAGE-LOCKED destinations they are issued as they
+// are: cudaMemcpy2DAsync on the copy stream, DMA straight into the caller's array (55 GB/s on the B200 boxes).  Into
+// PAGEABLE destinations -- what the reference allocates (spectralzeros, src/modecoupling.jl:199, src/covariance.jl:47)
+// -- the CUDA runtime stages every copy through its own bounce buffer with one host thread (20 GB/s measured: 15 ms for
+// one 302 MB matrix against 4.8 ms of TT kernels).  The staged path below does the bouncing itself: pieces of <= 8 MB are
+// DMA'd densely into a ring of page-locked chunks and nthreads host workers scatter finished chunks into the caller's
+// array (piece i belongs to worker i mod nthreads; a chunk is reused once its piece is scattered), so the DMA engine
+// and several memcpy streams run side by side and behind the kernels of the later sub-bands.
+// PSB200_STAGED=0 restores the runtime's own staging; PSB200_STAGE_THREADS / PSB200_STAGE_CHUNK_MB tune it.
+// ---------------------------------------------------------------------------------------
+struct Copy2D {
+    double* dst; size_t dpitch;             // host; bytes between consecutive rows of the copy
+    const double* src; size_t spitch;       // device (a host stand-in under the CPU test hook)
+    size_t width, h;                        // bytes per row, rows
+    int k;                                  // sub-band whose event the copy waits for
+};
+
+// the copies of one band, in the order the sub-bands finish (shared by the direct and the staged delivery)
+static std::vector<Copy2D> band_copies(int N, int lmin, int a, const std::vector<int>& sub, int nout, double* const* out, long ldo,
+                                       double* const* X, long ldX, const double* T, const std::vector<size_t>& toff)
+{
+    std::vector<Copy2D> cp;
+    const int ns = (int)sub.size() - 1;
+    for (int k = 0; k < ns; ++k) {
+        const int sa = sub[k], sb = sub[k + 1], nbs = sb - sa;
+        const int c0 = sb - lmin;                                  // first column right of this diagonal block
+        const size_t r0 = (size_t)(sa - lmin);
+        for (int o = 0; o < nout; ++o) {
+            const double* slab = X[o] + (size_t)(sa - a) * ldX;     // row sa of the slab
+            // block column: nbs columns of (N - r0) rows each
+            cp.push_back({out[o] + r0 * ldo + r0, (size_t)ldo * sizeof(double), slab + r0, (size_t)ldX * sizeof(double),
+                          (size_t)(N - r0) * sizeof(double), (size_t)nbs, k});
+            // block row: (N - c0) columns of nbs rows each
+            if (c0 < N) {
+                const double* Tk = T + toff[k] + (size_t)o * nbs * (N - c0);
+                cp.push_back({out[o] + (size_t)c0 * ldo + r0, (size_t)ldo * sizeof(double), Tk, (size_t)nbs * sizeof(double),
+                              (size_t)nbs * sizeof(double), (size_t)(N - c0), k});
+            }
+        }
+    }
+    return cp;
+}
+
+// cut every copy into pieces of at most chunk_bytes (whole rows)
+static std::vector<Copy2D> split_copies(const std::vector<Copy2D>& cp, size_t chunk_bytes)
+{
+    std::vector<Copy2D> out;
+    for (const Copy2D& c : cp) {
+        if (c.width == 0 || c.h == 0) continue;
+        const size_t rows = std::max<size_t>(1, chunk_bytes / c.width);
+        for (size_t r = 0; r < c.h; r += rows) {
+            Copy2D p = c;
+            p.dst = (double*)((char*)c.dst + r * c.dpitch);
+            p.src = (const double*)((const char*)c.src + r * c.spitch);
+            p.h = std::min(rows, c.h - r);
+            out.push_back(p);
+        }
+    }
+    return out;
+}
+
+// One row of a piece into the caller's array with streaming (non-temporal) stores: the destination is written once and
+// not read again by this call, so there is no point in reading its cache lines first (a plain memcpy of a 3-49 KB row
+// does: read-for-ownership, a third more memory traffic).  PSB200_STAGE_NT=0 selects memcpy.
+static inline void copy_row_nt(char* dst, const char* src, size_t n)
+{
+    size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (head > n) head = n;
+    if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+        _mm_stream_si128((__m128i*)(dst + i), a);
+        _mm_stream_si128((__m128i*)(dst + i + 16), b);
+        _mm_stream_si128((__m128i*)(dst + i + 32), c);
+        _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    for (; i + 16 <= n; i += 16) _mm_stream_si128((__m128i*)(dst + i), _mm_loadu_si128((const __m128i*)(src + i)));
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+
+// The pipeline: issue(i, chunk, c) starts the dense copy of piece i into chunk c and marks its completion, wait(c) blocks
+// until that copy has landed.  Both return 0 or an error code (message in the calling thread's g_err).
+template <class Issue, class Wait>
+static int deliver_staged(const std::vector<Copy2D>& pieces, char* ring, size_t chunk_bytes, int nch, int nthreads,
+                          Issue issue, Wait wait)
+{
+    const int P = (int)pieces.size();
+    if (P == 0) return OK;
+    nthreads = std::max(1, std::min(nthreads, P));
+    std::mutex m;
+    std::condition_variable cv;
+    int issued = 0, rc_shared = OK;
+    bool stop = false;
+    std::string err;
+    std::vector<char> busy(nch, 0);                    // chunk holds a piece that is not scattered yet
+    const char* nt_env = getenv("PSB200_STAGE_NT");
+    const bool nt = !(nt_env && nt_env[0] == '0');
+    auto give_up = [&](int rc) {
+        std::lock_guard<std::mutex> lk(m);
+        if (rc_shared == OK) { rc_shared = rc; err = g_err; }
+        stop = true;
+        cv.notify_all();
+    };
+    auto worker = [&](int t) {
+        for (int i = t; i < P; i += nthreads) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return issued > i || stop; });
+                if (issued <= i) return;               // stopped before piece i was issued
+            }
+            const int c = i % nch;
+            if (int rc = wait(c)) { give_up(rc); return; }
+            const Copy2D& p = pieces[i];
+            const char* src = ring + (size_t)c * chunk_bytes;
+            if (nt) {
+                for (size_t r = 0; r < p.h; ++r) copy_row_nt((char*)p.dst + r * p.dpitch, src + r * p.width, p.width);
+                _mm_sfence();
+            } else if (p.dpitch == p.width) memcpy(p.dst, src, p.width * p.h);
+            else for (size_t r = 0; r < p.h; ++r) memcpy((char*)p.dst + r * p.dpitch, src + r * p.width, p.width);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                busy[c] = 0;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+    for (int i = 0; i < P; ++i) {
+        const int c = i % nch;
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return !busy[c] || stop; });
+            if (stop) break;
+            busy[c] = 1;
+        }
+        if (int rc = issue(i, ring + (size_t)c * chunk_bytes, c)) { give_up(rc); break; }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            issued = i + 1;
+        }
+        cv.notify_all();
+    }
+    for (auto& t : th) t.join();
+    if (rc_shared != OK) g_err = err;
+    return rc_shared;
+}
+
+static size_t stage_chunk_bytes()
+{
+    size_t mb = 8;
+    if (const char* e = getenv("PSB200_STAGE_CHUNK_MB")) mb = (size_t)std::max(1, std::min(64, atoi(e)));
+    return mb << 20;
+}
+
+static int stage_threads(int ngpus_in_call)
+{
+    if (const char* e = getenv("PSB200_STAGE_THREADS")) return std::max(1, std::min(28, atoi(e)));
+    const int hw = (int)std::thread::hardware_concurrency();
+    // MEASURED (1 B200, 16 host threads, lmax 6143, ms per call; page-locked destination 7.0 / 22.3, CUDA runtime's bounce
+    // copies 33.3 / 70.0 for TT / fused EE-BB): 2 workers 36.9 / 75.3, 4: 20.2 / 38.0, 8: 13.4 / 27.9, 12: 11.8 / 24.5
+    return std::max(2, std::min(12, 3 * hw / (4 * std::max(1, ngpus_in_call))));
+}
+
+// is p ordinary (pageable) host memory?  Page-locked, registered and managed memory all answer otherwise.
+static bool is_pageable(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// page-locked ring of device g: nch chunks of chunk_bytes and their events
+static int stage_ring_reserve(int g, size_t chunk_bytes, int nch)
+{
+    DeviceScratch& s = g_scratch[g];
+    const size_t need = chunk_bytes * (size_t)nch;
+    if (s.ring_bytes < need) {
+        if (s.ring) cudaFreeHost(s.ring);
+        s.ring = nullptr; s.ring_bytes = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&s.ring, need, cudaHostAllocPortable));
+        s.ring_bytes = need;
+    }
+    for (int c = 0; c < nch; ++c)
+        if (!s.ring_ev[c]) CUDA_TRY(cudaEventCreateWithFlags(&s.ring_ev[c], cudaEventDisableTiming | cudaEventBlockingSync));
+    return OK;
+}
+
+int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err, int ngpus_in_call = 1)
 {
     auto body = [&]() -> int {
         const int N = hj.lmax - hj.lmin + 1;
@@ -742,27 +941,37 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err)
             CUDA_TRY(cudaEventRecord(s.ev[k], sk));
         }
 
-        // everything is queued; now the copies on the second stream (a copy into pageable memory blocks
-        // this host thread, which is harmless once nothing is left to launch)
-        for (int k = 0; k < ns; ++k) {
-            const int sa = sub[k], sb = sub[k + 1], nbs = sb - sa;
-            const int c0 = sb - hj.lmin;
-            const size_t r0 = (size_t)(sa - hj.lmin);
-            CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev[k], 0));
-            for (int o = 0; o < hj.nout; ++o) {
-                const double* slab = s.X[o] + (size_t)(sa - a) * ldX;
-                // block column: nbs columns of (N - r0) rows each
-                CUDA_TRY(cudaMemcpy2DAsync(hj.out[o] + r0 * hj.ldo + r0, hj.ldo * sizeof(double), slab + r0,
-                                           ldX * sizeof(double), (size_t)(N - r0) * sizeof(double), nbs,
-                                           cudaMemcpyDeviceToHost, s.copy_stream));
-                // block row: (N - c0) columns of nbs rows each
-                if (c0 < N) {
-                    const double* Tk = s.T + toff[k] + (size_t)o * nbs * (N - c0);
-                    CUDA_TRY(cudaMemcpy2DAsync(hj.out[o] + (size_t)c0 * hj.ldo + r0, hj.ldo * sizeof(double), Tk,
-                                               (size_t)nbs * sizeof(double), (size_t)nbs * sizeof(double), N - c0,
-                                               cudaMemcpyDeviceToHost, s.copy_stream));
-                }
+        // everything is queued; now the delivery on the copy stream (see "Delivery" above)
+        const std::vector<Copy2D> copies = band_copies(N, hj.lmin, a, sub, hj.nout, hj.out, hj.ldo, s.X, ldX, s.T, toff);
+        size_t bytes = 0;
+        for (const Copy2D& c : copies) bytes += c.width * c.h;
+        const char* st_env = getenv("PSB200_STAGED");
+        const bool staged = !(st_env && st_env[0] == '0') && bytes >= (size_t(4) << 20) && is_pageable(hj.out[0]);
+        if (!staged) {
+            int waited = -1;
+            for (const Copy2D& c : copies) {
+                if (c.k != waited) { CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev[c.k], 0)); waited = c.k; }
+                CUDA_TRY(cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.h, cudaMemcpyDeviceToHost, s.copy_stream));
             }
+        } else {
+            const size_t chunk = stage_chunk_bytes();
+            const int nthr = stage_threads(ngpus_in_call), nch = std::min(32, nthr + 4);   // chunks: one per worker + 4 in flight
+            if (int rc = stage_ring_reserve(g, chunk, nch)) return rc;
+            const std::vector<Copy2D> pieces = split_copies(copies, chunk);
+            int waited = -1;
+            auto issue = [&](int i, char* dst, int c) -> int {
+                const Copy2D& p = pieces[i];
+                if (p.k != waited) { CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev[p.k], 0)); waited = p.k; }
+                CUDA_TRY(cudaMemcpy2DAsync(dst, p.width, p.src, p.spitch, p.width, p.h, cudaMemcpyDeviceToHost, s.copy_stream));
+                CUDA_TRY(cudaEventRecord(s.ring_ev[c], s.copy_stream));
+                return OK;
+            };
+            auto wait = [&](int c) -> int {                   // runs on the worker threads
+                CUDA_TRY(cudaSetDevice(g));
+                CUDA_TRY(cudaEventSynchronize(s.ring_ev[c]));
+                return OK;
+            };
+            if (int rc = deliver_staged(pieces, s.ring, chunk, nch, nthr, issue, wait)) return rc;
         }
         tr.mark("   band: kernels + finish + transpose", g, s.stream);
         CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -875,8 +1084,8 @@ int run_host_job(const HostJob& hj, int ngpus)
     std::vector<std::string> errs(ngpus);
     std::vector<std::thread> th;
     for (int g = 1; g < ngpus; ++g)
-        th.emplace_back([&, g] { rcs[g] = run_band_on_device(hj, g, edges[g], edges[g + 1], &errs[g]); });
-    rcs[0] = run_band_on_device(hj, 0, edges[0], edges[1], &errs[0]);
+        th.emplace_back([&, g] { rcs[g] = run_band_on_device(hj, g, edges[g], edges[g + 1], &errs[g], ngpus); });
+    rcs[0] = run_band_on_device(hj, 0, edges[0], edges[1], &errs[0], ngpus);
     for (auto& t : th) t.join();
     tr.mark("all bands delivered", 0, g_scratch[0].stream);
     cudaSetDevice(cur);
@@ -1446,6 +1655,48 @@ int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, 
 
 #include "psb200_sht_abi.inl"
 
+/* Test hook (host memory only, no device): the delivery plan of one band [a, b) of an N x N result cut into nsub
+ * sub-bands, executed on stand-in "device" buffers filled with distinct numbers -- directly (staged = 0: the 2-D copies
+ * as the page-locked path issues them) or through the staged pipeline (ring of nch chunks of chunk_kb KB, nthreads
+ * scatter workers).  Both must leave the same bytes in out[0..nout-1]; tests/test_host.py compares them. */
+int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int staged, int chunk_kb, int nch,
+                             int nthreads, double* const* out, long ldo)
+{
+    const int N = lmax - lmin + 1, nb = b - a;
+    if (lmin < 0 || a < lmin || b > lmax + 1 || nb <= 0 || nout < 1 || nout > 5 || !out || ldo < N || chunk_kb < 1 || nch < 1 ||
+        nch > 32 || nthreads < 1)
+        return fail(ERR_ARG, "selftest_delivery: bad arguments");
+    const std::vector<int> sub = split_rows(a, b, lmax, lmax + 1, nsub);
+    const int ns = (int)sub.size() - 1;
+    std::vector<size_t> toff(ns + 1, 0);
+    for (int k = 0; k < ns; ++k)
+        toff[k + 1] = toff[k] + (size_t)(sub[k + 1] - sub[k]) * (size_t)(N - (sub[k + 1] - lmin)) * nout;
+    std::vector<std::vector<double>> Xs(nout, std::vector<double>((size_t)nb * N));
+    std::vector<double> T(toff[ns] + 1);
+    double* X[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int o = 0; o < nout; ++o) {
+        for (size_t i = 0; i < Xs[o].size(); ++i) Xs[o][i] = (double)(o + 1) * 1e9 + (double)i;
+        X[o] = Xs[o].data();
+    }
+    for (size_t i = 0; i < T.size(); ++i) T[i] = -(double)(i + 1);
+    const std::vector<Copy2D> copies = band_copies(N, lmin, a, sub, nout, out, ldo, X, N, T.data(), toff);
+    auto copy2d = [](char* dst, size_t dpitch, const Copy2D& c) {
+        for (size_t r = 0; r < c.h; ++r) memcpy(dst + r * dpitch, (const char*)c.src + r * c.spitch, c.width);
+    };
+    if (!staged) {
+        for (const Copy2D& c : copies) copy2d((char*)c.dst, c.dpitch, c);
+        return OK;
+    }
+    const size_t chunk = (size_t)chunk_kb << 10;
+    for (const Copy2D& c : copies)
+        if (c.width > chunk) return fail(ERR_ARG, "selftest_delivery: a row of %zu bytes does not fit a chunk", c.width);
+    const std::vector<Copy2D> pieces = split_copies(copies, chunk);
+    std::vector<char> ring(chunk * (size_t)nch);
+    auto issue = [&](int i, char* dst, int) -> int { copy2d(dst, pieces[i].width, pieces[i]); return OK; };
+    auto wait = [](int) -> int { return OK; };
+    return deliver_staged(pieces, ring.data(), chunk, nch, nthreads, issue, wait);
+}
+
 double psb200_dfma_peak(int iters)
 {
     if (device_count() <= 0) { fail(ERR_NODEVICE, "no CUDA device visible"); return -1.0; }
@@ -1474,3 +1725,5 @@ double psb200_dfma_peak(int iters)
 }
 
 }  // extern "C"
+
+#include "psb200_hostmem.inl"

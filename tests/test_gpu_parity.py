@@ -743,3 +743,24 @@ def test_error_codes(ps):
     with pytest.raises(ValueError):
         ps.mcm("XX", ps.SpectralVector(V))
     assert lib.psb200_mcm(0, 0, 7, vp, 8, mp, 8, None, 1) == 0
+
+
+def test_result_in_library_host_buffers(ps):
+    """psb200_mcm into psb200_host_alloc arrays (page-locked; one node and interleaved over the NUMA nodes) gives the
+    same matrix, bit for bit, as into a pageable numpy array."""
+    from powerspectra_jl_b200 import synthetic as syn
+    lmax = 1023
+    N = lmax + 1
+    V = np.ascontiguousarray(syn.mask_spectra(lmax, seeds=(7, 8))[(0, 1)])
+    L = ps.lib()
+    DP = ps._lib.DP
+    ref = np.zeros((N, N), order="F")
+    ps._lib.check(L.psb200_mcm(4, 0, lmax, V.ctypes.data_as(DP), V.size, ref.ctypes.data_as(DP), N,
+                               np.zeros((N, N), order="F").ctypes.data_as(DP), 1))
+    assert np.abs(ref).max() > 0
+    for interleave in (False, True):
+        H, H2 = ps._lib.HostMatrix(N, interleave), ps._lib.HostMatrix(N, interleave)
+        ps._lib.check(L.psb200_mcm(4, 0, lmax, V.ctypes.data_as(DP), V.size, H.array.ctypes.data_as(DP), N,
+                                   H2.array.ctypes.data_as(DP), 0))
+        assert np.array_equal(H.array, ref)
+        H.free(), H2.free()

@@ -201,3 +201,72 @@ def test_band_edges_properties_random(ps):
         assert len(q) == nb + 1 and q[0] == 0 and q[-1] == lmax + 1
         assert all(b >= a for a, b in zip(q, q[1:]))
     check()
+
+
+def test_host_result_buffers(ps):
+    """psb200_host_alloc / free / placement (no device needed: registration is skipped without one)."""
+    L = ps.lib()
+    assert L.psb200_host_numa_nodes() >= 1
+    assert L.psb200_host_alloc(0, 0) is None and b"host_alloc" in L.psb200_last_error()
+    assert L.psb200_host_alloc(4096, 2) is None
+    for interleave in (False, True):
+        H = ps._lib.HostMatrix(700, interleave=interleave)        # 3.9 MB: two 2 MB pieces
+        assert H._p % (2 << 20) == 0
+        A = H.array
+        assert A.shape == (700, 700) and A.flags.f_contiguous and not A.any()
+        A[3, 5] = 2.5
+        flat = np.ctypeslib.as_array(C.cast(H._p, ps._lib.DP), shape=(700 * 700,))
+        assert flat[3 + 5 * 700] == 2.5                            # column-major, like parent(SpectralArray)
+        pl = H.placement()
+        assert pl is None or sum(pl) >= 1
+        p = H._p
+        H.free()
+        assert L.psb200_host_free(p) == 1                          # already released
+    assert L.psb200_host_free(None) == 0
+    cnt = (C.c_int * 4)()
+    assert L.psb200_host_placement(C.c_void_p(12345), cnt, 4) == -1
+
+
+def _deliver(ps, lmin, lmax, a, b, nsub, nout, staged, chunk_kb=64, nch=3, nthreads=2, pad=0):
+    N = lmax - lmin + 1
+    ld = N + pad
+    outs = [np.asfortranarray(np.full((ld, N), np.nan)) for _ in range(nout)]   # column-major, leading dimension ld >= N
+    DP = ps._lib.DP
+    arr = (DP * nout)(*[o.ctypes.data_as(DP) for o in outs])
+    rc = ps.lib().psb200_selftest_delivery(lmin, lmax, a, b, nsub, nout, staged, chunk_kb, nch, nthreads, arr, ld)
+    assert rc == 0, ps.lib().psb200_last_error()
+    return outs
+
+
+@pytest.mark.parametrize("lmin,lmax,a,b,nsub,nout", [(0, 255, 0, 256, 4, 1), (0, 255, 0, 256, 1, 2), (2, 300, 2, 301, 16, 5),
+                                                     (0, 511, 100, 380, 8, 2), (0, 511, 380, 512, 2, 1), (5, 40, 7, 8, 1, 1)])
+def test_staged_delivery_equals_direct(ps, lmin, lmax, a, b, nsub, nout):
+    """The staged delivery (ring of page-locked chunks + scatter workers; what pageable result arrays get) leaves the
+    same bytes as the direct 2-D copies, for any chunk size / ring length / worker count, and the L-shaped region of a
+    band [a, b) -- rows >= a of its columns, its rows of the columns to the right -- is written completely and only."""
+    N = lmax - lmin + 1
+    direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, pad=3)
+    r0, r1 = a - lmin, b - lmin
+    region = np.zeros((N, N), dtype=bool)
+    region[r0:, r0:r1] = True                     # block column
+    region[r0:r1, r1:] = True                     # block row
+    for D in direct:
+        assert np.array_equal(~np.isnan(D[:N, :]), region)
+        assert np.isnan(D[N:, :]).all()           # the padding rows of the leading dimension stay untouched
+        vals = D[:N, :][region]
+        assert np.unique(vals).size == vals.size  # every entry from its own source element
+    for chunk_kb, nch, nthreads in [(4, 1, 1), (4, 2, 3), (16, 3, 2), (64, 12, 8), (1024, 2, 4)]:
+        if chunk_kb * 1024 < N * 8:
+            continue
+        staged = _deliver(ps, lmin, lmax, a, b, nsub, nout, 1, chunk_kb, nch, nthreads, pad=3)
+        for S, D in zip(staged, direct):
+            assert np.array_equal(S, D, equal_nan=True), (chunk_kb, nch, nthreads)
+
+
+def test_staged_delivery_argument_errors(ps):
+    L = ps.lib()
+    out = np.zeros((8, 8), order="F")
+    arr = (ps._lib.DP * 1)(out.ctypes.data_as(ps._lib.DP))
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 64, 2, 2, arr, 4) == 1        # ld < N
+    assert L.psb200_selftest_delivery(0, 7, 0, 9, 1, 1, 1, 64, 2, 2, arr, 8) == 1        # band beyond the matrix
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 64, 40, 2, arr, 8) == 1       # ring too long
