@@ -882,6 +882,85 @@ static int stage_ring_reserve(int g, size_t chunk_bytes, int nch)
     return OK;
 }
 
+// A contiguous device -> host copy of `bytes` on copy stream `cs` of device g, blocking until the bytes are in `hdst`:
+// staged (see above) when the destination is pageable and large, one cudaMemcpyAsync + synchronize otherwise.
+static int download_blocking(int g, void* hdst, const void* dsrc, size_t bytes, cudaStream_t cs, int ngpus_in_call)
+{
+    const char* st_env = getenv("PSB200_STAGED");
+    if ((st_env && st_env[0] == '0') || bytes < (size_t(4) << 20) || !is_pageable(hdst)) {
+        CUDA_TRY(cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        return OK;
+    }
+    DeviceScratch& s = g_scratch[g];
+    const size_t chunk = stage_chunk_bytes();
+    const int nthr = stage_threads(ngpus_in_call), nch = std::min(32, 2 * nthr);
+    if (int rc = stage_ring_reserve(g, chunk, nch)) return rc;
+    std::vector<Copy2D> pieces;
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t w = std::min(chunk, bytes - off);
+        pieces.push_back({(double*)((char*)hdst + off), w, (const double*)((const char*)dsrc + off), w, w, 1, 0});
+    }
+    auto issue = [&](int i, char* dst, int c) -> int {
+        CUDA_TRY(cudaMemcpyAsync(dst, pieces[i].src, pieces[i].width, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaEventRecord(s.ring_ev[c], cs));
+        return OK;
+    };
+    auto wait = [&](int c) -> int {
+        CUDA_TRY(cudaSetDevice(g));
+        CUDA_TRY(cudaEventSynchronize(s.ring_ev[c]));
+        return OK;
+    };
+    return deliver_staged(pieces, s.ring, chunk, nch, nthr, issue, wait);
+}
+
+// A contiguous host -> device copy of `bytes`, queued on stream `st` of device g (the copies are in the stream when the
+// call returns; the source may be reused only after the stream has passed them -- every caller synchronises before it
+// returns to the user).  Pageable sources are gathered into the page-locked ring by nthreads workers, each of which owns
+// two chunks and issues its own pieces: fill chunk, cudaMemcpyAsync, record the chunk's event, and wait for that event
+// before the chunk is filled again.  (The CUDA runtime's own path for a pageable source is one thread and one bounce
+// buffer: three 403 MB maps were about 110 ms of the 316 ms of a host-level map2alm at nside 2048.)
+static int upload_async(int g, void* ddst, const void* hsrc, size_t bytes, cudaStream_t st, int ngpus_in_call)
+{
+    const char* st_env = getenv("PSB200_STAGED");
+    if ((st_env && st_env[0] == '0') || bytes < (size_t(4) << 20) || !is_pageable(hsrc)) {
+        CUDA_TRY(cudaMemcpyAsync(ddst, hsrc, bytes, cudaMemcpyHostToDevice, st));
+        return OK;
+    }
+    DeviceScratch& s = g_scratch[g];
+    const size_t chunk = stage_chunk_bytes();
+    const int nthr = stage_threads(ngpus_in_call), nch = std::min(32, 2 * nthr);
+    if (int rc = stage_ring_reserve(g, chunk, nch)) return rc;
+    const int nw = nch / 2;                                       // worker t owns chunks t and t + nw
+    const size_t P = (bytes + chunk - 1) / chunk;
+    std::vector<int> rcs(nw, OK);
+    std::vector<std::string> errs(nw);
+    auto worker = [&](int t) {
+        auto body = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(g));
+            for (size_t i = t; i < P; i += nw) {
+                const int c = (int)(i % (size_t)nch);               // = t or t + nw: i = t (mod nw)
+                char* buf = s.ring + (size_t)c * chunk;
+                const size_t off = i * chunk, w = std::min(chunk, bytes - off);
+                CUDA_TRY(cudaEventSynchronize(s.ring_ev[c]));       // the chunk's previous piece has left (no-op on a fresh event)
+                memcpy(buf, (const char*)hsrc + off, w);
+                CUDA_TRY(cudaMemcpyAsync((char*)ddst + off, buf, w, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaEventRecord(s.ring_ev[c], st));
+            }
+            return OK;
+        };
+        rcs[t] = body();
+        if (rcs[t] != OK) errs[t] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nw; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& t : th) t.join();
+    for (int t = 0; t < nw; ++t)
+        if (rcs[t] != OK) { g_err = errs[t]; return rcs[t]; }
+    return OK;
+}
+
 int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err, int ngpus_in_call = 1)
 {
     auto body = [&]() -> int {

@@ -55,16 +55,15 @@ int psb200_map2alm(int nside, int lmax, int niter, int nfactors, const double* c
         if (int rc = scratch_reserve(dev, 0, (size_t)P->D.npix)) return rc;
         slot[2] = g_scratch[dev].X[0];
     }
-    for (int i = 0; i < nfactors; ++i) CUDA_TRY(cudaMemcpyAsync(slot[i], factors[i], nb, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < nfactors; ++i)
+        if (int rc = upload_async(dev, slot[i], factors[i], nb, st, 1)) return rc;      // pageable maps: staged (psb200.cu "Delivery")
     if (nfactors > 1 || scale != 1.0) {
         psb::sht_product_kernel<<<1184, 256, 0, st>>>(P->D.npix, slot[0], nfactors > 1 ? slot[1] : nullptr,
                                                      nfactors > 2 ? slot[2] : nullptr, scale, P->work);
         CUDA_TRY(cudaGetLastError());
     }
     if (int rc = sht_map2alm(*P, st, P->work, P->alm, niter)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(alm, P->alm, (size_t)2 * P->D.nalm * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return OK;
+    return download_blocking(dev, alm, P->alm, (size_t)2 * P->D.nalm * sizeof(double), st, 1);
 }
 
 int psb200_alm2map(int nside, int lmax, const double* alm, double* map)
@@ -76,11 +75,9 @@ int psb200_alm2map(int nside, int lmax, const double* alm, double* map)
     cudaStream_t st = g_scratch[dev].stream;
     ShtPlan* P = nullptr;
     if (int rc = sht_plan(dev, nside, lmax, st, &P)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(P->alm, alm, (size_t)2 * P->D.nalm * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_async(dev, P->alm, alm, (size_t)2 * P->D.nalm * sizeof(double), st, 1)) return rc;
     if (int rc = sht_synthesis(*P, st, P->alm, nullptr, P->work)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(map, P->work, (size_t)P->D.npix * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return OK;
+    return download_blocking(dev, map, P->work, (size_t)P->D.npix * sizeof(double), st, 1);
 }
 
 int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
@@ -107,7 +104,7 @@ int psb200_alm2cl(int lmax, const double* alm1, const double* alm2, double* cl)
 // products dealt to device `dev`: k = first, first + stride, ...; every unique map the device needs is uploaded once
 static int map2alm_many_on_device(int dev, int first, int stride, int nside, int lmax, int niter, int nmaps,
                                   const double* const* maps, int nprod, const int* idx, const double* scale,
-                                  double* const* alm, std::string* err)
+                                  double* const* alm, std::string* err, int ngpus_in_call)
 {
     auto run = [&]() -> int {
         CUDA_TRY(cudaSetDevice(dev));
@@ -124,27 +121,33 @@ static int map2alm_many_on_device(int dev, int first, int stride, int nside, int
                 if (i < 0 || dmap[i]) continue;
                 const cudaError_t e = cudaMalloc(&dmap[i], nb);
                 if (e != cudaSuccess) { dmap[i] = nullptr; rc = fail(ERR_OOM, "map2alm_many: device copy of map %d: %s", i, cudaGetErrorString(e)); break; }
-                if (cudaMemcpyAsync(dmap[i], maps[i], nb, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = fail(ERR_CUDA, "map2alm_many: upload of map %d failed", i);
+                rc = upload_async(dev, dmap[i], maps[i], nb, st, ngpus_in_call);
             }
-        // the alm of product n goes to the host on the copy stream while product n + 1 is computed (two staging buffers)
+        // The alm of product n goes to the host on the copy stream while product n + 1 is computed (two alm buffers).  A
+        // download into pageable memory blocks this thread until the bytes have arrived, so the kernels of product n + 1
+        // are queued BEFORE product n is fetched; buffer b is free again once its download has returned.
         cudaStream_t cs = g_scratch[dev].copy_stream;
-        cudaEvent_t* ev = g_scratch[dev].ev;                 // ev[b]: alm in buffer b computed; ev[2 + b]: buffer b copied out
-        int n = 0;
+        cudaEvent_t* ev = g_scratch[dev].ev;                 // ev[b]: alm in buffer b computed
+        const size_t alm_bytes = (size_t)2 * P->D.nalm * sizeof(double);
+        auto fetch = [&](int k, int b) -> int {
+            if (cudaStreamWaitEvent(cs, ev[b], 0) != cudaSuccess) return fail(ERR_CUDA, "map2alm_many: event wait");
+            return download_blocking(dev, alm[k], b ? P->alm2 : P->alm, alm_bytes, cs, ngpus_in_call);
+        };
+        int n = 0, kprev = -1;
         for (int k = first; k < nprod && rc == OK; k += stride, ++n) {
             const int* ix = idx + 3 * k;
             const int b = n & 1;
             double* dalm = b ? P->alm2 : P->alm;
-            if (n >= 2 && cudaStreamWaitEvent(st, ev[2 + b], 0) != cudaSuccess) { rc = fail(ERR_CUDA, "map2alm_many: event wait"); break; }
             psb::sht_product_kernel<<<1184, 256, 0, st>>>(P->D.npix, dmap[ix[0]], ix[1] >= 0 ? dmap[ix[1]] : nullptr,
                                                          ix[2] >= 0 ? dmap[ix[2]] : nullptr, scale[k], P->work);
             if (cudaGetLastError() != cudaSuccess) { rc = fail(ERR_CUDA, "map2alm_many: product kernel"); break; }
             rc = sht_map2alm(*P, st, P->work, dalm, niter);
             if (rc != OK) break;
-            if (cudaEventRecord(ev[b], st) != cudaSuccess || cudaStreamWaitEvent(cs, ev[b], 0) != cudaSuccess ||
-                cudaMemcpyAsync(alm[k], dalm, (size_t)2 * P->D.nalm * sizeof(double), cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
-                cudaEventRecord(ev[2 + b], cs) != cudaSuccess)
-                rc = fail(ERR_CUDA, "map2alm_many: download of alm %d failed", k);
+            if (cudaEventRecord(ev[b], st) != cudaSuccess) { rc = fail(ERR_CUDA, "map2alm_many: event record"); break; }
+            if (kprev >= 0) rc = fetch(kprev, b ^ 1);
+            kprev = k;
         }
+        if (rc == OK && kprev >= 0) rc = fetch(kprev, (n - 1) & 1);
         const cudaError_t es = cudaStreamSynchronize(st), ec = cudaStreamSynchronize(cs);
         if (rc == OK && (es != cudaSuccess || ec != cudaSuccess)) rc = fail(ERR_CUDA, "map2alm_many: %s", cudaGetErrorString(es != cudaSuccess ? es : ec));
         for (double* p : dmap) cudaFree(p);
@@ -177,14 +180,14 @@ int psb200_map2alm_many(int nside, int lmax, int niter, int nmaps, const double*
     CUDA_TRY(cudaGetDevice(&cur));
     if (ng == 1) {                                            // the caller's current device
         if (cur >= 16) return fail(ERR_ARG, "device index %d above the supported 15", cur);
-        return map2alm_many_on_device(cur, 0, 1, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, nullptr);
+        return map2alm_many_on_device(cur, 0, 1, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, nullptr, 1);
     }
     std::vector<int> rcs(ng, OK);
     std::vector<std::string> errs(ng);
     std::vector<std::thread> th;
     for (int g = 1; g < ng; ++g)
-        th.emplace_back([&, g] { rcs[g] = map2alm_many_on_device(g, g, ng, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, &errs[g]); });
-    rcs[0] = map2alm_many_on_device(0, 0, ng, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, &errs[0]);
+        th.emplace_back([&, g] { rcs[g] = map2alm_many_on_device(g, g, ng, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, &errs[g], ng); });
+    rcs[0] = map2alm_many_on_device(0, 0, ng, nside, lmax, niter, nmaps, maps, nprod, idx, scale, alm, &errs[0], ng);
     for (auto& t : th) t.join();
     cudaSetDevice(cur);
     for (int g = 0; g < ng; ++g)
