@@ -465,32 +465,34 @@ def run_gpu(args, lmax):
         # allocations are timed in every such run and both numbers are reported; e2e is the faster one.
         if world > 1 and e2e_alloc["numa_nodes"] > 1 and not os.environ.get("PSB200_BENCH_NO_INTERLEAVE"):
             import ctypes
-            blocks, host_il = [], {}
-            for name, v in outs.items():
-                host_il[name] = []
-                for _ in v:
-                    p = L.psb200_host_alloc(N * N * 8, 1)
-                    if not p:
-                        raise SystemExit("psb200_host_alloc: " + L.psb200_last_error().decode())
-                    blocks.append(p)
-                    host_il[name].append(np.ctypeslib.as_array(ctypes.cast(p, DP), shape=(N, N)))
-            cnt = (ctypes.c_int * 8)()
-            seen = L.psb200_host_placement(blocks[0], cnt, 8)
-            host_calls(host_il, world)
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
+            blocks = []
+            try:                                        # an optional second measurement: it must never cost the line
+                host_il = {}
+                for name, v in outs.items():
+                    host_il[name] = []
+                    for _ in v:
+                        p = L.psb200_host_alloc(N * N * 8, 1)
+                        if not p:
+                            raise RuntimeError("psb200_host_alloc: " + L.psb200_last_error().decode())
+                        blocks.append(p)
+                        host_il[name].append(np.ctypeslib.as_array(ctypes.cast(p, DP), shape=(N, N)))
+                cnt = (ctypes.c_int * 8)()
+                seen = L.psb200_host_placement(blocks[0], cnt, 8)
                 host_calls(host_il, world)
-            wall_il = (time.perf_counter() - t0) * 1e3
-            same = all(np.array_equal(a, b) for name in host_out for a, b in zip(host_out[name], host_il[name]))
-            e2e_alloc.update({"one_node_ms_per_step": wall_e2e / e2e_steps, "interleaved_ms_per_step": wall_il / e2e_steps,
-                              "interleaved_placement_sample": list(cnt)[:e2e_alloc["numa_nodes"]] if seen > 0 else None,
-                              "interleaved_equals_one_node": bool(same)})
-            if not same:
-                raise SystemExit("bench: results in the interleaved arrays differ from the one-node arrays")
-            if wall_il < wall_e2e:
-                wall_e2e = wall_il
-                e2e_alloc["used"] = "page-locked arrays interleaved over the NUMA nodes (psb200_host_alloc policy 1)"
-            del host_il
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    host_calls(host_il, world)
+                wall_il = (time.perf_counter() - t0) * 1e3
+                same = all(np.array_equal(a, b) for name in host_out for a, b in zip(host_out[name], host_il[name]))
+                e2e_alloc.update({"one_node_ms_per_step": wall_e2e / e2e_steps, "interleaved_ms_per_step": wall_il / e2e_steps,
+                                  "interleaved_placement_sample": list(cnt)[:e2e_alloc["numa_nodes"]] if seen > 0 else None,
+                                  "interleaved_equals_one_node": bool(same)})
+                if same and wall_il < wall_e2e:
+                    wall_e2e = wall_il
+                    e2e_alloc["used"] = "page-locked arrays interleaved over the NUMA nodes (psb200_host_alloc policy 1)"
+                del host_il
+            except Exception as exc:                    # reported, not fatal: e2e stays the one-node measurement
+                e2e_alloc["interleaved_error"] = repr(exc)
             for p in blocks:
                 L.psb200_host_free(p)
 
