@@ -1,0 +1,109 @@
+"""Multiprecision known answers for mode-coupling matrix ENTRIES at BASELINE's full sizes (lmax 6143 and 12287).
+
+Independent of oracle/ and of the CUDA path: mpmath at 50 digits, plain forward three-term recurrence in l3 from
+l3 = |l1 - l2| (stable here: for the two families of this path, (0,0,0) and (0,-2,2), all but a few values at either end
+of a family lie in the classical region -- checked below by repeating a sample of the families at 400 digits), the
+normalisation sum (2 l3 + 1) f^2 = 1, the sign rule sgn f(l1 + l2) = (-1)^(l1 - l2), and then the four sums of
+/root/reference/src/modecoupling.jl:3-66 over the window spectrum V taken as exact binary doubles:
+
+    Xi_TT = sum_l3            (2 l3 + 1) f00^2    V[l3] / 4 pi        -> M00 = (2 l2 + 1) Xi_TT      (:78-95)
+    Xi_TE = sum_{l1+l2+l3 even} (2 l3 + 1) f00 f22 V[l3] / 4 pi        -> M02                         (:99-119)
+    Xi_EE = sum_{even}          (2 l3 + 1) f22^2   V[l3] / 4 pi        -> M++                         (:123-139)
+    Xi_EB = sum_{odd}           (2 l3 + 1) f22^2   V[l3] / 4 pi        -> M--                         (:143-159)
+
+with l3 from |l1 - l2| to min(l1 + l2, len(V) - 1).  Stored per entry: the four Xi, and the sums of |terms| (the
+condition of each sum, for the condition-aware bound of tests/conftest.py).  The window spectra are the synthetic
+cross-mask spectra the GPU tests use (powerspectra_jl_b200/synthetic.py, seeds 1001 x 1002), stored verbatim so that
+the fixture does not depend on how numpy rounds on another machine.
+
+    python tests/golden/make_golden_highl.py        # ~3 minutes on 8 cores; writes tests/golden/mcm_entries_mp.npz
+"""
+import os
+import sys
+from multiprocessing import Pool
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+
+def family(mp, l1, l2, m2, m3):
+    """(l3 l1 l2; 0 m2 m3) with m2 + m3 = 0, l3 = |l1-l2| .. l1+l2, as a list of mpf."""
+    d, s = abs(l2 - l1), l1 + l2 + 1
+    a = lambda j: mp.sqrt((mp.mpf(j) ** 2 - d * d) * (mp.mpf(s) ** 2 - mp.mpf(j) ** 2))
+    f, fm = [mp.mpf(1)], mp.mpf(0)
+    for j in range(d, l1 + l2):
+        fn = -((2 * j + 1) * (m3 - m2) * f[-1] + a(j) * fm) / a(j + 1)
+        fm = f[-1]
+        f.append(fn)
+    norm = mp.sqrt(sum((2 * (d + t) + 1) * v * v for t, v in enumerate(f)))
+    sgn = 1 if (f[-1] > 0) == ((l1 - l2) % 2 == 0) else -1
+    return [sgn * v / norm for v in f]
+
+
+def entry(args):
+    l1, l2, V, dps = args
+    import mpmath as mp
+    mp.mp.dps = dps
+    d = abs(l2 - l1)
+    f00, f22 = family(mp, l1, l2, 0, 0), family(mp, l1, l2, -2, 2)
+    last = min(l1 + l2, len(V) - 1)
+    xi = [mp.mpf(0)] * 4
+    sa = [mp.mpf(0)] * 4
+    for l3 in range(d, last + 1):
+        t = l3 - d
+        w = (2 * l3 + 1) * mp.mpf(float(V[l3]))
+        even = (l1 + l2 + l3) % 2 == 0
+        terms = (w * f00[t] ** 2, w * f00[t] * f22[t] if even else 0, w * f22[t] ** 2 if even else 0,
+                 0 if even else w * f22[t] ** 2)
+        for k in range(4):
+            xi[k] += terms[k]
+            sa[k] += abs(terms[k])
+    fourpi = 4 * mp.pi
+    return [float(x / fourpi) for x in xi], [float(x / fourpi) for x in sa]
+
+
+def pairs_for(lmax, n, rng):
+    """l1 <= l2 pairs: near and far from the diagonal, lowest spin-2 rows, last rows, edges of 8-way bands."""
+    P = {(2, 2), (2, lmax), (3, lmax - 1), (lmax, lmax), (lmax - 1, lmax), (lmax // 2, lmax // 2), (lmax // 2, lmax),
+         (2, lmax // 2 + 1), (17, 18), (lmax // 3, 2 * lmax // 3 + 1)}
+    while len(P) < n:
+        l1 = int(rng.integers(2, lmax + 1))
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            l2 = min(lmax, l1 + int(rng.integers(0, 40)))           # near the diagonal
+        elif kind == 1:
+            l2 = int(rng.integers(l1, lmax + 1))                    # anywhere right of it
+        else:
+            l1 = int(rng.integers(2, 200))                          # short families against a far column
+            l2 = int(rng.integers(lmax // 2, lmax + 1))
+        P.add((l1, l2))
+    return sorted(P)
+
+
+def main():
+    from powerspectra_jl_b200 import synthetic as syn
+    rng = np.random.default_rng(20261017)
+    out = {}
+    with Pool(min(8, os.cpu_count() or 1)) as pool:
+        for lmax, n in ((6143, 96), (12287, 48)):
+            V = np.ascontiguousarray(syn.mask_spectra(lmax, seeds=(1001, 1002))[(0, 1)])
+            P = pairs_for(lmax, n, rng)
+            res = pool.map(entry, [(l1, l2, V, 50) for l1, l2 in P], chunksize=2)
+            xi = np.array([r[0] for r in res])
+            sabs = np.array([r[1] for r in res])
+            # the recurrence is run again at 400 digits for every eighth entry: the 50-digit values must not move
+            chk = pool.map(entry, [(l1, l2, V, 400) for l1, l2 in P[::8]], chunksize=1)
+            dev = max(abs(a - b) / max(abs(b), 1e-300) for r, q in zip(res[::8], chk) for a, b in zip(r[0], q[0]))
+            assert dev < 1e-14, dev
+            out[f"V_{lmax}"] = V
+            out[f"pairs_{lmax}"] = np.array(P, dtype=np.int32)
+            out[f"xi_{lmax}"] = xi          # columns: Xi_TT, Xi_TE, Xi_EE, Xi_EB
+            out[f"sabs_{lmax}"] = sabs
+            print(lmax, len(P), "entries; 50 vs 400 digits:", dev, flush=True)
+    np.savez_compressed(os.path.join(HERE, "mcm_entries_mp.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

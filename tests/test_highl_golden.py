@@ -1,0 +1,98 @@
+"""Mode-coupling matrix entries at BASELINE's full sizes (lmax 6143, 12287) against multiprecision known answers.
+
+tests/golden/mcm_entries_mp.npz (made by tests/golden/make_golden_highl.py) holds, for 96 + 48 (l1, l2) pairs -- near and
+far from the diagonal, lowest spin-2 rows, last rows -- the four sums Xi_TT / Xi_TE / Xi_EE / Xi_EB of
+/root/reference/src/modecoupling.jl:3-66 evaluated with mpmath at 50 digits by a plain forward recurrence: no code of
+oracle/ and none of the CUDA path is involved.  The CPU tests hold the oracle (both instantiations) to them, the GPU
+tests the library; both triangles M[l1,l2] = (2 l2 + 1) Xi, M[l2,l1] = (2 l1 + 1) Xi (:90-91).
+
+Criterion: the north-star 1e-10 relative on every entry whose l3 sum does not cancel by more than 1e3, and the
+condition-aware bound 1e-10 |ref| + 1e-13 S_abs of tests/conftest.py on all of them.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, RTOL, TAU
+
+KIND_COL = {0: 0, 1: 1, 2: 2, 3: 3}           # psb200_mcm kind -> column of xi / sabs
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "mcm_entries_mp.npz"))
+
+
+def _check(get, gold, lmax, kinds, label):
+    """get(kind) -> N x N matrix (or a callable (i, j) -> value); every golden entry, both triangles."""
+    P, XI, SA = gold[f"pairs_{lmax}"], gold[f"xi_{lmax}"], gold[f"sabs_{lmax}"]
+    worst_strict, worst_bound, nstrict = 0.0, 0.0, 0
+    for kind in kinds:
+        M = get(kind)
+        c = KIND_COL[kind]
+        for (l1, l2), xi, sa in zip(P, XI[:, c], SA[:, c]):
+            for (i, j) in ((l1, l2), (l2, l1)):
+                ref, cond = (2 * j + 1) * xi, (2 * j + 1) * sa
+                err = abs(M[i, j] - ref)
+                worst_bound = max(worst_bound, err / (RTOL * abs(ref) + TAU * cond))
+                if cond <= 1e3 * abs(ref):
+                    worst_strict = max(worst_strict, err / abs(ref))
+                    nstrict += 1
+    assert worst_bound <= 1.0, (label, lmax, worst_bound)
+    assert worst_strict < RTOL, (label, lmax, worst_strict)
+    assert nstrict > len(P)                    # the strict criterion applies to most entries
+    return worst_strict, worst_bound
+
+
+def test_golden_file_is_self_consistent(gold):
+    """Completeness of the two families over a flat window would need len(V) > 2 lmax; what the file itself allows:
+    |Xi| <= S_abs, Xi_TT's terms are non-negative only if V is (it is not: cross-mask spectrum), Xi_EE + Xi_EB and
+    Xi_TT share the bound sum (2 l3 + 1) f^2 |V| / 4 pi <= max|V| / 4 pi."""
+    for lmax in (6143, 12287):
+        P, XI, SA, V = gold[f"pairs_{lmax}"], gold[f"xi_{lmax}"], gold[f"sabs_{lmax}"], gold[f"V_{lmax}"]
+        assert V.size == lmax + 1 and P.shape[1] == 2 and XI.shape == SA.shape == (len(P), 4)
+        assert (P[:, 0] <= P[:, 1]).all() and P.min() >= 2 and P.max() == lmax
+        assert (np.abs(XI) <= SA * (1 + 1e-12)).all()
+        vmax = np.abs(V).max() / (4 * np.pi)
+        assert (SA[:, 0] <= vmax * (1 + 1e-12)).all() and (SA[:, 2] + SA[:, 3] <= vmax * (1 + 1e-12)).all()
+
+
+@pytest.mark.parametrize("ld", [False, True])
+def test_oracle_entries_lmax6143(oracle, gold, ld):
+    lmax = 6143
+    rows = np.unique(gold[f"pairs_{lmax}"][:, 0])
+    V = gold[f"V_{lmax}"]
+    _check(lambda kind: oracle.mcm(kind, 0, lmax, V, ld=ld, rows=rows), gold, lmax, (0, 1, 2, 3), f"oracle ld={ld}")
+
+
+def test_oracle_entries_lmax12287(oracle, gold):
+    lmax = 12287
+    rows = np.unique(gold[f"pairs_{lmax}"][:, 0])
+    V = gold[f"V_{lmax}"]
+    _check(lambda kind: oracle.mcm(kind, 0, lmax, V, ld=True, rows=rows), gold, lmax, (0, 3), "oracle ld")
+
+
+@pytest.mark.gpu
+def test_gpu_entries_lmax6143(ps, gold):
+    lmax = 6143
+    V = ps.SpectralVector(gold[f"V_{lmax}"])
+    ee_bb = ps.mcm("EE_BB", V)
+    mats = {0: ps.mcm("TT", V).parent, 1: ps.mcm("TE", V).parent,
+            2: ee_bb.getblock(0, 0).parent, 3: ee_bb.getblock(0, 1).parent}
+    ws, wb = _check(mats.__getitem__, gold, lmax, (0, 1, 2, 3), "gpu")
+    print(f"gpu vs 50-digit entries, lmax {lmax}: strict max {ws:.2e}, err/bound max {wb:.3f}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kinds", [(0,), (2, 3)])
+def test_gpu_entries_lmax12287(ps, gold, kinds):
+    lmax = 12287
+    V = ps.SpectralVector(gold[f"V_{lmax}"])
+    if kinds == (0,):
+        mats = {0: ps.mcm("TT", V).parent}
+    else:
+        ee_bb = ps.mcm("EE_BB", V)
+        mats = {2: ee_bb.getblock(0, 0).parent, 3: ee_bb.getblock(0, 1).parent}
+    ws, wb = _check(mats.__getitem__, gold, lmax, kinds, "gpu")
+    print(f"gpu vs 50-digit entries, lmax {lmax}, kinds {kinds}: strict max {ws:.2e}, err/bound max {wb:.3f}")
