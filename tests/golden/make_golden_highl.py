@@ -16,7 +16,12 @@ condition of each sum, for the condition-aware bound of tests/conftest.py).  The
 cross-mask spectra the GPU tests use (powerspectra_jl_b200/synthetic.py, seeds 1001 x 1002), stored verbatim so that
 the fixture does not depend on how numpy rounds on another machine.
 
-    python tests/golden/make_golden_highl.py        # ~3 minutes on 8 cores; writes tests/golden/mcm_entries_mp.npz
+The same families give known answers for the three covariance blocks of the benchmark step at lmax 6143 -- TTTT, EEEE,
+TETE, /root/reference/src/covariance.jl:92-122, :153-183, :261-302 -- over inputs built from exactly rounded
+arithmetic only (tests/highl_inputs.py; the fixture stores their digest, not the vectors): 32 entries per block, with
+the condition sum  S_abs = sum_k |coefficient_k| sum_l3 |term|.
+
+    python tests/golden/make_golden_highl.py        # ~2 minutes on 8 cores; writes mcm_entries_mp.npz, cov_entries_mp.npz
 """
 import os
 import sys
@@ -64,6 +69,58 @@ def entry(args):
     return [float(x / fourpi) for x in xi], [float(x / fourpi) for x in sa]
 
 
+def cov_entry(args):
+    """TTTT, EEEE, TETE at one (l1, l2): value and condition sum of each, formulas as in the reference."""
+    l1, l2, inputs, dps = args
+    import mpmath as mp
+    mp.mp.dps = dps
+    d = abs(l2 - l1)
+    f00, f22 = family(mp, l1, l2, 0, 0), family(mp, l1, l2, -2, 2)
+    fourpi = 4 * mp.pi
+    F = lambda x, l: mp.mpf(float(x[l]))
+
+    def xi(W, w, parity):
+        """(sum, sum of |terms|) of (2 l3 + 1) w(l3) W[l3] / 4 pi; parity None = every l3, 0 = l1+l2+l3 even."""
+        s = a = mp.mpf(0)
+        for l3 in range(d, min(l1 + l2, len(W) - 1) + 1):
+            if parity is not None and (l1 + l2 + l3) % 2 != parity:
+                continue
+            t = (2 * l3 + 1) * w[l3 - d] * mp.mpf(float(W[l3]))
+            s += t
+            a += abs(t)
+        return s / fourpi, a / fourpi
+
+    w00 = [v * v for v in f00]
+    w22 = [v * v for v in f22]
+    w02 = [u * v for u, v in zip(f00, f22)]
+    out = {}
+    for name, w, par in (("TTTT", w00, None), ("EEEE", w22, 0)):
+        (sp, rt, W) = inputs[name]
+        ip, jq, iq, jp = sp
+        r_ip, r_jq, r_iq, r_jp = rt
+        X = [xi(Wk, w, par) for Wk in W]
+        coef = [mp.sqrt(F(ip, l1) * F(ip, l2) * F(jq, l1) * F(jq, l2)),
+                mp.sqrt(F(iq, l1) * F(iq, l2) * F(jp, l1) * F(jp, l2)),
+                mp.sqrt(F(ip, l1) * F(ip, l2)) * F(r_jq, l1) * F(r_jq, l2),
+                mp.sqrt(F(jq, l1) * F(jq, l2)) * F(r_ip, l1) * F(r_ip, l2),
+                mp.sqrt(F(iq, l1) * F(iq, l2)) * F(r_jp, l1) * F(r_jp, l2),
+                mp.sqrt(F(jp, l1) * F(jp, l2)) * F(r_iq, l1) * F(r_iq, l2),
+                F(r_ip, l1) * F(r_jq, l1) * F(r_ip, l2) * F(r_jq, l2),
+                F(r_iq, l1) * F(r_jp, l1) * F(r_iq, l2) * F(r_jp, l2)]
+        out[name] = (float(sum(c * x[0] for c, x in zip(coef, X))), float(sum(abs(c) * x[1] for c, x in zip(coef, X))))
+    (sp, rt, W) = inputs["TETE"]
+    TTip, EEjq, TEiq, TEjp = sp
+    rT, rP = rt
+    X = [xi(W[0], w02, 0), xi(W[1], w00, None), xi(W[2], w02, 0), xi(W[3], w02, 0), xi(W[4], w02, 0)]
+    coef = [mp.sqrt(F(TTip, l1) * F(TTip, l2) * F(EEjq, l1) * F(EEjq, l2)),
+            (F(TEiq, l1) * F(TEjp, l2) + F(TEjp, l1) * F(TEiq, l2)) / 2,
+            mp.sqrt(F(TTip, l1) * F(TTip, l2)) * F(rP, l1) * F(rP, l2),
+            mp.sqrt(F(EEjq, l1) * F(EEjq, l2)) * F(rT, l1) * F(rT, l2),
+            F(rT, l1) * F(rT, l2) * F(rP, l1) * F(rP, l2)]
+    out["TETE"] = (float(sum(c * x[0] for c, x in zip(coef, X))), float(sum(abs(c) * x[1] for c, x in zip(coef, X))))
+    return out
+
+
 def pairs_for(lmax, n, rng):
     """l1 <= l2 pairs: near and far from the diagonal, lowest spin-2 rows, last rows, edges of 8-way bands."""
     P = {(2, 2), (2, lmax), (3, lmax - 1), (lmax, lmax), (lmax - 1, lmax), (lmax // 2, lmax // 2), (lmax // 2, lmax),
@@ -103,6 +160,23 @@ def main():
             out[f"sabs_{lmax}"] = sabs
             print(lmax, len(P), "entries; 50 vs 400 digits:", dev, flush=True)
     np.savez_compressed(os.path.join(HERE, "mcm_entries_mp.npz"), **out)
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    import highl_inputs
+    lmax = 6143
+    inputs = highl_inputs.cov_inputs(lmax)
+    P = pairs_for(lmax, 32, rng)
+    with Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(cov_entry, [(l1, l2, inputs, 50) for l1, l2 in P], chunksize=1)
+        chk = pool.map(cov_entry, [(l1, l2, inputs, 400) for l1, l2 in P[::8]], chunksize=1)
+    dev = max(abs(r[b][0] - q[b][0]) / abs(q[b][0]) for r, q in zip(res[::8], chk) for b in r)
+    assert dev < 1e-14, dev
+    cov = {"pairs": np.array(P, dtype=np.int32), "lmax": np.int32(lmax), "inputs_sha256": np.array(highl_inputs.digest(inputs))}
+    for b in ("TTTT", "EEEE", "TETE"):
+        cov[b] = np.array([r[b][0] for r in res])
+        cov[b + "_sabs"] = np.array([r[b][1] for r in res])
+    np.savez_compressed(os.path.join(HERE, "cov_entries_mp.npz"), **cov)
+    print("cov", len(P), "entries per block; 50 vs 400 digits:", dev, flush=True)
 
 
 if __name__ == "__main__":

@@ -1,10 +1,14 @@
-"""Mode-coupling matrix entries at BASELINE's full sizes (lmax 6143, 12287) against multiprecision known answers.
+"""Mode-coupling matrix and covariance entries at BASELINE's full sizes (lmax 6143, 12287) against multiprecision known
+answers.
 
 tests/golden/mcm_entries_mp.npz (made by tests/golden/make_golden_highl.py) holds, for 96 + 48 (l1, l2) pairs -- near and
 far from the diagonal, lowest spin-2 rows, last rows -- the four sums Xi_TT / Xi_TE / Xi_EE / Xi_EB of
 /root/reference/src/modecoupling.jl:3-66 evaluated with mpmath at 50 digits by a plain forward recurrence: no code of
 oracle/ and none of the CUDA path is involved.  The CPU tests hold the oracle (both instantiations) to them, the GPU
 tests the library; both triangles M[l1,l2] = (2 l2 + 1) Xi, M[l2,l1] = (2 l1 + 1) Xi (:90-91).
+
+tests/golden/cov_entries_mp.npz: the same for 32 entries of each covariance block of the benchmark step (TTTT, EEEE,
+TETE at lmax 6143; src/covariance.jl:92-122, :153-183, :261-302) over the inputs of tests/highl_inputs.py.
 
 Criterion: the north-star 1e-10 relative on every entry whose l3 sum does not cancel by more than 1e3, and the
 condition-aware bound 1e-10 |ref| + 1e-13 S_abs of tests/conftest.py on all of them.
@@ -96,3 +100,55 @@ def test_gpu_entries_lmax12287(ps, gold, kinds):
         mats = {2: ee_bb.getblock(0, 0).parent, 3: ee_bb.getblock(0, 1).parent}
     ws, wb = _check(mats.__getitem__, gold, lmax, kinds, "gpu")
     print(f"gpu vs 50-digit entries, lmax {lmax}, kinds {kinds}: strict max {ws:.2e}, err/bound max {wb:.3f}")
+
+
+# ---- covariance blocks of the benchmark step at lmax 6143 (cov_entries_mp.npz) ----------------------------------
+
+@pytest.fixture(scope="module")
+def cov_gold():
+    import highl_inputs
+    g = np.load(os.path.join(GOLDEN, "cov_entries_mp.npz"))
+    inputs = highl_inputs.cov_inputs(int(g["lmax"]))
+    assert highl_inputs.digest(inputs) == str(g["inputs_sha256"]), "tests/highl_inputs.py no longer makes the vectors of the fixture"
+    return g, inputs
+
+
+def _check_cov(get, g, label):
+    worst_strict, worst_bound, nstrict = 0.0, 0.0, 0
+    for block in ("TTTT", "EEEE", "TETE"):
+        Cm = get(block)
+        for (l1, l2), ref, cond in zip(g["pairs"], g[block], g[block + "_sabs"]):
+            assert Cm[l1, l2] == Cm[l2, l1]                       # symmetric by copy (src/covariance.jl:119)
+            err = abs(Cm[l1, l2] - ref)
+            worst_bound = max(worst_bound, err / (RTOL * abs(ref) + TAU * cond))
+            if cond <= 1e3 * abs(ref):
+                worst_strict = max(worst_strict, err / abs(ref))
+                nstrict += 1
+    assert worst_bound <= 1.0, (label, worst_bound)
+    assert worst_strict < RTOL, (label, worst_strict)
+    assert nstrict >= 2 * len(g["pairs"])
+    return worst_strict, worst_bound
+
+
+@pytest.mark.parametrize("ld", [False, True])
+def test_oracle_cov_entries_lmax6143(oracle, cov_gold, ld):
+    g, inputs = cov_gold
+    lmax = int(g["lmax"])
+    rows = np.unique(g["pairs"][:, 0])
+    ws, wb = _check_cov(lambda b: oracle.cov(b, 0, lmax, *inputs[b], ld=ld, rows=rows), g, f"oracle ld={ld}")
+    print(f"oracle ld={ld} vs 50-digit covariance entries: strict max {ws:.2e}, err/bound max {wb:.4f}")
+
+
+@pytest.mark.gpu
+def test_gpu_cov_entries_lmax6143(ps, cov_gold):
+    g, inputs = cov_gold
+    lmax = int(g["lmax"])
+    loops = {"TTTT": ps.loop_covTTTT, "EEEE": ps.loop_covEEEE, "TETE": ps.loop_covTETE}
+
+    def get(block):
+        sp, rt, W = inputs[block]
+        Cm = ps.spectralzeros(range(0, lmax + 1), range(0, lmax + 1))
+        loops[block](Cm, *[ps.SpectralVector(x) for x in sp], *[ps.SpectralVector(x) for x in rt], *[ps.SpectralVector(x) for x in W])
+        return Cm.parent
+    ws, wb = _check_cov(get, g, "gpu")
+    print(f"gpu vs 50-digit covariance entries, lmax {lmax}: strict max {ws:.2e}, err/bound max {wb:.3f}")
