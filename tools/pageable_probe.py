@@ -1,5 +1,5 @@
 """Host calls into PAGEABLE result arrays: the library's staged delivery against the CUDA runtime's bounce copies, over
-worker counts and chunk sizes (no torch: starts in seconds).  python tools/pageable_probe.py [lmax]"""
+worker counts and chunk sizes (no torch: starts in seconds).  python tools/pageable_probe.py [lmax] [ngpus] [quick]"""
 import ctypes, json, os, sys, time
 
 import numpy as np
@@ -9,6 +9,8 @@ import powerspectra_jl_b200 as ps
 from powerspectra_jl_b200 import synthetic as syn
 
 lmax = int(sys.argv[1]) if len(sys.argv) > 1 else 6143
+NG = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+QUICK = len(sys.argv) > 3
 N = lmax + 1
 L, DP = ps.lib(), ps._lib.DP
 V = np.ascontiguousarray(syn.mask_spectra(lmax, seeds=(1001, 1002))[(0, 1)])
@@ -21,20 +23,20 @@ def call(kind, X, Y, reps=4):
     for _ in range(reps):
         t0 = time.perf_counter()
         ps._lib.check(L.psb200_mcm(kind, 0, lmax, V.ctypes.data_as(DP), V.size, X.ctypes.data_as(DP), N,
-                                   Y.ctypes.data_as(DP) if kind == 4 else None, 1))
+                                   Y.ctypes.data_as(DP) if kind == 4 else None, NG))
         best = min(best, (time.perf_counter() - t0) * 1e3)
     return best
 
 
 for kind in (0, 4):
     call(kind, HA.array, HB.array, 1)
-    row = {"lmax": lmax, "kind": kind, "page_locked_ms": call(kind, HA.array, HB.array)}
+    row = {"lmax": lmax, "ngpus": NG, "kind": kind, "page_locked_ms": call(kind, HA.array, HB.array)}
     refA, refB = HA.array.copy(), HB.array.copy()
     os.environ["PSB200_STAGED"] = "0"
     row["runtime_bounce_ms"] = call(kind, A, B)
     os.environ["PSB200_STAGED"] = "1"
-    for nt in (0, 1):
-        for thr in (2, 4, 8, 12, 15):
+    for nt in ((1,) if QUICK else (0, 1)):
+        for thr in ((4, 8) if QUICK else (2, 4, 8, 12, 15)):
             for mb in (4, 8, 16) if thr == 12 else (8,):
                 os.environ["PSB200_STAGE_THREADS"], os.environ["PSB200_STAGE_CHUNK_MB"] = str(thr), str(mb)
                 os.environ["PSB200_STAGE_NT"] = str(nt)
