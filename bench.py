@@ -523,6 +523,30 @@ def run_gpu(args, lmax):
             if pageable.get("staged_equals_page_locked") is False or pageable.get("runtime_bounce_equals_page_locked") is False:
                 raise SystemExit(f"bench: results in pageable arrays differ from the page-locked ones: {pageable}")
 
+        # ---- the TT matrix of this very step against multiprecision known answers (tests/golden/mcm_entries_mp.npz: 96
+        # entries at lmax 6143 computed with mpmath at 50 digits, independent of oracle/ and of the library) ----
+        known = None
+        try:
+            gpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "mcm_entries_mp.npz")
+            if lmax == 6143 and os.path.exists(gpath):
+                g = np.load(gpath)
+                if np.array_equal(g["V_6143"], inp["M00"]["V"]):
+                    A = host_out["M00"][0]                       # A[l2, l1] = M[l1, l2] (column-major result in a C-ordered array)
+                    worst, n = 0.0, 0
+                    for (l1, l2), xi, sa in zip(g["pairs_6143"], g["xi_6143"][:, 0], g["sabs_6143"][:, 0]):
+                        for i, j in ((l1, l2), (l2, l1)):
+                            if (2 * j + 1) * sa <= 1e3 * abs((2 * j + 1) * xi):      # sums that do not cancel: strict criterion
+                                worst = max(worst, abs(A[j, i] - (2 * j + 1) * xi) / abs((2 * j + 1) * xi))
+                                n += 1
+                    known = {"matrix": "M00 of the e2e host call", "entries": n, "strict_max_rel": worst, "north_star": 1e-10,
+                             "reference": "mpmath, 50 digits (tests/golden/make_golden_highl.py)"}
+                else:
+                    known = {"skipped": "this host's numpy rounds the synthetic window spectrum differently from the fixture"}
+        except Exception as exc:
+            known = {"error": repr(exc)}
+        if known and known.get("strict_max_rel", 0.0) > 1e-10:
+            raise SystemExit(f"bench: the TT matrix misses the multiprecision known answers: {known}")
+
         # ---- the outputs themselves: N-GPU host call == 1-GPU host call == NCCL-gather driver, bit for bit ----
         # (every (l1,l2) pair is computed independently of the banding, src/modecoupling.jl:84-92, so any difference
         # is a bug in the band delivery / gather / finish plumbing)
@@ -631,6 +655,7 @@ def run_gpu(args, lmax):
                                          "output bytes (151 MB), part of which is still in L2 at kernel end",
                          "all_kernels": kern},
             "multi_gpu_check": check,
+            "known_answers": known,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
