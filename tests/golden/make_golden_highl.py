@@ -16,8 +16,9 @@ condition of each sum, for the condition-aware bound of tests/conftest.py).  The
 cross-mask spectra the GPU tests use (powerspectra_jl_b200/synthetic.py, seeds 1001 x 1002), stored verbatim so that
 the fixture does not depend on how numpy rounds on another machine.
 
-The same families give known answers for the three covariance blocks of the benchmark step at lmax 6143 -- TTTT, EEEE,
-TETE, /root/reference/src/covariance.jl:92-122, :153-183, :261-302 -- over inputs built from exactly rounded
+The same families give known answers for all seven covariance blocks at lmax 6143 -- TTTT, EEEE, TETE (the benchmark
+step), TTTE, TEEE_planck, TEEE, TTEE; /root/reference/src/covariance.jl:92-122, :153-183, :261-302, :208-235, :376-402,
+:337-372, :422-446 -- over inputs built from exactly rounded
 arithmetic only (tests/highl_inputs.py; the fixture stores their digest, not the vectors): 32 entries per block, with
 the condition sum  S_abs = sum_k |coefficient_k| sum_l3 |term|.
 
@@ -118,6 +119,26 @@ def cov_entry(args):
             mp.sqrt(F(EEjq, l1) * F(EEjq, l2)) * F(rT, l1) * F(rT, l2),
             F(rT, l1) * F(rT, l2) * F(rP, l1) * F(rP, l2)]
     out["TETE"] = (float(sum(c * x[0] for c, x in zip(coef, X))), float(sum(abs(c) * x[1] for c, x in zip(coef, X))))
+
+    # TTTE (:208-235, f00^2, every l3), TEEE_planck (:376-402, f22^2, even), TEEE (:337-372, f00 f22, even): one shape
+    for name, w, par in (("TTTE", w00, None), ("TEEE_planck", w22, 0), ("TEEE", w02, 0)):
+        (sp, rt, W) = inputs[name]
+        a, b, c1, c2 = sp                       # TTTE: TTip TTjp TEiq TEjq;  TEEE*: EEjq EEjp TEip TEiq
+        ra, rb = rt
+        X = [xi(Wk, w, par) for Wk in W]
+        if name == "TTTE":
+            s1, s2 = F(c2, l1) + F(c2, l2), F(c1, l1) + F(c1, l2)        # (TEjq1 + TEjq2), (TEiq1 + TEiq2)
+        else:
+            s1, s2 = F(c1, l1) + F(c1, l2), F(c2, l1) + F(c2, l2)        # (TEip1 + TEip2), (TEiq1 + TEiq2)
+        coef = [mp.sqrt(F(a, l1) * F(a, l2)) * s1 / 2, mp.sqrt(F(b, l1) * F(b, l2)) * s2 / 2,
+                s1 * F(ra, l1) * F(ra, l2) / 2, s2 * F(rb, l1) * F(rb, l2) / 2]
+        out[name] = (float(sum(c * x[0] for c, x in zip(coef, X))), float(sum(abs(c) * x[1] for c, x in zip(coef, X))))
+    # TTEE (:422-446, f00^2, every l3)
+    (sp, rt, W) = inputs["TTEE"]
+    TEip, TEiq, TEjq, TEjp = sp
+    X = [xi(W[0], w00, None), xi(W[1], w00, None)]
+    coef = [(F(TEip, l1) * F(TEjq, l2) + F(TEjq, l1) * F(TEip, l2)) / 2, (F(TEiq, l1) * F(TEjp, l2) + F(TEjp, l1) * F(TEiq, l2)) / 2]
+    out["TTEE"] = (float(sum(c * x[0] for c, x in zip(coef, X))), float(sum(abs(c) * x[1] for c, x in zip(coef, X))))
     return out
 
 
@@ -172,7 +193,7 @@ def main():
     dev = max(abs(r[b][0] - q[b][0]) / abs(q[b][0]) for r, q in zip(res[::8], chk) for b in r)
     assert dev < 1e-14, dev
     cov = {"pairs": np.array(P, dtype=np.int32), "lmax": np.int32(lmax), "inputs_sha256": np.array(highl_inputs.digest(inputs))}
-    for b in ("TTTT", "EEEE", "TETE"):
+    for b in ("TTTT", "EEEE", "TETE", "TTTE", "TEEE_planck", "TEEE", "TTEE"):
         cov[b] = np.array([r[b][0] for r in res])
         cov[b + "_sabs"] = np.array([r[b][1] for r in res])
     np.savez_compressed(os.path.join(HERE, "cov_entries_mp.npz"), **cov)

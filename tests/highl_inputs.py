@@ -18,6 +18,10 @@ def cov_inputs(lmax):
         "TTTT": (tt, r, W),
         "EEEE": (ee, r, W),
         "TETE": ([tt[0], ee[1], te[2], te[3]], [r[0], r[1]], W[:5]),
+        "TTTE": ([tt[0], tt[3], te[2], te[1]], [r[0], r[3]], W[:4]),
+        "TEEE_planck": ([ee[1], ee[3], te[0], te[2]], [r[1], r[3]], W[:4]),
+        "TEEE": ([ee[1], ee[3], te[0], te[2]], [r[1], r[3]], W[:4]),
+        "TTEE": ([te[0], te[2], te[1], te[3]], [], W[:2]),
     }
     return {k: tuple([np.ascontiguousarray(x) for x in part] for part in v) for k, v in blocks.items()}
 

@@ -7,8 +7,8 @@ far from the diagonal, lowest spin-2 rows, last rows -- the four sums Xi_TT / Xi
 oracle/ and none of the CUDA path is involved.  The CPU tests hold the oracle (both instantiations) to them, the GPU
 tests the library; both triangles M[l1,l2] = (2 l2 + 1) Xi, M[l2,l1] = (2 l1 + 1) Xi (:90-91).
 
-tests/golden/cov_entries_mp.npz: the same for 32 entries of each covariance block of the benchmark step (TTTT, EEEE,
-TETE at lmax 6143; src/covariance.jl:92-122, :153-183, :261-302) over the inputs of tests/highl_inputs.py.
+tests/golden/cov_entries_mp.npz: the same for 32 entries of each of the seven covariance blocks at lmax 6143
+(src/covariance.jl:92-446) over the inputs of tests/highl_inputs.py.
 
 Criterion: the north-star 1e-10 relative on every entry whose l3 sum does not cancel by more than 1e3, and the
 condition-aware bound 1e-10 |ref| + 1e-13 S_abs of tests/conftest.py on all of them.
@@ -113,9 +113,12 @@ def cov_gold():
     return g, inputs
 
 
+BLOCKS = ("TTTT", "EEEE", "TETE", "TTTE", "TEEE_planck", "TEEE", "TTEE")
+
+
 def _check_cov(get, g, label):
     worst_strict, worst_bound, nstrict = 0.0, 0.0, 0
-    for block in ("TTTT", "EEEE", "TETE"):
+    for block in BLOCKS:
         Cm = get(block)
         for (l1, l2), ref, cond in zip(g["pairs"], g[block], g[block + "_sabs"]):
             assert Cm[l1, l2] == Cm[l2, l1]                       # symmetric by copy (src/covariance.jl:119)
@@ -143,7 +146,8 @@ def test_oracle_cov_entries_lmax6143(oracle, cov_gold, ld):
 def test_gpu_cov_entries_lmax6143(ps, cov_gold):
     g, inputs = cov_gold
     lmax = int(g["lmax"])
-    loops = {"TTTT": ps.loop_covTTTT, "EEEE": ps.loop_covEEEE, "TETE": ps.loop_covTETE}
+    loops = {"TTTT": ps.loop_covTTTT, "EEEE": ps.loop_covEEEE, "TETE": ps.loop_covTETE, "TTTE": ps.loop_covTTTE,
+             "TEEE_planck": ps.loop_covTEEE_planck, "TEEE": ps.loop_covTEEE, "TTEE": ps.loop_covTTEE}
 
     def get(block):
         sp, rt, W = inputs[block]
