@@ -41,7 +41,8 @@ std::vector<std::pair<int, std::vector<int>>> numa_nodes_with_cpus()
         fclose(f);
         if (!got) continue;
         std::vector<int> cpus;
-        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        char* save = nullptr;
+        for (char* tok = strtok_r(line, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
             int a = 0, b = 0;
             const int n = sscanf(tok, "%d-%d", &a, &b);
             if (n == 1) b = a;
