@@ -142,6 +142,56 @@ def cov_entry(args):
     return out
 
 
+def general_family(mp, j2, j3, m2, m3):
+    """(j j2 j3; -(m2+m3) m2 m3), j = max(|j2-j3|, |m2+m3|) .. j2+j3: Schulten-Gordon three-term recurrence upwards from
+    the first j, normalised and signed as WignerFamilies does.  Returns (first j, values)."""
+    m1 = -(m2 + m3)
+    if m1 == 0:
+        return abs(j2 - j3), family(mp, j2, j3, m2, m3)
+    jmin, jmax = max(abs(j2 - j3), abs(m1)), j2 + j3
+    A = lambda j: mp.sqrt((mp.mpf(j) ** 2 - (j2 - j3) ** 2) * ((j2 + j3 + 1) ** 2 - mp.mpf(j) ** 2) * (mp.mpf(j) ** 2 - m1 * m1))
+    B = lambda j: -(2 * j + 1) * (j2 * (j2 + 1) * m1 - j3 * (j3 + 1) * m1 - j * (j + 1) * (m3 - m2))
+    f = [mp.mpf(1)]
+    if jmax > jmin:
+        f.append(-B(jmin) * f[0] / (jmin * A(jmin + 1)))            # A(jmin) = 0
+    for j in range(jmin + 1, jmax):
+        f.append(-(B(j) * f[-1] + (j + 1) * A(j) * f[-2]) / (j * A(j + 1)))
+    norm = mp.sqrt(sum((2 * (jmin + t) + 1) * v * v for t, v in enumerate(f)))
+    sgn = 1 if (f[-1] > 0) == ((j2 - j3 - m1) % 2 == 0) else -1
+    return jmin, [sgn * v / norm for v in f]
+
+
+def quickpol_entry(args):
+    """Xi[l'', l] of quickpolXi! (/root/reference/src/beam.jl:72-101, Xisum :17-28) and the sum of |terms|."""
+    lpp, l, nu1, nu2, s1, s2, W, dps = args
+    import mpmath as mp
+    mp.mp.dps = dps
+    if abs(s1) > l or abs(s2) > l or abs(nu1) > lpp or abs(nu2) > lpp:
+        return 0.0, 0.0                   # a projection larger than its angular momentum: the symbol is 0
+    a1, f1 = general_family(mp, l, lpp, -s1, -nu1)
+    a2, f2 = general_family(mp, l, lpp, -s2, -nu2)
+    lo, hi = max(a1, a2), min(l + lpp, len(W) - 1)
+    s = a = mp.mpf(0)
+    for lp in range(lo, hi + 1):
+        t = mp.mpf(float(W[lp])) * f1[lp - a1] * f2[lp - a2]
+        s += t
+        a += abs(t)
+    sgn = -1 if (s1 + s2 + nu1 + nu2) % 2 else 1
+    return float(sgn * s), float(a)
+
+
+def check_general_family_against_sympy():
+    import mpmath as mp
+    from sympy import N
+    from sympy.physics.wigner import wigner_3j
+    mp.mp.dps = 50
+    for (j2, j3, m2, m3) in [(7, 9, -2, -3), (12, 12, 2, 2), (30, 25, -4, 1), (9, 40, 2, -12), (5, 5, 0, 0), (6, 8, -2, 2)]:
+        jmin, f = general_family(mp, j2, j3, m2, m3)
+        for t, v in enumerate(f):
+            exact = N(wigner_3j(jmin + t, j2, j3, -(m2 + m3), m2, m3), 40)
+            assert abs(float(v) - float(exact)) < 1e-15, (j2, j3, m2, m3, jmin + t, float(v), float(exact))
+
+
 def pairs_for(lmax, n, rng):
     """l1 <= l2 pairs: near and far from the diagonal, lowest spin-2 rows, last rows, edges of 8-way bands."""
     P = {(2, 2), (2, lmax), (3, lmax - 1), (lmax, lmax), (lmax - 1, lmax), (lmax // 2, lmax // 2), (lmax // 2, lmax),
@@ -198,6 +248,30 @@ def main():
         cov[b + "_sabs"] = np.array([r[b][1] for r in res])
     np.savez_compressed(os.path.join(HERE, "cov_entries_mp.npz"), **cov)
     print("cov", len(P), "entries per block; 50 vs 400 digits:", dev, flush=True)
+
+    # QuickPol Xi: lmax 6143, band +-128, window of lmax + 1 entries, four spin cases
+    check_general_family_against_sympy()
+    band = 128
+    W = highl_inputs.quickpol_window(lmax)
+    cases = [(2, -2, 2, 2), (0, 0, 0, 0), (1, 3, -2, 2), (-12, 5, 4, -3)]          # (nu1, nu2, s1, s2)
+    ent = {(2, 2), (2, 2 + band), (lmax, lmax), (lmax, lmax - band), (lmax - band, lmax), (13, 14), (lmax // 2, lmax // 2 + 7)}
+    while len(ent) < 24:
+        lpp = int(rng.integers(2, lmax + 1))
+        l = int(rng.integers(max(2, lpp - band), min(lmax, lpp + band) + 1))
+        ent.add((lpp, l))
+    ent = sorted(ent)
+    jobs = [(lpp, l, *c, W, 60) for c in cases for (lpp, l) in ent]
+    with Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(quickpol_entry, jobs, chunksize=1)
+        chk = pool.map(quickpol_entry, [(*j[:7], 400) for j in jobs[::6]], chunksize=1)
+    dev = max(abs(r[0] - q[0]) / max(abs(q[0]), 1e-300) for r, q in zip(res[::6], chk))
+    assert dev < 1e-14, dev
+    np.savez_compressed(os.path.join(HERE, "quickpol_entries_mp.npz"), lmax=np.int32(lmax), band=np.int32(band),
+                        cases=np.array(cases, dtype=np.int32), entries=np.array(ent, dtype=np.int32),
+                        xi=np.array([r[0] for r in res]).reshape(len(cases), len(ent)),
+                        sabs=np.array([r[1] for r in res]).reshape(len(cases), len(ent)),
+                        window_sha256=np.array(highl_inputs.digest({"W": ([W],)})))
+    print("quickpol", len(cases), "x", len(ent), "entries; 60 vs 400 digits:", dev, flush=True)
 
 
 if __name__ == "__main__":

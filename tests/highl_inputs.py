@@ -26,6 +26,12 @@ def cov_inputs(lmax):
     return {k: tuple([np.ascontiguousarray(x) for x in part] for part in v) for k, v in blocks.items()}
 
 
+def quickpol_window(lmax):
+    """W_l' of the QuickPol known answers (what quickpolW hands to quickpolXi!, src/beam.jl:43-56): changes sign."""
+    l = np.arange(lmax + 1, dtype=np.float64)
+    return np.ascontiguousarray((np.fmod(l, 5.0) - 1.5) / ((1.0 + l / 200.0) * (1.0 + l / 200.0)))
+
+
 def digest(inputs):
     h = hashlib.sha256()
     for name in sorted(inputs):

@@ -156,3 +156,69 @@ def test_gpu_cov_entries_lmax6143(ps, cov_gold):
         return Cm.parent
     ws, wb = _check_cov(get, g, "gpu")
     print(f"gpu vs 50-digit covariance entries, lmax {lmax}: strict max {ws:.2e}, err/bound max {wb:.3f}")
+
+
+# ---- QuickPol Xi at lmax 6143, band +-128 (quickpol_entries_mp.npz) ----------------------------------------------
+
+@pytest.fixture(scope="module")
+def qp_gold():
+    import highl_inputs
+    g = np.load(os.path.join(GOLDEN, "quickpol_entries_mp.npz"))
+    W = highl_inputs.quickpol_window(int(g["lmax"]))
+    assert highl_inputs.digest({"W": ([W],)}) == str(g["window_sha256"])
+    return g, W
+
+
+def _check_qp(get, g, label):
+    """get(case index) -> callable (l'', l) -> Xi value; every golden entry of every spin case."""
+    worst_strict, worst_bound, nstrict = 0.0, 0.0, 0
+    for c in range(len(g["cases"])):
+        Xi = get(c)
+        for (lpp, l), ref, cond in zip(g["entries"], g["xi"][c], g["sabs"][c]):
+            err = abs(Xi(int(lpp), int(l)) - ref)
+            if cond == 0.0:                                       # projection larger than the angular momentum: exactly 0
+                assert err == 0.0
+                continue
+            worst_bound = max(worst_bound, err / (RTOL * abs(ref) + TAU * cond))
+            if cond <= 1e3 * abs(ref):
+                worst_strict = max(worst_strict, err / abs(ref))
+                nstrict += 1
+    assert worst_bound <= 1.0, (label, worst_bound)
+    assert worst_strict < RTOL, (label, worst_strict)
+    assert nstrict >= 2 * len(g["entries"])
+    return worst_strict, worst_bound
+
+
+@pytest.mark.parametrize("ld", [False, True])
+def test_oracle_quickpol_entries(oracle, qp_gold, ld):
+    """The oracle's general-spin family routine at high l: Xi entries rebuilt from its families (Xisum, src/beam.jl:17-28)."""
+    import math
+    g, W = qp_gold
+
+    def get(c):
+        nu1, nu2, s1, s2 = (int(x) for x in g["cases"][c])
+        sgn = -1.0 if (s1 + s2 + nu1 + nu2) % 2 else 1.0
+
+        def Xi(lpp, l):
+            if abs(s1) > l or abs(s2) > l or abs(nu1) > lpp or abs(nu2) > lpp:
+                return 0.0
+            a1, f1 = oracle.w3j_family(l, lpp, -s1, -nu1, ld=ld)
+            a2, f2 = oracle.w3j_family(l, lpp, -s2, -nu2, ld=ld)
+            lo, hi = max(a1, a2), min(a1 + f1.size - 1, a2 + f2.size - 1, W.size - 1)
+            return sgn * math.fsum(W[lo:hi + 1] * f1[lo - a1:hi - a1 + 1] * f2[lo - a2:hi - a2 + 1])
+        return Xi
+    ws, wb = _check_qp(get, g, f"oracle ld={ld}")
+    print(f"oracle families ld={ld} vs 60-digit QuickPol entries: strict max {ws:.2e}, err/bound max {wb:.4f}")
+
+
+@pytest.mark.gpu
+def test_gpu_quickpol_entries(ps, qp_gold):
+    g, W = qp_gold
+    lmax, band = int(g["lmax"]), int(g["band"])
+
+    def get(c):
+        case = tuple(int(x) for x in g["cases"][c])               # (nu1, nu2, s1, s2)
+        Xi = ps.quickpolXi(ps.BandedSpectralMatrix(lmax, band, band), *case, ps.SpectralVector(W))
+        return lambda lpp, l: Xi[lpp, l]
+    ws, wb = _check_qp(get, g, "gpu")
+    print(f"gpu vs 60-digit QuickPol entries, lmax {lmax}, band +-{band}: strict max {ws:.2e}, err/bound max {wb:.3f}")
