@@ -270,3 +270,21 @@ def test_staged_delivery_argument_errors(ps):
     assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 64, 2, 2, arr, 4) == 1        # ld < N
     assert L.psb200_selftest_delivery(0, 7, 0, 9, 1, 1, 1, 64, 2, 2, arr, 8) == 1        # band beyond the matrix
     assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 64, 40, 2, arr, 8) == 1       # ring too long
+
+
+def test_staged_delivery_random_shapes(ps):
+    """Seeded random bands, sub-band counts, leading dimensions, chunk sizes, ring lengths and worker counts."""
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        lmax = int(rng.integers(30, 400))
+        lmin = int(rng.integers(0, 3))
+        N = lmax - lmin + 1
+        a = int(rng.integers(lmin, lmax))
+        b = int(rng.integers(a + 1, lmax + 2))
+        nsub, nout, pad = int(rng.integers(1, 17)), int(rng.integers(1, 6)), int(rng.integers(0, 5))
+        chunk_kb = int(rng.integers((N * 8 + 1023) // 1024, 120))
+        nch, nthreads = int(rng.integers(1, 33)), int(rng.integers(1, 12))
+        direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, pad=pad)
+        staged = _deliver(ps, lmin, lmax, a, b, nsub, nout, 1, chunk_kb, nch, nthreads, pad=pad)
+        for S, D in zip(staged, direct):
+            assert np.array_equal(S, D, equal_nan=True), (lmin, lmax, a, b, nsub, nout, pad, chunk_kb, nch, nthreads)
