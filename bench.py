@@ -496,6 +496,35 @@ def run_gpu(args, lmax):
             for p in blocks:
                 L.psb200_host_free(p)
 
+        # ---- mirror delivery (PSB200_MIRROR=1, off by default): only the block columns of the results cross PCIe and the
+        # library's host threads write the symmetric side from the same bytes -- bit-identical by construction (the same
+        # IEEE products), half the DMA volume.  Timed in every run next to the standard delivery; e2e is the faster of
+        # the two when, and only when, the matrices are identical. ----
+        mirror = None
+        if not os.environ.get("PSB200_BENCH_NO_MIRROR"):
+            saved = os.environ.get("PSB200_MIRROR")
+            try:                                        # an additional measurement: it must never cost the line
+                os.environ["PSB200_MIRROR"] = "1"
+                host_mr = {name: [torch.empty((N, N), dtype=torch.float64).pin_memory().numpy() for _ in v]
+                           for name, v in outs.items()}
+                host_calls(host_mr, world)
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    host_calls(host_mr, world)
+                wall_mr = (time.perf_counter() - t0) * 1e3
+                same = all(np.array_equal(a, b) for name in host_out for a, b in zip(host_out[name], host_mr[name]))
+                mirror = {"ms_per_step": wall_mr / e2e_steps, "standard_ms_per_step": wall_e2e / e2e_steps,
+                          "equals_standard_delivery": bool(same), "used_for_e2e": bool(same and wall_mr < wall_e2e)}
+                if same and wall_mr < wall_e2e:
+                    wall_e2e = wall_mr
+                del host_mr
+            except Exception as exc:
+                mirror = {"error": repr(exc)}
+            if saved is None:
+                os.environ.pop("PSB200_MIRROR", None)
+            else:
+                os.environ["PSB200_MIRROR"] = saved
+
         # ---- the same calls into PAGEABLE result arrays, which is what the reference allocates (spectralzeros): the
         # library's staged delivery (page-locked ring + scatter threads) beside the CUDA runtime's own bounce copies ----
         pageable = None
@@ -632,8 +661,9 @@ def run_gpu(args, lmax):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e / e2e_steps,
                     "path": f"psb200_mcm / psb200_cov C-ABI host calls with ngpus={world} (pageable inputs, pinned "
-                            "host outputs; every GPU copies its own band of the result to the host)",
-                    "host_arrays": e2e_alloc, "pageable_outputs": pageable,
+                            "host outputs; every GPU copies its own band of the result to the host"
+                            + ("; mirror delivery, PSB200_MIRROR=1: see mirror_delivery)" if mirror and mirror.get("used_for_e2e") else ")"),
+                    "host_arrays": e2e_alloc, "mirror_delivery": mirror, "pageable_outputs": pageable,
                     "per_rank_driver": None if ms_driver is None else {
                         "ms_per_step": ms_driver, "value": terms_step / (ms_driver * 1e-3),
                         "path": "pinned host -> H2D -> band kernels -> NCCL gather -> finish -> D2H on rank 0"}},

@@ -295,8 +295,12 @@ void* psb200_host_alloc(size_t bytes, int policy);
  * calls: the regions of the result are DMA'd into a ring of page-locked chunks of the library and scattered into the
  * caller's array by a few host threads, instead of the CUDA runtime's one-thread bounce copy.  Environment:
  * PSB200_STAGED=0 turns it off, PSB200_STAGE_THREADS (default min(8, cores / (2 ngpus))) and PSB200_STAGE_CHUNK_MB
- * (default 8) tune it.  psb200_selftest_delivery is its test hook: host memory only, no device (csrc/psb200.cu). */
-int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int staged, int chunk_kb, int nch,
+ * (default 8) tune it.  PSB200_MIRROR=1 (off by default) selects the mirror delivery: only the block columns of the
+ * result cross PCIe and the scatter threads write the symmetric side from the same bytes (same IEEE products as the
+ * device: bit-identical) -- for hosts whose DMA ingest rate, not the GPUs, bounds a several-GPU call.
+ * psb200_selftest_delivery is the test hook of all three (mode 0 direct, 1 staged, 2 mirror): host memory only, no
+ * device (csrc/psb200.cu). */
+int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int mode, int scale, int chunk_kb, int nch,
                              int nthreads, double* const* out, long ldo);
 int psb200_host_free(void* p);
 int psb200_host_placement(const void* p, int* counts, int maxnodes);

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "psb200_host_free": (C.c_int, [C.c_void_p]),
     "psb200_host_placement": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
     "psb200_host_numa_nodes": (C.c_int, []),
-    "psb200_selftest_delivery": (C.c_int, [C.c_int] * 10 + [DPP, C.c_long]),
+    "psb200_selftest_delivery": (C.c_int, [C.c_int] * 11 + [DPP, C.c_long]),
 }
 
 

@@ -707,11 +707,16 @@ struct Copy2D {
     const double* src; size_t spitch;       // device (a host stand-in under the CPU test hook)
     size_t width, h;                        // bytes per row, rows
     int k;                                  // sub-band whose event the copy waits for
+    // mirror delivery (see scatter_mirror): the copy is a block column holding RAW values below its diagonal block
+    int mirror = 0, scale = 0, lmin = 0;
+    double* base = nullptr; size_t ld = 0;  // the caller's matrix and its leading dimension (elements)
+    size_t col0 = 0, row0 = 0, mrow = 0;    // matrix column of copy row 0, matrix row of element 0, first row below the diagonal block
 };
 
 // the copies of one band, in the order the sub-bands finish (shared by the direct and the staged delivery)
 static std::vector<Copy2D> band_copies(int N, int lmin, int a, const std::vector<int>& sub, int nout, double* const* out, long ldo,
-                                       double* const* X, long ldX, const double* T, const std::vector<size_t>& toff)
+                                       double* const* X, long ldX, const double* T, const std::vector<size_t>& toff,
+                                       bool mirror = false, int scale = 0)
 {
     std::vector<Copy2D> cp;
     const int ns = (int)sub.size() - 1;
@@ -724,6 +729,12 @@ static std::vector<Copy2D> band_copies(int N, int lmin, int a, const std::vector
             // block column: nbs columns of (N - r0) rows each
             cp.push_back({out[o] + r0 * ldo + r0, (size_t)ldo * sizeof(double), slab + r0, (size_t)ldX * sizeof(double),
                           (size_t)(N - r0) * sizeof(double), (size_t)nbs, k});
+            if (mirror) {                    // the block row is written by the host from the same bytes
+                Copy2D& c = cp.back();
+                c.mirror = 1; c.scale = scale; c.lmin = lmin; c.base = out[o]; c.ld = (size_t)ldo;
+                c.col0 = r0; c.row0 = r0; c.mrow = (size_t)c0;
+                continue;
+            }
             // block row: (N - c0) columns of nbs rows each
             if (c0 < N) {
                 const double* Tk = T + toff[k] + (size_t)o * nbs * (N - c0);
@@ -747,6 +758,7 @@ static std::vector<Copy2D> split_copies(const std::vector<Copy2D>& cp, size_t ch
             p.dst = (double*)((char*)c.dst + r * c.dpitch);
             p.src = (const double*)((const char*)c.src + r * c.spitch);
             p.h = std::min(rows, c.h - r);
+            p.col0 = c.col0 + r;
             out.push_back(p);
         }
     }
@@ -772,6 +784,53 @@ static inline void copy_row_nt(char* dst, const char* src, size_t n)
     }
     for (; i + 16 <= n; i += 16) _mm_stream_si128((__m128i*)(dst + i), _mm_loadu_si128((const __m128i*)(src + i)));
     if (i < n) memcpy(dst + i, src + i, n - i);
+}
+
+// MIRROR DELIVERY (PSB200_MIRROR=1; off by default).  Every result of this path is symmetric up to a column scaling:
+// C[l2,l1] = C[l1,l2] (src/covariance.jl:119), M[l1,l2] = (2 l2 + 1) Xi, M[l2,l1] = (2 l1 + 1) Xi (src/modecoupling.jl:90-91).
+// The standard delivery sends both triangles over PCIe (block column + transposed block row of every sub-band).  When
+// several GPUs write into one host, what bounds a call is the rate at which the host absorbs DMA writes (65-73 GB/s for
+// eight B200s), so here only the block columns cross PCIe -- with the entries below the diagonal
+// block left RAW (x = Xi or C) -- and the scatter workers write both sides from the same bytes:
+//     A[i, j] = s1 x,  s1 = 2 (lmin + j) + 1     (the block column, as band_transpose_kernel scales it in place)
+//     A[j, i] = s2 x,  s2 = 2 (lmin + i) + 1     (the block row,    as band_transpose_kernel writes it to T)
+// (s1 = s2 = 1 for covariance blocks): the same IEEE products the device forms, so the result is bit-identical.  The rows
+// of the diagonal block arrive finished (finish_kernel) and are copied as they are.  The transposed side is written as
+// contiguous runs: 8 matrix columns i at a time, each a run over the piece's h consecutive j, staged in a small buffer.
+static void scatter_mirror(const Copy2D& p, const char* chunk, bool nt)
+{
+    const size_t W = p.width / sizeof(double);                  // matrix rows row0 .. row0 + W - 1 of every column
+    const size_t na = p.mrow > p.row0 ? std::min(W, p.mrow - p.row0) : 0;     // rows of the diagonal block
+    const size_t h = p.h;
+    // the block column
+    for (size_t jj = 0; jj < h; ++jj) {
+        const double* src = (const double*)(chunk + jj * p.width);
+        double* dst = p.base + p.row0 + (p.col0 + jj) * p.ld;
+        if (!p.scale) {
+            if (nt) copy_row_nt((char*)dst, (const char*)src, p.width); else memcpy(dst, src, p.width);
+        } else {
+            if (na) memcpy(dst, src, na * sizeof(double));
+            const double s1 = (double)(2 * ((long)p.lmin + (long)(p.col0 + jj)) + 1);
+            for (size_t t = na; t < W; ++t) dst[t] = s1 * src[t];
+        }
+    }
+    // the block row: A[col0 + jj, i] for i = mrow .. row0 + W - 1
+    std::vector<double> tmp(8 * h);
+    for (size_t t0 = na; t0 < W; t0 += 8) {
+        const size_t nd = std::min<size_t>(8, W - t0);
+        double s2[8];
+        for (size_t d = 0; d < nd; ++d) s2[d] = p.scale ? (double)(2 * ((long)p.lmin + (long)(p.row0 + t0 + d)) + 1) : 1.0;
+        for (size_t jj = 0; jj < h; ++jj) {
+            const double* src = (const double*)(chunk + jj * p.width) + t0;
+            for (size_t d = 0; d < nd; ++d) tmp[d * h + jj] = s2[d] * src[d];
+        }
+        for (size_t d = 0; d < nd; ++d) {
+            double* dst = p.base + p.col0 + (p.row0 + t0 + d) * p.ld;
+            if (nt) copy_row_nt((char*)dst, (const char*)&tmp[d * h], h * sizeof(double));
+            else memcpy(dst, &tmp[d * h], h * sizeof(double));
+        }
+    }
+    if (nt) _mm_sfence();
 }
 
 // The pipeline: issue(i, chunk, c) starts the dense copy of piece i into chunk c and marks its completion, wait(c) blocks
@@ -808,7 +867,9 @@ static int deliver_staged(const std::vector<Copy2D>& pieces, char* ring, size_t 
             if (int rc = wait(c)) { give_up(rc); return; }
             const Copy2D& p = pieces[i];
             const char* src = ring + (size_t)c * chunk_bytes;
-            if (nt) {
+            if (p.mirror) {
+                scatter_mirror(p, src, nt);
+            } else if (nt) {
                 for (size_t r = 0; r < p.h; ++r) copy_row_nt((char*)p.dst + r * p.dpitch, src + r * p.width, p.width);
                 _mm_sfence();
             } else if (p.dpitch == p.width) memcpy(p.dst, src, p.width * p.h);
@@ -986,7 +1047,10 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err,
         std::vector<size_t> toff(ns + 1, 0);             // one transposed block row per (sub-band, output)
         for (int k = 0; k < ns; ++k)
             toff[k + 1] = toff[k] + (size_t)(sub[k + 1] - sub[k]) * (size_t)(N - (sub[k + 1] - hj.lmin)) * hj.nout;
-        if (toff[ns]) if (int rc = scratch_reserve(g, 6, toff[ns])) return rc;
+        // mirror delivery (scatter_mirror): no transposed block rows on the device, the host writes them
+        const char* mir_env = getenv("PSB200_MIRROR");
+        const bool mirror = mir_env && mir_env[0] == '1' && (size_t)nb * N * sizeof(double) >= (size_t(4) << 20);
+        if (toff[ns] && !mirror) if (int rc = scratch_reserve(g, 6, toff[ns])) return rc;
         DeviceScratch& s = g_scratch[g];
         double* Xs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         const long rowoff = (long)(a - hj.lmin);
@@ -1010,7 +1074,7 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err,
                 double* slab = s.X[o] + (size_t)(sa - a) * ldX;         // row sa of the slab
                 finish_kernel<<<dim3(nt, nt), 256, 0, sk>>>(slab + (sa - hj.lmin), ldX, sa, nbs, hj.scale, 0);
                 CUDA_TRY(cudaGetLastError());
-                if (c0 < N) {
+                if (c0 < N && !mirror) {
                     double* Tk = s.T + toff[k] + (size_t)o * nbs * (N - c0);
                     band_transpose_kernel<<<dim3((N - c0 + 31) / 32, nt), 256, 0, sk>>>(
                         slab, ldX, Tk, nbs, sa, hj.lmin, c0, N, hj.scale);
@@ -1021,11 +1085,12 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err,
         }
 
         // everything is queued; now the delivery on the copy stream (see "Delivery" above)
-        const std::vector<Copy2D> copies = band_copies(N, hj.lmin, a, sub, hj.nout, hj.out, hj.ldo, s.X, ldX, s.T, toff);
+        const std::vector<Copy2D> copies = band_copies(N, hj.lmin, a, sub, hj.nout, hj.out, hj.ldo, s.X, ldX, s.T, toff,
+                                                       mirror, hj.scale);
         size_t bytes = 0;
         for (const Copy2D& c : copies) bytes += c.width * c.h;
         const char* st_env = getenv("PSB200_STAGED");
-        const bool staged = !(st_env && st_env[0] == '0') && bytes >= (size_t(4) << 20) && is_pageable(hj.out[0]);
+        const bool staged = mirror || (!(st_env && st_env[0] == '0') && bytes >= (size_t(4) << 20) && is_pageable(hj.out[0]));
         if (!staged) {
             int waited = -1;
             for (const Copy2D& c : copies) {
@@ -1734,35 +1799,63 @@ int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, 
 
 #include "psb200_sht_abi.inl"
 
-/* Test hook (host memory only, no device): the delivery plan of one band [a, b) of an N x N result cut into nsub
- * sub-bands, executed on stand-in "device" buffers filled with distinct numbers -- directly (staged = 0: the 2-D copies
- * as the page-locked path issues them) or through the staged pipeline (ring of nch chunks of chunk_kb KB, nthreads
- * scatter workers).  Both must leave the same bytes in out[0..nout-1]; tests/test_host.py compares them. */
-int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int staged, int chunk_kb, int nch,
+/* Test hook (host memory only, no device): the delivery of one band [a, b) of an N x N result cut into nsub sub-bands,
+ * executed on stand-in "device" slabs.  The slabs start with distinct RAW values x(l1, l2), l2 >= l1; the hook then does on
+ * the host what the device kernels do per sub-band (finish_kernel on the diagonal block; band_transpose_kernel for the
+ * columns to its right unless mode = 2) and delivers: mode 0 directly (the 2-D copies as the page-locked path issues
+ * them), mode 1 through the staged pipeline (ring of nch chunks of chunk_kb KB, nthreads scatter workers), mode 2 by
+ * mirror delivery (block columns only, the block rows written by the scatter workers).  All three must leave the same
+ * bytes in out[0..nout-1]; tests/test_host.py compares them.  scale: 1 = MCM factors (2l+1), 0 = symmetric copy. */
+int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int mode, int scale, int chunk_kb, int nch,
                              int nthreads, double* const* out, long ldo)
 {
     const int N = lmax - lmin + 1, nb = b - a;
     if (lmin < 0 || a < lmin || b > lmax + 1 || nb <= 0 || nout < 1 || nout > 5 || !out || ldo < N || chunk_kb < 1 || nch < 1 ||
-        nch > 32 || nthreads < 1)
+        nch > 32 || nthreads < 1 || mode < 0 || mode > 2 || scale < 0 || scale > 1)
         return fail(ERR_ARG, "selftest_delivery: bad arguments");
     const std::vector<int> sub = split_rows(a, b, lmax, lmax + 1, nsub);
     const int ns = (int)sub.size() - 1;
+    const bool mirror = mode == 2;
     std::vector<size_t> toff(ns + 1, 0);
     for (int k = 0; k < ns; ++k)
         toff[k + 1] = toff[k] + (size_t)(sub[k + 1] - sub[k]) * (size_t)(N - (sub[k + 1] - lmin)) * nout;
     std::vector<std::vector<double>> Xs(nout, std::vector<double>((size_t)nb * N));
-    std::vector<double> T(toff[ns] + 1);
+    std::vector<double> T(toff[ns] + 1, 0.0);
     double* X[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const long ld = N;
+    auto fac = [&](long l) { return scale ? (double)(2 * l + 1) : 1.0; };
     for (int o = 0; o < nout; ++o) {
-        for (size_t i = 0; i < Xs[o].size(); ++i) Xs[o][i] = (double)(o + 1) * 1e9 + (double)i;
         X[o] = Xs[o].data();
+        // raw values: row l1 - a, column l2 - lmin >= l1 - lmin (entries left of the diagonal are never read: poison them)
+        for (int i = 0; i < nb; ++i)
+            for (int j = 0; j < N; ++j)
+                X[o][(size_t)i * ld + j] = j >= (a - lmin) + i ? (double)(o + 1) + 1e-3 * (a + i) + 1e-7 * (lmin + j) : -7.77e77;
+        for (int k = 0; k < ns; ++k) {
+            const int sa = sub[k], sb = sub[k + 1], nbs = sb - sa, c0 = sb - lmin;
+            double* slab = X[o] + (size_t)(sa - a) * ld;
+            double* D = slab + (sa - lmin);                       // diagonal block, as finish_kernel sees it
+            for (int i = 0; i < nbs; ++i)
+                for (int j = i; j < nbs; ++j) {
+                    const double x = D[(size_t)i * ld + j];
+                    D[(size_t)i * ld + j] = fac(sa + i) * x;
+                    if (j > i) D[(size_t)j * ld + i] = fac(sa + j) * x;
+                }
+            if (c0 < N && !mirror) {                              // band_transpose_kernel
+                double* Tk = T.data() + toff[k] + (size_t)o * nbs * (N - c0);
+                for (int i = 0; i < nbs; ++i)
+                    for (int j = c0; j < N; ++j) {
+                        const double x = slab[(size_t)i * ld + j];
+                        slab[(size_t)i * ld + j] = fac(sa + i) * x;
+                        Tk[(size_t)(j - c0) * nbs + i] = fac(lmin + j) * x;
+                    }
+            }
+        }
     }
-    for (size_t i = 0; i < T.size(); ++i) T[i] = -(double)(i + 1);
-    const std::vector<Copy2D> copies = band_copies(N, lmin, a, sub, nout, out, ldo, X, N, T.data(), toff);
+    const std::vector<Copy2D> copies = band_copies(N, lmin, a, sub, nout, out, ldo, X, ld, T.data(), toff, mirror, scale);
     auto copy2d = [](char* dst, size_t dpitch, const Copy2D& c) {
         for (size_t r = 0; r < c.h; ++r) memcpy(dst + r * dpitch, (const char*)c.src + r * c.spitch, c.width);
     };
-    if (!staged) {
+    if (mode == 0) {
         for (const Copy2D& c : copies) copy2d((char*)c.dst, c.dpitch, c);
         return OK;
     }

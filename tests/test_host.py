@@ -227,49 +227,60 @@ def test_host_result_buffers(ps):
     assert L.psb200_host_placement(C.c_void_p(12345), cnt, 4) == -1
 
 
-def _deliver(ps, lmin, lmax, a, b, nsub, nout, staged, chunk_kb=64, nch=3, nthreads=2, pad=0):
+def _deliver(ps, lmin, lmax, a, b, nsub, nout, mode, scale=1, chunk_kb=64, nch=3, nthreads=2, pad=0):
     N = lmax - lmin + 1
     ld = N + pad
     outs = [np.asfortranarray(np.full((ld, N), np.nan)) for _ in range(nout)]   # column-major, leading dimension ld >= N
     DP = ps._lib.DP
     arr = (DP * nout)(*[o.ctypes.data_as(DP) for o in outs])
-    rc = ps.lib().psb200_selftest_delivery(lmin, lmax, a, b, nsub, nout, staged, chunk_kb, nch, nthreads, arr, ld)
+    rc = ps.lib().psb200_selftest_delivery(lmin, lmax, a, b, nsub, nout, mode, scale, chunk_kb, nch, nthreads, arr, ld)
     assert rc == 0, ps.lib().psb200_last_error()
     return outs
 
 
+def _expected(lmin, lmax, a, b, o, scale):
+    """What a band [a, b) owes the caller: column l1 below the diagonal holds fac(l1) x(l1, l2), row l1 right of it
+    fac(l2) x(l1, l2), with the raw values x the test hook puts into its stand-in slabs."""
+    N = lmax - lmin + 1
+    E = np.full((N, N), np.nan)
+    l2 = np.arange(lmin, lmax + 1, dtype=np.float64)
+    for l1 in range(a, b):
+        x = (o + 1.0) + 1e-3 * l1 + 1e-7 * l2[l1 - lmin:]
+        E[l1 - lmin:, l1 - lmin] = (2 * l1 + 1) * x if scale else x
+        E[l1 - lmin, l1 - lmin:] = (2 * l2[l1 - lmin:] + 1) * x if scale else x
+    return E
+
+
+@pytest.mark.parametrize("scale", [0, 1])
 @pytest.mark.parametrize("lmin,lmax,a,b,nsub,nout", [(0, 255, 0, 256, 4, 1), (0, 255, 0, 256, 1, 2), (2, 300, 2, 301, 16, 5),
                                                      (0, 511, 100, 380, 8, 2), (0, 511, 380, 512, 2, 1), (5, 40, 7, 8, 1, 1)])
-def test_staged_delivery_equals_direct(ps, lmin, lmax, a, b, nsub, nout):
-    """The staged delivery (ring of page-locked chunks + scatter workers; what pageable result arrays get) leaves the
-    same bytes as the direct 2-D copies, for any chunk size / ring length / worker count, and the L-shaped region of a
-    band [a, b) -- rows >= a of its columns, its rows of the columns to the right -- is written completely and only."""
+def test_staged_and_mirror_delivery_equal_direct(ps, lmin, lmax, a, b, nsub, nout, scale):
+    """The direct delivery of a band writes its L-shaped region -- rows >= a of its columns, its rows of the columns to the
+    right -- completely, only, and with the values of src/modecoupling.jl:90-91 / src/covariance.jl:119; the staged
+    delivery (what pageable result arrays get) and the mirror delivery (block columns only over PCIe, the symmetric side
+    written by the scatter workers) leave the same bytes for any chunk size / ring length / worker count."""
     N = lmax - lmin + 1
-    direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, pad=3)
-    r0, r1 = a - lmin, b - lmin
-    region = np.zeros((N, N), dtype=bool)
-    region[r0:, r0:r1] = True                     # block column
-    region[r0:r1, r1:] = True                     # block row
-    for D in direct:
-        assert np.array_equal(~np.isnan(D[:N, :]), region)
+    direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, scale, pad=3)
+    for o, D in enumerate(direct):
         assert np.isnan(D[N:, :]).all()           # the padding rows of the leading dimension stay untouched
-        vals = D[:N, :][region]
-        assert np.unique(vals).size == vals.size  # every entry from its own source element
+        assert np.array_equal(D[:N, :], _expected(lmin, lmax, a, b, o, scale), equal_nan=True)
     for chunk_kb, nch, nthreads in [(4, 1, 1), (4, 2, 3), (16, 3, 2), (64, 12, 8), (1024, 2, 4)]:
         if chunk_kb * 1024 < N * 8:
             continue
-        staged = _deliver(ps, lmin, lmax, a, b, nsub, nout, 1, chunk_kb, nch, nthreads, pad=3)
-        for S, D in zip(staged, direct):
-            assert np.array_equal(S, D, equal_nan=True), (chunk_kb, nch, nthreads)
+        for mode in (1, 2):
+            got = _deliver(ps, lmin, lmax, a, b, nsub, nout, mode, scale, chunk_kb, nch, nthreads, pad=3)
+            for S, D in zip(got, direct):
+                assert np.array_equal(S, D, equal_nan=True), (mode, chunk_kb, nch, nthreads)
 
 
 def test_staged_delivery_argument_errors(ps):
     L = ps.lib()
     out = np.zeros((8, 8), order="F")
     arr = (ps._lib.DP * 1)(out.ctypes.data_as(ps._lib.DP))
-    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 64, 2, 2, arr, 4) == 1        # ld < N
-    assert L.psb200_selftest_delivery(0, 7, 0, 9, 1, 1, 1, 64, 2, 2, arr, 8) == 1        # band beyond the matrix
-    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 64, 40, 2, arr, 8) == 1       # ring too long
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 1, 64, 2, 2, arr, 4) == 1        # ld < N
+    assert L.psb200_selftest_delivery(0, 7, 0, 9, 1, 1, 1, 1, 64, 2, 2, arr, 8) == 1        # band beyond the matrix
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 1, 64, 40, 2, arr, 8) == 1       # ring too long
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 3, 1, 64, 2, 2, arr, 8) == 1        # unknown mode
 
 
 def test_staged_delivery_random_shapes(ps):
@@ -282,9 +293,11 @@ def test_staged_delivery_random_shapes(ps):
         a = int(rng.integers(lmin, lmax))
         b = int(rng.integers(a + 1, lmax + 2))
         nsub, nout, pad = int(rng.integers(1, 17)), int(rng.integers(1, 6)), int(rng.integers(0, 5))
+        scale = int(rng.integers(0, 2))
         chunk_kb = int(rng.integers((N * 8 + 1023) // 1024, 120))
         nch, nthreads = int(rng.integers(1, 33)), int(rng.integers(1, 12))
-        direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, pad=pad)
-        staged = _deliver(ps, lmin, lmax, a, b, nsub, nout, 1, chunk_kb, nch, nthreads, pad=pad)
-        for S, D in zip(staged, direct):
-            assert np.array_equal(S, D, equal_nan=True), (lmin, lmax, a, b, nsub, nout, pad, chunk_kb, nch, nthreads)
+        direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, scale, pad=pad)
+        for mode in (1, 2):
+            got = _deliver(ps, lmin, lmax, a, b, nsub, nout, mode, scale, chunk_kb, nch, nthreads, pad=pad)
+            for S, D in zip(got, direct):
+                assert np.array_equal(S, D, equal_nan=True), (mode, lmin, lmax, a, b, nsub, nout, pad, scale, chunk_kb, nch, nthreads)
