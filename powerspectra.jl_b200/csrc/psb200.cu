@@ -709,6 +709,7 @@ struct Copy2D {
     int k;                                  // sub-band whose event the copy waits for
     // mirror delivery (see scatter_mirror): the copy is a block column holding RAW values below its diagonal block
     int mirror = 0, scale = 0, lmin = 0;
+    int direct = 0;                         // mirror delivery of a symmetric copy into a page-locked array: DMA straight to dst
     double* base = nullptr; size_t ld = 0;  // the caller's matrix and its leading dimension (elements)
     size_t col0 = 0, row0 = 0, mrow = 0;    // matrix column of copy row 0, matrix row of element 0, first row below the diagonal block
 };
@@ -797,13 +798,17 @@ static inline void copy_row_nt(char* dst, const char* src, size_t n)
 // (s1 = s2 = 1 for covariance blocks): the same IEEE products the device forms, so the result is bit-identical.  The rows
 // of the diagonal block arrive finished (finish_kernel) and are copied as they are.  The transposed side is written as
 // contiguous runs: 8 matrix columns i at a time, each a run over the piece's h consecutive j, staged in a small buffer.
+// For covariance blocks (no scaling) going into a PAGE-LOCKED array the block column needs no host thread at all: it is
+// DMA'd straight to its place (p.direct) and the workers read it back from there for the symmetric side only.
 static void scatter_mirror(const Copy2D& p, const char* chunk, bool nt)
 {
     const size_t W = p.width / sizeof(double);                  // matrix rows row0 .. row0 + W - 1 of every column
     const size_t na = p.mrow > p.row0 ? std::min(W, p.mrow - p.row0) : 0;     // rows of the diagonal block
     const size_t h = p.h;
+    const size_t pitch = p.direct ? p.dpitch : p.width;         // bytes between consecutive matrix columns of the source
+    if (p.direct) chunk = (const char*)p.dst;
     // the block column
-    for (size_t jj = 0; jj < h; ++jj) {
+    for (size_t jj = 0; jj < h && !p.direct; ++jj) {
         const double* src = (const double*)(chunk + jj * p.width);
         double* dst = p.base + p.row0 + (p.col0 + jj) * p.ld;
         if (!p.scale) {
@@ -814,20 +819,32 @@ static void scatter_mirror(const Copy2D& p, const char* chunk, bool nt)
             for (size_t t = na; t < W; ++t) dst[t] = s1 * src[t];
         }
     }
-    // the block row: A[col0 + jj, i] for i = mrow .. row0 + W - 1
-    std::vector<double> tmp(8 * h);
-    for (size_t t0 = na; t0 < W; t0 += 8) {
-        const size_t nd = std::min<size_t>(8, W - t0);
-        double s2[8];
-        for (size_t d = 0; d < nd; ++d) s2[d] = p.scale ? (double)(2 * ((long)p.lmin + (long)(p.row0 + t0 + d)) + 1) : 1.0;
-        for (size_t jj = 0; jj < h; ++jj) {
-            const double* src = (const double*)(chunk + jj * p.width) + t0;
-            for (size_t d = 0; d < nd; ++d) tmp[d * h + jj] = s2[d] * src[d];
-        }
-        for (size_t d = 0; d < nd; ++d) {
-            double* dst = p.base + p.col0 + (p.row0 + t0 + d) * p.ld;
-            if (nt) copy_row_nt((char*)dst, (const char*)&tmp[d * h], h * sizeof(double));
-            else memcpy(dst, &tmp[d * h], h * sizeof(double));
+    // the block row: A[col0 + jj, i] for i = mrow .. row0 + W - 1.  Tiles of TI matrix columns i x TJ rows jj through a
+    // 64 KB buffer: the source is read as TI consecutive doubles per jj (the lines of the next jj are prefetched: at a
+    // stride of W doubles the hardware prefetchers see nothing), the destination is written as TI runs of TJ doubles.
+    // MEASURED (host microbenchmark, one thread, 8 MB piece): 1.5 GB/s with buffer rows exactly TJ doubles apart (2 KB: the
+    // TI store streams of the gather fall into two L1 sets), 4.8 GB/s with the rows 8 doubles further apart; block column 8-11 GB/s
+    constexpr size_t TI = 32, TJ = 256, TS = TJ + 8;
+    double tmp[TI * TS];
+    for (size_t j0 = 0; j0 < h; j0 += TJ) {
+        const size_t nj = std::min(TJ, h - j0);
+        for (size_t t0 = na; t0 < W; t0 += TI) {
+            const size_t nd = std::min(TI, W - t0);
+            double s2[TI];
+            for (size_t d = 0; d < nd; ++d) s2[d] = p.scale ? (double)(2 * ((long)p.lmin + (long)(p.row0 + t0 + d)) + 1) : 1.0;
+            for (size_t jj = 0; jj < nj; ++jj) {
+                const double* src = (const double*)(chunk + (j0 + jj) * pitch) + t0;
+                if (jj + 1 < nj) {
+                    const char* nx = (const char*)src + pitch;
+                    for (size_t b = 0; b < nd * sizeof(double); b += 64) _mm_prefetch(nx + b, _MM_HINT_T0);
+                }
+                for (size_t d = 0; d < nd; ++d) tmp[d * TS + jj] = s2[d] * src[d];
+            }
+            for (size_t d = 0; d < nd; ++d) {
+                double* dst = p.base + (p.col0 + j0) + (p.row0 + t0 + d) * p.ld;
+                if (nt) copy_row_nt((char*)dst, (const char*)&tmp[d * TS], nj * sizeof(double));
+                else memcpy(dst, &tmp[d * TS], nj * sizeof(double));
+            }
         }
     }
     if (nt) _mm_sfence();
@@ -910,12 +927,13 @@ static size_t stage_chunk_bytes()
     return mb << 20;
 }
 
-static int stage_threads(int ngpus_in_call)
+static int stage_threads(int ngpus_in_call, bool mirror = false)
 {
     if (const char* e = getenv("PSB200_STAGE_THREADS")) return std::max(1, std::min(28, atoi(e)));
     const int hw = (int)std::thread::hardware_concurrency();
     // MEASURED (1 B200, 16 host threads, lmax 6143, ms per call; page-locked destination 7.0 / 22.3, CUDA runtime's bounce
     // copies 33.3 / 70.0 for TT / fused EE-BB): 2 workers 36.9 / 75.3, 4: 20.2 / 38.0, 8: 13.4 / 27.9, 12: 11.8 / 24.5
+    if (mirror) return std::max(2, std::min(12, hw / std::max(1, ngpus_in_call)));   // the workers do the transposing: every core
     return std::max(2, std::min(12, 3 * hw / (4 * std::max(1, ngpus_in_call))));
 }
 
@@ -1099,13 +1117,18 @@ int run_band_on_device(const HostJob& hj, int g, int a, int b, std::string* err,
             }
         } else {
             const size_t chunk = stage_chunk_bytes();
-            const int nthr = stage_threads(ngpus_in_call), nch = std::min(32, nthr + 4);   // chunks: one per worker + 4 in flight
+            const int nthr = stage_threads(ngpus_in_call, mirror), nch = std::min(32, nthr + 4);   // chunks: one per worker + 4 in flight
             if (int rc = stage_ring_reserve(g, chunk, nch)) return rc;
-            const std::vector<Copy2D> pieces = split_copies(copies, chunk);
+            std::vector<Copy2D> pieces = split_copies(copies, chunk);
+            if (mirror && hj.scale == 0 && !is_pageable(hj.out[0]))
+                for (Copy2D& p : pieces) p.direct = 1;
             int waited = -1;
             auto issue = [&](int i, char* dst, int c) -> int {
                 const Copy2D& p = pieces[i];
                 if (p.k != waited) { CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.ev[p.k], 0)); waited = p.k; }
+                if (p.direct)
+                    CUDA_TRY(cudaMemcpy2DAsync(p.dst, p.dpitch, p.src, p.spitch, p.width, p.h, cudaMemcpyDeviceToHost, s.copy_stream));
+                else
                 CUDA_TRY(cudaMemcpy2DAsync(dst, p.width, p.src, p.spitch, p.width, p.h, cudaMemcpyDeviceToHost, s.copy_stream));
                 CUDA_TRY(cudaEventRecord(s.ring_ev[c], s.copy_stream));
                 return OK;
@@ -1804,18 +1827,19 @@ int psb200_zonal_alm(int nfields, int nnodes, const double* x, const double* w, 
  * the host what the device kernels do per sub-band (finish_kernel on the diagonal block; band_transpose_kernel for the
  * columns to its right unless mode = 2) and delivers: mode 0 directly (the 2-D copies as the page-locked path issues
  * them), mode 1 through the staged pipeline (ring of nch chunks of chunk_kb KB, nthreads scatter workers), mode 2 by
- * mirror delivery (block columns only, the block rows written by the scatter workers).  All three must leave the same
- * bytes in out[0..nout-1]; tests/test_host.py compares them.  scale: 1 = MCM factors (2l+1), 0 = symmetric copy. */
+ * mirror delivery (block columns only, the block rows written by the scatter workers), mode 3 by mirror delivery with the
+ * block columns copied straight to their place (scale 0 only: what a page-locked array gets for a covariance block).  All
+ * must leave the same bytes in out[0..nout-1]; tests/test_host.py compares them.  scale: 1 = MCM factors (2l+1), 0 = symmetric copy. */
 int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nout, int mode, int scale, int chunk_kb, int nch,
                              int nthreads, double* const* out, long ldo)
 {
     const int N = lmax - lmin + 1, nb = b - a;
     if (lmin < 0 || a < lmin || b > lmax + 1 || nb <= 0 || nout < 1 || nout > 5 || !out || ldo < N || chunk_kb < 1 || nch < 1 ||
-        nch > 32 || nthreads < 1 || mode < 0 || mode > 2 || scale < 0 || scale > 1)
+        nch > 32 || nthreads < 1 || mode < 0 || mode > 3 || scale < 0 || scale > 1 || (mode == 3 && scale != 0))
         return fail(ERR_ARG, "selftest_delivery: bad arguments");
     const std::vector<int> sub = split_rows(a, b, lmax, lmax + 1, nsub);
     const int ns = (int)sub.size() - 1;
-    const bool mirror = mode == 2;
+    const bool mirror = mode >= 2;
     std::vector<size_t> toff(ns + 1, 0);
     for (int k = 0; k < ns; ++k)
         toff[k + 1] = toff[k] + (size_t)(sub[k + 1] - sub[k]) * (size_t)(N - (sub[k + 1] - lmin)) * nout;
@@ -1862,11 +1886,22 @@ int psb200_selftest_delivery(int lmin, int lmax, int a, int b, int nsub, int nou
     const size_t chunk = (size_t)chunk_kb << 10;
     for (const Copy2D& c : copies)
         if (c.width > chunk) return fail(ERR_ARG, "selftest_delivery: a row of %zu bytes does not fit a chunk", c.width);
-    const std::vector<Copy2D> pieces = split_copies(copies, chunk);
+    std::vector<Copy2D> pieces = split_copies(copies, chunk);
+    if (mode == 3)
+        for (Copy2D& p : pieces) p.direct = 1;
     std::vector<char> ring(chunk * (size_t)nch);
-    auto issue = [&](int i, char* dst, int) -> int { copy2d(dst, pieces[i].width, pieces[i]); return OK; };
+    auto issue = [&](int i, char* dst, int) -> int {
+        if (pieces[i].direct) copy2d((char*)pieces[i].dst, pieces[i].dpitch, pieces[i]);
+        else copy2d(dst, pieces[i].width, pieces[i]);
+        return OK;
+    };
     auto wait = [](int) -> int { return OK; };
-    return deliver_staged(pieces, ring.data(), chunk, nch, nthreads, issue, wait);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = deliver_staged(pieces, ring.data(), chunk, nch, nthreads, issue, wait);
+    if (trace_level() >= 1)
+        fprintf(stderr, "[psb200] selftest delivery mode %d, %d workers: %.3f ms\n", mode, nthreads,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return rc;
 }
 
 double psb200_dfma_peak(int iters)

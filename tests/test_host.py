@@ -267,7 +267,7 @@ def test_staged_and_mirror_delivery_equal_direct(ps, lmin, lmax, a, b, nsub, nou
     for chunk_kb, nch, nthreads in [(4, 1, 1), (4, 2, 3), (16, 3, 2), (64, 12, 8), (1024, 2, 4)]:
         if chunk_kb * 1024 < N * 8:
             continue
-        for mode in (1, 2):
+        for mode in (1, 2) + ((3,) if scale == 0 else ()):
             got = _deliver(ps, lmin, lmax, a, b, nsub, nout, mode, scale, chunk_kb, nch, nthreads, pad=3)
             for S, D in zip(got, direct):
                 assert np.array_equal(S, D, equal_nan=True), (mode, chunk_kb, nch, nthreads)
@@ -280,7 +280,8 @@ def test_staged_delivery_argument_errors(ps):
     assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 1, 64, 2, 2, arr, 4) == 1        # ld < N
     assert L.psb200_selftest_delivery(0, 7, 0, 9, 1, 1, 1, 1, 64, 2, 2, arr, 8) == 1        # band beyond the matrix
     assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 1, 1, 64, 40, 2, arr, 8) == 1       # ring too long
-    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 3, 1, 64, 2, 2, arr, 8) == 1        # unknown mode
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 4, 1, 64, 2, 2, arr, 8) == 1        # unknown mode
+    assert L.psb200_selftest_delivery(0, 7, 0, 8, 1, 1, 3, 1, 64, 2, 2, arr, 8) == 1        # direct mirror is for symmetric copies
 
 
 def test_staged_delivery_random_shapes(ps):
@@ -297,7 +298,7 @@ def test_staged_delivery_random_shapes(ps):
         chunk_kb = int(rng.integers((N * 8 + 1023) // 1024, 120))
         nch, nthreads = int(rng.integers(1, 33)), int(rng.integers(1, 12))
         direct = _deliver(ps, lmin, lmax, a, b, nsub, nout, 0, scale, pad=pad)
-        for mode in (1, 2):
+        for mode in (1, 2) + ((3,) if scale == 0 else ()):
             got = _deliver(ps, lmin, lmax, a, b, nsub, nout, mode, scale, chunk_kb, nch, nthreads, pad=pad)
             for S, D in zip(got, direct):
                 assert np.array_equal(S, D, equal_nan=True), (mode, lmin, lmax, a, b, nsub, nout, pad, scale, chunk_kb, nch, nthreads)
