@@ -23,7 +23,12 @@ What the JSON line carries besides the contract keys:
                      possible because the kernel executes fewer and cheaper terms than declared
   multi_gpu_check    the N-GPU host call, the 1-GPU host call and the NCCL-gather driver compared bit for bit
   parity             strict north-star statistics of sampled rows against the CPU oracle (Float64 and long double)
-  extra              fused master call, TE at lmax 3071, QuickPol, the lmax 12287 sweep point
+  known_answers      the TT matrix of the e2e host call against 50-digit entries (tests/golden/mcm_entries_mp.npz)
+  e2e.pageable_outputs   the same step into pageable result arrays: the library's staged delivery and the CUDA runtime's own
+  e2e.host_arrays    several GPUs on a multi-node host: one-node against NUMA-interleaved page-locked result arrays
+  e2e.mirror_delivery    several GPUs: the step with PSB200_MIRROR=1 (half the DMA volume), measured in a subprocess
+  extra              fused master call, TE at lmax 3071, QuickPol, the lmax 12287 sweep point, device-side decoupling,
+                     W-spectrum production
 """
 from __future__ import annotations
 
