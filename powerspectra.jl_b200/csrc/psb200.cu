@@ -816,7 +816,16 @@ static void scatter_mirror(const Copy2D& p, const char* chunk, bool nt)
         } else {
             if (na) memcpy(dst, src, na * sizeof(double));
             const double s1 = (double)(2 * ((long)p.lmin + (long)(p.col0 + jj)) + 1);
-            for (size_t t = na; t < W; ++t) dst[t] = s1 * src[t];
+            if (!nt) {
+                for (size_t t = na; t < W; ++t) dst[t] = s1 * src[t];
+            } else {                              // scaled through a small buffer so that the stores can stream
+                double buf[512];
+                for (size_t t = na; t < W; t += 512) {
+                    const size_t n = std::min<size_t>(512, W - t);
+                    for (size_t u = 0; u < n; ++u) buf[u] = s1 * src[t + u];
+                    copy_row_nt((char*)(dst + t), (const char*)buf, n * sizeof(double));
+                }
+            }
         }
     }
     // the block row: A[col0 + jj, i] for i = mrow .. row0 + W - 1.  Tiles of TI matrix columns i x TJ rows jj through a
