@@ -522,8 +522,12 @@ def run_gpu(args, lmax):
                 mirror["in_process_standard_ms_per_step"] = wall_e2e / e2e_steps
                 mirror["used_for_e2e"] = bool(mirror["equals_standard_delivery"]
                                               and mirror["mirror_ms_per_step"] < min(mirror["standard_ms_per_step"], wall_e2e / e2e_steps))
+                # what crosses PCIe with the mirror delivery: the block columns (lower triangles + the diagonal blocks of
+                # the sub-bands, counted here as N (N + 1) / 2 entries per matrix)
+                mirror["d2h_bytes_per_step"] = int(sum(len(v) for v in outs.values()) * (N * (N + 1) // 2) * 8)
                 if mirror["used_for_e2e"]:
                     wall_e2e = mirror["mirror_ms_per_step"] * e2e_steps
+                    d2h_bytes = mirror["d2h_bytes_per_step"]
             except Exception as exc:
                 mirror = {"error": repr(exc)}
 
