@@ -19,12 +19,12 @@ from .modecoupling import (Alm, alm2cl, inner_mcm00, inner_mcm02, inner_mcmmm, i
                            inner_mcmpp_mcmmm, maskedalm2spectra, maskedalm2spectra_device, mcm,
                            mcm_master, mcm_solve)
 from .spectral import (BlockSpectralMatrix, SpectralArray, SpectralVector, decouple_covmat, decouple_covmat_device,
-                       spectralones,
-                       spectralzeros)
+                       free_pinned, pinned_spectralzeros, spectralones, spectralzeros)
 
 __all__ = [
     "mcm", "mcm_master", "mcm_solve", "maskedalm2spectra", "maskedalm2spectra_device", "decouple_covmat_device", "coupledcov", "CovarianceWorkspace", "window_function_W", "ConstantDict",
     "SpectralArray", "SpectralVector", "BlockSpectralMatrix", "spectralzeros", "spectralones",
     "decouple_covmat", "BandedSpectralMatrix", "quickpolXi", "quickpolW", "k_u", "Alm", "alm2cl", "HealpixMap", "PolarizedHealpixMap", "CovField", "map2alm", "alm2map", "alm2cl_device",
     "effective_weight_alm", "precompute_effective_weights", "weights_needed", "nside2lmax", "nside2npix", "lib", "LIB_PATH", "PSB200Error",
+    "pinned_spectralzeros", "free_pinned",
 ]

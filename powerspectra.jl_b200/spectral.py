@@ -139,6 +139,31 @@ def spectralzeros(*ranges):
     return SpectralArray(np.zeros(shape, order="F"), offs)
 
 
+_PINNED = {}          # address of the first element -> the library block that owns the memory
+
+
+def pinned_spectralzeros(r, interleave=False):
+    """A zero N x N SpectralArray over the multipoles of `r` (a range or a size) in page-locked memory of the library
+    (psb200_host_alloc; `pinned_spectralzeros` of julia/PowerSpectraB200.jl): the result of a host call lands in it at the
+    full PCIe rate.  `interleave=True` spreads it over the NUMA nodes of the host (calls on several GPUs).  Pass it to
+    the in-place functions (inner_mcm00, loop_covTTTT, ...); release it with `free_pinned` -- the memory is not
+    garbage collected, and the array must not be touched afterwards."""
+    from ._lib import HostMatrix
+    lo, n = _rng(r)
+    H = HostMatrix(n, interleave)
+    A = SpectralArray(H.array, (lo, lo))
+    _PINNED[A.parent.ctypes.data] = H
+    return A
+
+
+def free_pinned(A):
+    H = _PINNED.pop(A.parent.ctypes.data, None)
+    if H is None:
+        raise ValueError("not a pinned_spectralzeros array")
+    A.parent = None
+    H.free()
+
+
 def spectralones(*ranges):
     offs, shape = zip(*[_rng(r) for r in ranges])
     return SpectralArray(np.ones(shape, order="F"), offs)

@@ -223,6 +223,13 @@ def test_host_result_buffers(ps):
         H.free()
         assert L.psb200_host_free(p) == 1                          # already released
     assert L.psb200_host_free(None) == 0
+    A = ps.pinned_spectralzeros(range(2, 302), interleave=True)       # the mirror of the shim's pinned_spectralzeros
+    assert A.axes(0) == range(2, 302) and A.parent.flags.f_contiguous and not A.parent.any()
+    A[5, 7] = 1.25
+    assert A.parent[3, 5] == 1.25
+    ps.free_pinned(A)
+    with pytest.raises(ValueError):
+        ps.free_pinned(ps.spectralzeros(4, 4))
     cnt = (C.c_int * 4)()
     assert L.psb200_host_placement(C.c_void_p(12345), cnt, 4) == -1
 
